@@ -1,0 +1,260 @@
+// All-pairs RDF kernel for sm_100a: persistent CTAs, TMA-staged column tiles, block-private
+// shared-memory histograms, exact float32 arithmetic.
+//
+// Replaces, fused into one kernel, the reference's K1-K9 TensorFlow ops:
+//   get_partial_triu_indices   mdsuite/utils/linalg.py:102-122      -> the (row, col) tile schedule
+//   get_dij                    calculators/radial_distribution_function.py:647-689
+//   apply_minimum_image        mdsuite/utils/linalg.py:84-99
+//   bin_minibatch              calculators/radial_distribution_function.py:616-645
+//   apply_system_cutoff        mdsuite/utils/linalg.py:125-136
+//   tf.histogram_fixed_width   calculators/radial_distribution_function.py:642-644
+//   combine_dictionaries       calculators/radial_distribution_function.py:601-614, :884-885
+//
+// Layout: one work item = (frame, species pair, row tile of THREADS*R atoms, column range).
+// Each thread keeps R row atoms in registers and walks the column range through a
+// double-buffered shared-memory tile that one elected thread fills with cp.async.bulk (TMA 1-D)
+// and an mbarrier; every column atom is one broadcast LDS.128 for R pair evaluations.
+// In-cutoff pairs are binned against the squared-distance threshold table and counted with a
+// shared-memory atomic; the CTA's histogram is merged into the global uint64 counts once, at
+// the end (or before 2^31 increments could overflow a 32-bit bin).
+#include "rdf_common.cuh"
+#include "rdf_launch.h"
+
+namespace mds {
+
+constexpr int TJ = 512;  // column atoms per shared-memory tile (8 KB per stage)
+
+template <int R, bool FAST, bool DIAG, bool HIST_SMEM, bool DENSE>
+__device__ __forceinline__ void pair_tile(const float4* __restrict__ jt, int cnt, int jbase,
+                                          const float (&xi)[R], const float (&yi)[R],
+                                          const float (&zi)[R], const int (&ig)[R], float bx,
+                                          float by, float bz, float s_cut, float inv_step,
+                                          uint32_t c_edge, uint32_t d_hist,
+                                          const float* __restrict__ edges_g,
+                                          unsigned long long* hist_g) {
+#pragma unroll 2
+  for (int jj = 0; jj < cnt; ++jj) {
+    const float4 pj = jt[jj];
+    float s[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float dx = __fsub_rn(pj.x, xi[r]);
+      const float dy = __fsub_rn(pj.y, yi[r]);
+      const float dz = __fsub_rn(pj.z, zi[r]);
+      float mx, my, mz;
+      if (FAST) {
+        mx = minimg_fast(dx, bx);
+        my = minimg_fast(dy, by);
+        mz = minimg_fast(dz, bz);
+      } else {
+        mx = minimg_general(dx, bx);
+        my = minimg_general(dy, by);
+        mz = minimg_general(dz, bz);
+      }
+      s[r] = sq_norm(mx, my, mz);
+    }
+    const int jg = jbase + jj;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (HIST_SMEM && DENSE) {
+        bin_count_dense<DIAG>(s[r], s_cut, inv_step, c_edge, d_hist, jg, ig[r]);
+      } else {
+        bool in = s[r] < s_cut;  // false for NaN (padding rows, NaN input)
+        if (DIAG) in = in && (jg > ig[r]);
+        if (in) {
+          if (HIST_SMEM) {
+            bin_count(s[r], inv_step, c_edge, d_hist);
+          } else {
+            atomicAdd(hist_g + bin_of_s(s[r], inv_step, edges_g), 1ull);
+          }
+        }
+      }
+    }
+  }
+}
+
+// Coalesced merge of the block-private histogram into the global uint64 counts (skips the sink
+// slot of every pair).
+template <int THREADS>
+__device__ __forceinline__ void merge_hist(uint32_t* s_hist, const AllPairsParams& p, int tid,
+                                           bool clear) {
+  const int stride = p.nbins + 1;
+  for (int pr = 0; pr < p.pair_cnt; ++pr) {
+    unsigned long long* g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
+    uint32_t* h = s_hist + pr * stride;
+    for (int k = tid; k < p.nbins; k += THREADS) {
+      const uint32_t v = h[k];
+      if (v) {
+        atomicAdd(g + k, (unsigned long long)v);
+        if (clear) h[k] = 0u;
+      }
+    }
+    if (clear && tid == 0) h[p.nbins] = 0u;
+  }
+}
+
+template <int THREADS, int R, int MINB, bool HIST_SMEM>
+__global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPairsParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4* jt = reinterpret_cast<float4*>(smem_raw);                  // [2][TJ]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(jt + 2 * TJ);         // [2]
+  volatile int* s_item = reinterpret_cast<volatile int*>(bars + 2);  // 16 B slot
+  float* s_edges = reinterpret_cast<float*>(bars + 4);
+  const int n_edges = p.nbins + 2;
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_edges + ((n_edges + 3) & ~3));
+  const int hist_stride = p.nbins + 1;  // slot nbins of every pair is the out-of-cutoff sink
+  const int n_hist = p.pair_cnt * hist_stride;
+  const int tid = threadIdx.x;
+
+  if (HIST_SMEM) {
+    for (int k = tid; k < n_edges; k += THREADS) s_edges[k] = p.edges[k];
+    for (int k = tid; k < n_hist; k += THREADS) s_hist[k] = 0u;
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const uint32_t edges1_sa = smem_u32(s_edges + 1);
+  const float bx = p.box[0], by = p.box[1], bz = p.box[2];
+  const float s_cut = p.s_cut, inv_step = p.inv_step;
+  const bool dense = HIST_SMEM && (p.dense != 0);
+  const long long total = (long long)p.n_items * (long long)p.n_frames;
+  uint32_t ph0 = 0, ph1 = 0;
+  unsigned long long since_flush = 0;
+
+  for (;;) {
+    if (tid == 0) *s_item = (int)atomicAdd(p.work_counter, 1u);
+    __syncthreads();
+    const long long idx = (unsigned int)*s_item;
+    __syncthreads();  // everyone has read the slot before thread 0 overwrites it
+    if (idx >= total) break;
+    // big items first: consecutive indices walk the frames of one item
+    const PairItem it = p.items[idx / p.n_frames];
+    const int frame = (int)(idx % p.n_frames);
+    const float4* __restrict__ fpos = p.pos + (long long)frame * p.frame_stride;
+    const bool fast = ((p.frame_flags[frame] & 3u) != 3u);  // see rdf_pack.cu
+
+    float xi[R], yi[R], zi[R];
+    int ig[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int li = tid + r * THREADS;
+      ig[r] = it.i0 + li;
+      if (li < it.i_cnt) {
+        const float4 v = __ldg(fpos + ig[r]);
+        xi[r] = v.x; yi[r] = v.y; zi[r] = v.z;
+      } else {
+        xi[r] = yi[r] = zi[r] = __int_as_float(0x7fc00000);  // NaN: never in cutoff
+      }
+    }
+
+    const uint32_t c_edge = edges1_sa - kMagic4;
+    const uint32_t d_hist = smem_u32(s_hist + (it.pair - p.pair_lo) * hist_stride) - edges1_sa;
+    unsigned long long* hist_g = p.counts + (long long)it.pair * p.nbins;
+    const int n_cols = it.j1 - it.j0;
+    const int n_tiles = (n_cols + TJ - 1) / TJ;
+
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)min(TJ, n_cols) * 16u;
+      fence_proxy_async();
+      mbar_expect_tx(&bars[0], bytes);
+      tma_load_1d(jt, fpos + it.j0, bytes, &bars[0]);
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+      const int st = t & 1;
+      if (tid == 0 && t + 1 < n_tiles) {
+        const int nb = it.j0 + (t + 1) * TJ;
+        const uint32_t bytes = (uint32_t)min(TJ, it.j1 - nb) * 16u;
+        fence_proxy_async();
+        mbar_expect_tx(&bars[st ^ 1], bytes);
+        tma_load_1d(jt + (st ^ 1) * TJ, fpos + nb, bytes, &bars[st ^ 1]);
+      }
+      if (st == 0) { mbar_wait(&bars[0], ph0); ph0 ^= 1u; }
+      else         { mbar_wait(&bars[1], ph1); ph1 ^= 1u; }
+      const int jbase = it.j0 + t * TJ;
+      const int cnt = min(TJ, it.j1 - jbase);
+      const float4* tile = jt + st * TJ;
+      const bool diag = it.diag && (jbase < it.i0 + it.i_cnt);
+#define MDS_TILE(FASTV, DIAGV, DENSEV)                                                         \
+  pair_tile<R, FASTV, DIAGV, HIST_SMEM, DENSEV>(tile, cnt, jbase, xi, yi, zi, ig, bx, by, bz,     \
+                                                s_cut, inv_step, c_edge, d_hist, p.edges, hist_g)
+      if (dense) {
+        if (fast) { if (diag) MDS_TILE(true, true, true); else MDS_TILE(true, false, true); }
+        else      { if (diag) MDS_TILE(false, true, true); else MDS_TILE(false, false, true); }
+      } else {
+        if (fast) { if (diag) MDS_TILE(true, true, false); else MDS_TILE(true, false, false); }
+        else      { if (diag) MDS_TILE(false, true, false); else MDS_TILE(false, false, false); }
+      }
+#undef MDS_TILE
+      __syncthreads();  // tile `st` fully consumed before it is refilled two iterations later
+    }
+
+    if (HIST_SMEM) {
+      since_flush += (unsigned long long)it.i_cnt * (unsigned long long)n_cols;
+      if (since_flush >= (1ull << 31)) {  // uniform across the CTA
+        merge_hist<THREADS>(s_hist, p, tid, true);
+        since_flush = 0;
+        __syncthreads();
+      }
+    }
+  }
+
+  if (HIST_SMEM) {
+    merge_hist<THREADS>(s_hist, p, tid, false);
+  }
+}
+
+// ---- host-side launch table ----------------------------------------------------------------
+
+size_t allpairs_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem) {
+  size_t b = 2 * TJ * sizeof(float4) + 4 * sizeof(uint64_t);
+  if (hist_in_smem) {
+    b += (size_t)((nbins + 2 + 3) & ~3) * sizeof(float);
+    b += (size_t)pair_cnt * (size_t)(nbins + 1) * sizeof(uint32_t);
+  }
+  return b;
+}
+
+template <int THREADS, int R, int MINB>
+static cudaError_t launch_variant(const AllPairsParams& p, int sm_count, cudaStream_t stream,
+                                  int* grid_out) {
+  const size_t smem = allpairs_smem_bytes(p.nbins, p.pair_cnt, p.hist_in_smem != 0);
+  auto kern = p.hist_in_smem ? rdf_allpairs_kernel<THREADS, R, MINB, true>
+                             : rdf_allpairs_kernel<THREADS, R, MINB, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  long long total = (long long)p.n_items * p.n_frames;
+  long long grid = (long long)per_sm * sm_count;  // persistent: a multiple of the SM count
+  if (grid > total) grid = total;
+  if (grid < 1) grid = 1;
+  if (grid_out) *grid_out = (int)grid;
+  kern<<<(unsigned)grid, THREADS, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_allpairs(const AllPairsParams& p, int variant, int sm_count,
+                            cudaStream_t stream, int* grid_out) {
+  switch (variant) {
+    case 0: return launch_variant<256, 1, 3>(p, sm_count, stream, grid_out);
+    case 1: return launch_variant<256, 2, 3>(p, sm_count, stream, grid_out);
+    case 2: return launch_variant<256, 4, 3>(p, sm_count, stream, grid_out);
+    case 3: return launch_variant<512, 2, 2>(p, sm_count, stream, grid_out);
+    case 4: return launch_variant<512, 4, 2>(p, sm_count, stream, grid_out);
+    case 5: return launch_variant<256, 4, 2>(p, sm_count, stream, grid_out);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+int allpairs_variant_tile(int variant) {
+  static const int tiles[] = {256, 512, 1024, 1024, 2048, 1024};
+  return (variant >= 0 && variant < 6) ? tiles[variant] : -1;
+}
+
+}  // namespace mds

@@ -1,0 +1,699 @@
+// C ABI of the RDF hot path (include/mds_rdf.h): handle, threshold table, work schedule,
+// stream pipeline.  Host code only; the kernels live in rdf_allpairs.cu / rdf_pack.cu /
+// rdf_cells.cu.  There is deliberately no CPU fallback: every entry point that computes
+// needs a CUDA device and fails with MDS_ERR_CUDA without one.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mds_rdf.h"
+#include "rdf_common.cuh"
+#include "rdf_launch.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(MDS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+
+// ---- the squared-distance threshold table ----------------------------------------------------
+// Reference chain for an in-range pair:
+//   d = sqrt_rn(s);  keep iff d < float32(cutoff);
+//   step = double(float32(cutoff) - 0.0f) / double(B);  bin = int32(min(double(d) / step, B - 1)).
+// Every stage is monotone non-decreasing in s, so bin(s) is a step function of s and the whole
+// chain collapses to comparisons of s against float32 thresholds computed here, on the host,
+// with the same IEEE operations (sqrtf and double division are correctly rounded on x86-64).
+
+inline int ref_bin_of_d(float d, double step, int nbins) {
+  double q = (double)d / step;
+  const double last = (double)(nbins - 1);
+  if (q > last) q = last;
+  return (int)q;
+}
+
+// smallest float32 s >= 0 with sqrtf(s) >= d  (d >= 0)
+float smallest_s_with_sqrt_ge(float d) {
+  if (d <= 0.0f) return 0.0f;
+  float s = (float)((double)d * (double)d);
+  while (s > 0.0f && sqrtf(s) >= d) s = nextafterf(s, -INFINITY);
+  while (sqrtf(s) < d) s = nextafterf(s, INFINITY);
+  return s;
+}
+
+void build_threshold_table(float cutoff, int nbins, std::vector<float>& edges, float& s_cut) {
+  const double step = (double)(cutoff - 0.0f) / (double)nbins;
+  edges.assign((size_t)nbins + 2, 0.0f);
+  edges[0] = -INFINITY;
+  for (int k = 1; k < nbins; ++k) {
+    float d = (float)((double)k * step);
+    while (d > 0.0f && ref_bin_of_d(d, step, nbins) >= k) d = nextafterf(d, -INFINITY);
+    while (ref_bin_of_d(d, step, nbins) < k) d = nextafterf(d, INFINITY);
+    edges[k] = smallest_s_with_sqrt_ge(d);
+  }
+  s_cut = smallest_s_with_sqrt_ge(cutoff);
+  edges[nbins] = s_cut;  // everything from here on falls into the out-of-cutoff sink
+  edges[nbins + 1] = INFINITY;
+}
+
+}  // namespace
+
+struct mds_rdf {
+  // configuration
+  int n_species = 0;
+  std::vector<int64_t> counts;
+  int nbins = 0;
+  float cutoff = 0.f;
+  float box[3] = {0, 0, 0};
+  uint32_t flags = 0;
+  int device = 0;
+  int batch_frames = 0;
+  int sm_count = 0;
+  // derived
+  int64_t n_atoms = 0;   // raw atoms per frame
+  int32_t n_packed = 0;  // atoms per frame after dropping the Q1 atoms
+  int64_t frame_stride = 0;
+  int n_pairs = 0;
+  double pairs_per_frame = 0;  // the reference's (row, col) count per frame for this mode
+  std::vector<float> edges;
+  float s_cut = 0.f, inv_step = 0.f;
+  std::vector<int32_t> poff, pcnt;  // packed offsets / counts per species
+  int variant = 2;
+  std::vector<mds::PairItem> items;
+  int pair_group = 1;  // species pairs per launch (shared-memory capacity)
+  bool hist_in_smem = true;
+  bool dense = true;  // expected in-cutoff fraction is high: predicated binning
+  // device state
+  int32_t* d_src_index = nullptr;
+  int32_t* d_species = nullptr;
+  float* d_edges = nullptr;
+  mds::PairItem* d_items = nullptr;
+  unsigned long long* d_counts = nullptr;
+  unsigned long long* d_general = nullptr;
+  unsigned int* d_work = nullptr;  // ring of work counters
+  int work_slot = 0;
+  float4* d_packed[2] = {nullptr, nullptr};
+  uint32_t* d_flags[2] = {nullptr, nullptr};
+  float* d_raw[2] = {nullptr, nullptr};  // staging for host submits (lazy)
+  size_t raw_bytes = 0;
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_raw_ready[2] = {nullptr, nullptr};  // H2D of staging buffer done
+  cudaEvent_t ev_raw_free[2] = {nullptr, nullptr};   // pack consumed staging buffer
+  cudaEvent_t ev_ext = nullptr;                      // caller stream -> compute stream
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+  bool timing_valid = false;
+  int buf = 0;
+  // statistics
+  int64_t frames_done = 0;
+  int64_t launches = 0;
+};
+
+namespace {
+
+constexpr int WORK_RING = 4096;
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+void build_items(mds_rdf* h, int tile_rows, int64_t frames_hint) {
+  h->items.clear();
+  // column chunk: keep items big enough to amortise their prologue, small enough that
+  // frames_hint * n_items gives every persistent CTA several items.
+  int pair = 0;
+  std::vector<mds::PairItem> items;
+  for (int a = 0; a < h->n_species; ++a) {
+    for (int b = a; b < h->n_species; ++b, ++pair) {
+      const int a0 = h->poff[a], a1 = a0 + h->pcnt[a];
+      const int b0 = h->poff[b], b1 = b0 + h->pcnt[b];
+      for (int i0 = a0; i0 < a1; i0 += tile_rows) {
+        const int i_cnt = std::min(tile_rows, a1 - i0);
+        const int j0 = (a == b) ? i0 + 1 : b0;
+        const int j1 = (a == b) ? a1 : b1;
+        if (j0 >= j1) continue;
+        items.push_back({pair, i0, i_cnt, j0, j1, (a == b) ? 1 : 0, 0, 0});
+      }
+    }
+  }
+  // split long column ranges until there is enough parallel slack
+  const long long want = 8LL * h->sm_count * 3;
+  int chunk = 1 << 30;
+  auto count_items = [&](int c) {
+    long long n = 0;
+    for (auto& it : items) n += ((it.j1 - it.j0) + c - 1) / c;
+    return n;
+  };
+  if (!items.empty()) {
+    int max_cols = 0;
+    for (auto& it : items) max_cols = std::max(max_cols, it.j1 - it.j0);
+    chunk = std::max(512, ((max_cols + 511) / 512) * 512);
+    while (chunk > 2048 && count_items(chunk) * std::max<int64_t>(frames_hint, 1) < want)
+      chunk = std::max(2048, ((chunk / 2 + 511) / 512) * 512);
+    if (chunk > 8192) chunk = 8192;
+  }
+  for (auto& it : items) {
+    for (int j = it.j0; j < it.j1; j += chunk) {
+      mds::PairItem c = it;
+      c.j0 = j;
+      c.j1 = std::min(it.j1, j + chunk);
+      h->items.push_back(c);
+    }
+  }
+  std::stable_sort(h->items.begin(), h->items.end(), [](const mds::PairItem& x, const mds::PairItem& y) {
+    return (long long)x.i_cnt * (x.j1 - x.j0) > (long long)y.i_cnt * (y.j1 - y.j0);
+  });
+}
+
+int pick_variant(const mds_rdf* h) {
+  if (const char* env = getenv("MDS_RDF_VARIANT")) {
+    int v = atoi(env);
+    if (v >= 0 && v < mds::ALLPAIRS_N_VARIANTS) return v;
+  }
+  int max_species = 0;
+  for (int c : h->pcnt) max_species = std::max(max_species, c);
+  if (max_species >= 4096) return 2;  // 256 threads x 4 rows
+  if (max_species >= 1024) return 1;  // 256 x 2
+  return 0;                           // 256 x 1
+}
+
+int upload_items(mds_rdf* h) {
+  if (h->d_items) { cudaFree(h->d_items); h->d_items = nullptr; }
+  if (h->items.empty()) return MDS_OK;
+  CUDA_TRY(cudaMalloc(&h->d_items, h->items.size() * sizeof(mds::PairItem)));
+  CUDA_TRY(cudaMemcpy(h->d_items, h->items.data(), h->items.size() * sizeof(mds::PairItem),
+                      cudaMemcpyHostToDevice));
+  return MDS_OK;
+}
+
+// pack one batch that already sits in device memory, then run the pair kernels on it
+int process_batch(mds_rdf* h, const float* d_xyz, int layout, int64_t frame0, int64_t n_frames,
+                  int64_t n_frames_total, int buf) {
+  CUDA_TRY(cudaMemsetAsync(h->d_flags[buf], 0, sizeof(uint32_t) * (size_t)n_frames, h->s_compute));
+  mds::PackParams pp;
+  pp.xyz = d_xyz;
+  pp.layout = layout;
+  pp.n_atoms = h->n_atoms;
+  pp.n_frames = n_frames;
+  pp.frame0 = frame0;
+  pp.n_frames_total = n_frames_total;
+  pp.src_index = h->d_src_index;
+  pp.species = h->d_species;
+  pp.n_packed = h->n_packed;
+  pp.out = h->d_packed[buf];
+  pp.frame_stride = h->frame_stride;
+  pp.frame_flags = h->d_flags[buf];
+  for (int k = 0; k < 3; ++k) pp.box[k] = h->box[k];
+  CUDA_TRY(mds::launch_pack(pp, h->s_compute));
+  CUDA_TRY(mds::launch_count_general(h->d_flags[buf], (int)n_frames, h->d_general, h->s_compute));
+  h->launches += 2;
+  if (h->items.empty()) return MDS_OK;
+
+  for (int p0 = 0; p0 < h->n_pairs; p0 += h->pair_group) {
+    const int pc = std::min(h->pair_group, h->n_pairs - p0);
+    // items are shared by all groups; a launch only sees the ones of its pairs
+    mds::AllPairsParams ap;
+    ap.pos = h->d_packed[buf];
+    ap.frame_stride = h->frame_stride;
+    ap.n_frames = (int32_t)n_frames;
+    ap.edges = h->d_edges;
+    ap.frame_flags = h->d_flags[buf];
+    ap.counts = h->d_counts;
+    ap.nbins = h->nbins;
+    ap.pair_lo = p0;
+    ap.pair_cnt = pc;
+    ap.hist_in_smem = h->hist_in_smem ? 1 : 0;
+    ap.s_cut = h->s_cut;
+    ap.inv_step = h->inv_step;
+    ap.dense = h->dense ? 1 : 0;
+    for (int k = 0; k < 3; ++k) ap.box[k] = h->box[k];
+    // item sub-range of this pair group (items are regrouped per pair group at create time)
+    int first = -1, last = -1;
+    for (int i = 0; i < (int)h->items.size(); ++i)
+      if (h->items[i].pair >= p0 && h->items[i].pair < p0 + pc) {
+        if (first < 0) first = i;
+        last = i;
+      }
+    if (first < 0) continue;
+    ap.items = h->d_items + first;
+    ap.n_items = last - first + 1;
+    if (h->work_slot >= WORK_RING) {
+      CUDA_TRY(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int) * WORK_RING, h->s_compute));
+      h->work_slot = 0;
+    }
+    ap.work_counter = h->d_work + h->work_slot++;
+    CUDA_TRY(mds::launch_allpairs(ap, h->variant, h->sm_count, h->s_compute, nullptr));
+    h->launches += 1;
+  }
+  return MDS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mds_last_error(void) { return g_last_error.c_str(); }
+int mds_abi_version(void) { return MDS_RDF_ABI_VERSION; }
+
+int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
+  if (!out) return fail(MDS_ERR_INVALID, "mds_rdf_create: out is NULL");
+  *out = nullptr;
+  if (!cfg) return fail(MDS_ERR_INVALID, "mds_rdf_create: cfg is NULL");
+  if (cfg->struct_size != sizeof(mds_rdf_config))
+    return fail(MDS_ERR_INVALID, "mds_rdf_create: struct_size %u != %zu (ABI mismatch)",
+                cfg->struct_size, sizeof(mds_rdf_config));
+  if (cfg->n_species < 1 || !cfg->counts)
+    return fail(MDS_ERR_INVALID, "mds_rdf_create: need n_species >= 1 and counts");
+  if (cfg->nbins < 1 || cfg->nbins > mds::MDS_MAX_BINS)
+    return fail(MDS_ERR_INVALID, "mds_rdf_create: nbins %d outside [1, %d]", cfg->nbins,
+                mds::MDS_MAX_BINS);
+  if (!(cfg->cutoff > 0.f) || !std::isfinite(cfg->cutoff))
+    return fail(MDS_ERR_INVALID, "mds_rdf_create: cutoff must be finite and > 0");
+  for (int k = 0; k < 3; ++k)
+    if (!(cfg->box[k] > 0.f) || !std::isfinite(cfg->box[k]))
+      return fail(MDS_ERR_INVALID, "mds_rdf_create: box[%d] must be finite and > 0", k);
+  if ((cfg->flags & MDS_RDF_PATH_ALLPAIRS) && (cfg->flags & MDS_RDF_PATH_CELLLIST))
+    return fail(MDS_ERR_INVALID, "mds_rdf_create: both PATH flags set");
+  if (cfg->flags & MDS_RDF_PATH_CELLLIST)
+    return fail(MDS_ERR_UNSUPPORTED, "mds_rdf_create: cell-list path not built yet");
+  int64_t n_atoms = 0;
+  for (int s = 0; s < cfg->n_species; ++s) {
+    if (cfg->counts[s] < 0) return fail(MDS_ERR_INVALID, "mds_rdf_create: counts[%d] < 0", s);
+    n_atoms += cfg->counts[s];
+  }
+  if (n_atoms > (int64_t)std::numeric_limits<int32_t>::max() / 2)
+    return fail(MDS_ERR_UNSUPPORTED, "mds_rdf_create: %lld atoms per frame is too many",
+                (long long)n_atoms);
+
+  int n_dev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  if (ce != cudaSuccess || n_dev < 1)
+    return fail(MDS_ERR_CUDA, "mds_rdf_create: no CUDA device (%s); this library has no CPU path",
+                cudaGetErrorString(ce));
+  if (cfg->device < 0 || cfg->device >= n_dev)
+    return fail(MDS_ERR_INVALID, "mds_rdf_create: device %d not in [0, %d)", cfg->device, n_dev);
+
+  mds_rdf* h = new (std::nothrow) mds_rdf();
+  if (!h) return fail(MDS_ERR_NOMEM, "mds_rdf_create: out of host memory");
+  h->n_species = cfg->n_species;
+  h->counts.assign(cfg->counts, cfg->counts + cfg->n_species);
+  h->nbins = cfg->nbins;
+  h->cutoff = cfg->cutoff;
+  for (int k = 0; k < 3; ++k) h->box[k] = cfg->box[k];
+  h->flags = cfg->flags;
+  h->device = cfg->device;
+  h->n_atoms = n_atoms;
+  h->n_pairs = cfg->n_species * (cfg->n_species + 1) / 2;
+
+  DeviceGuard guard(h->device);
+  cudaDeviceProp prop;
+  ce = cudaGetDeviceProperties(&prop, h->device);
+  if (ce != cudaSuccess) {
+    delete h;
+    return fail(MDS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(ce));
+  }
+  if (prop.major < 10) {
+    delete h;
+    return fail(MDS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
+                h->device, prop.major, prop.minor);
+  }
+  h->sm_count = prop.multiProcessorCount;
+
+  // packed order: species concatenated, the Q1 atom of each species dropped in parity mode
+  const int first = (h->flags & MDS_RDF_PARITY_SKIP_FIRST) ? 1 : 0;
+  std::vector<int32_t> src_index, species;
+  int64_t off = 0;
+  h->pairs_per_frame = 0;
+  for (int s = 0; s < h->n_species; ++s) {
+    h->poff.push_back((int32_t)src_index.size());
+    const int64_t n = std::max<int64_t>(0, h->counts[s] - first);
+    h->pcnt.push_back((int32_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+      src_index.push_back((int32_t)(off + first + i));
+      species.push_back(s);
+    }
+    off += h->counts[s];
+  }
+  for (int a = 0; a < h->n_species; ++a)
+    for (int b = a; b < h->n_species; ++b)
+      h->pairs_per_frame += (a == b) ? 0.5 * (double)h->pcnt[a] * (double)(h->pcnt[a] - 1)
+                                     : (double)h->pcnt[a] * (double)h->pcnt[b];
+  h->n_packed = (int32_t)src_index.size();
+  h->frame_stride = ((int64_t)h->n_packed + 7) & ~7LL;  // 128 B aligned frames
+  if (h->frame_stride == 0) h->frame_stride = 8;
+
+  build_threshold_table(h->cutoff, h->nbins, h->edges, h->s_cut);
+  h->inv_step = (float)((double)h->nbins / (double)h->cutoff * (double)mds::kBinGuessBias);
+
+  // how many species pairs fit in shared memory next to the threshold table
+  const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
+  const size_t target = std::min<size_t>(smem_cap, 100 * 1024);  // keep >= 2 CTAs per SM if possible
+  h->hist_in_smem = true;
+  h->pair_group = h->n_pairs;
+  while (h->pair_group > 1 && mds::allpairs_smem_bytes(h->nbins, h->pair_group, true) > target)
+    --h->pair_group;
+  if (mds::allpairs_smem_bytes(h->nbins, h->pair_group, true) > target) {
+    // a single pair does not fit the 2-CTA budget: allow the full opt-in size, then give up on smem
+    if (mds::allpairs_smem_bytes(h->nbins, 1, true) > smem_cap) {
+      h->hist_in_smem = false;
+      h->pair_group = h->n_pairs;
+    }
+  }
+
+  {
+    // expected fraction of pairs inside the cutoff sphere (ideal gas): 4/3 pi rc^3 / V
+    const double vol = (double)h->box[0] * h->box[1] * h->box[2];
+    const double phi = std::min(1.0, 4.18879 * (double)h->cutoff * h->cutoff * h->cutoff / vol);
+    h->dense = phi > 0.08;
+    if (const char* env = getenv("MDS_RDF_DENSE")) h->dense = atoi(env) != 0;
+  }
+  h->variant = pick_variant(h);
+  int bf = cfg->max_frames_in_flight;
+  if (bf <= 0) {
+    const int64_t per_frame = h->frame_stride * 16;
+    bf = (int)std::min<int64_t>(4096, std::max<int64_t>(1, (128LL << 20) / per_frame));
+  }
+  h->batch_frames = bf;
+  build_items(h, mds::allpairs_variant_tile(h->variant), bf);
+  // group items by pair group so a launch sees a contiguous range (stable: keeps cost order)
+  std::stable_sort(h->items.begin(), h->items.end(), [h](const mds::PairItem& x, const mds::PairItem& y) {
+    return x.pair / h->pair_group < y.pair / h->pair_group;
+  });
+
+#define CREATE_TRY(expr)                                                                   \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      fail(MDS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));                  \
+      mds_rdf_destroy(h);                                                                  \
+      return MDS_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+  const size_t np = std::max<size_t>(1, src_index.size());
+  CREATE_TRY(cudaMalloc(&h->d_src_index, np * sizeof(int32_t)));
+  CREATE_TRY(cudaMalloc(&h->d_species, np * sizeof(int32_t)));
+  if (!src_index.empty()) {
+    CREATE_TRY(cudaMemcpy(h->d_src_index, src_index.data(), src_index.size() * sizeof(int32_t),
+                          cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(h->d_species, species.data(), species.size() * sizeof(int32_t),
+                          cudaMemcpyHostToDevice));
+  }
+  CREATE_TRY(cudaMalloc(&h->d_edges, h->edges.size() * sizeof(float)));
+  CREATE_TRY(cudaMemcpy(h->d_edges, h->edges.data(), h->edges.size() * sizeof(float),
+                        cudaMemcpyHostToDevice));
+  const size_t n_counts = (size_t)h->n_pairs * (size_t)h->nbins;
+  CREATE_TRY(cudaMalloc(&h->d_counts, n_counts * sizeof(unsigned long long)));
+  CREATE_TRY(cudaMemset(h->d_counts, 0, n_counts * sizeof(unsigned long long)));
+  CREATE_TRY(cudaMalloc(&h->d_general, sizeof(unsigned long long)));
+  CREATE_TRY(cudaMemset(h->d_general, 0, sizeof(unsigned long long)));
+  CREATE_TRY(cudaMalloc(&h->d_work, sizeof(unsigned int) * WORK_RING));
+  CREATE_TRY(cudaMemset(h->d_work, 0, sizeof(unsigned int) * WORK_RING));
+  for (int b = 0; b < 2; ++b) {
+    CREATE_TRY(cudaMalloc(&h->d_packed[b], (size_t)h->frame_stride * 16 * (size_t)bf));
+    CREATE_TRY(cudaMalloc(&h->d_flags[b], sizeof(uint32_t) * (size_t)bf));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_raw_ready[b], cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_raw_free[b], cudaEventDisableTiming));
+  }
+  CREATE_TRY(cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming));
+  CREATE_TRY(cudaEventCreate(&h->ev_t0));
+  CREATE_TRY(cudaEventCreate(&h->ev_t1));
+  CREATE_TRY(cudaEventCreate(&h->ev_k0));
+  CREATE_TRY(cudaEventCreate(&h->ev_k1));
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+  {
+    int rc = upload_items(h);
+    if (rc != MDS_OK) { mds_rdf_destroy(h); return rc; }
+  }
+#undef CREATE_TRY
+  *out = h;
+  return MDS_OK;
+}
+
+void mds_rdf_destroy(mds_rdf_t* h) {
+  if (!h) return;
+  DeviceGuard guard(h->device);
+  if (h->s_compute) cudaStreamSynchronize(h->s_compute);
+  if (h->s_copy) cudaStreamSynchronize(h->s_copy);
+  cudaFree(h->d_src_index);
+  cudaFree(h->d_species);
+  cudaFree(h->d_edges);
+  cudaFree(h->d_items);
+  cudaFree(h->d_counts);
+  cudaFree(h->d_general);
+  cudaFree(h->d_work);
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(h->d_packed[b]);
+    cudaFree(h->d_flags[b]);
+    cudaFree(h->d_raw[b]);
+    if (h->ev_raw_ready[b]) cudaEventDestroy(h->ev_raw_ready[b]);
+    if (h->ev_raw_free[b]) cudaEventDestroy(h->ev_raw_free[b]);
+  }
+  if (h->ev_ext) cudaEventDestroy(h->ev_ext);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+  if (h->ev_k0) cudaEventDestroy(h->ev_k0);
+  if (h->ev_k1) cudaEventDestroy(h->ev_k1);
+  if (h->s_compute) cudaStreamDestroy(h->s_compute);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  delete h;
+}
+
+static int check_submit_args(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
+                             const char* who) {
+  if (!h) return fail(MDS_ERR_INVALID, "%s: handle is NULL", who);
+  if (n_frames < 0) return fail(MDS_ERR_INVALID, "%s: n_frames < 0", who);
+  if (n_frames > 0 && h->n_atoms > 0 && !xyz) return fail(MDS_ERR_INVALID, "%s: xyz is NULL", who);
+  if (layout != MDS_LAYOUT_FRAME_MAJOR_XYZ && layout != MDS_LAYOUT_ATOM_MAJOR_XYZ)
+    return fail(MDS_ERR_INVALID, "%s: unknown layout %d", who, layout);
+  return MDS_OK;
+}
+
+int mds_rdf_submit_device(mds_rdf_t* h, const float* d_xyz, int64_t n_frames, int layout,
+                          void* stream) {
+  int rc = check_submit_args(h, d_xyz, n_frames, layout, "mds_rdf_submit_device");
+  if (rc != MDS_OK) return rc;
+  if (n_frames == 0) return MDS_OK;
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaEventRecord(h->ev_ext, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_ext, 0));
+  CUDA_TRY(cudaEventRecord(h->ev_t0, h->s_compute));
+  CUDA_TRY(cudaEventRecord(h->ev_k0, h->s_compute));
+  for (int64_t f0 = 0; f0 < n_frames; f0 += h->batch_frames) {
+    const int64_t nf = std::min<int64_t>(h->batch_frames, n_frames - f0);
+    rc = process_batch(h, d_xyz, layout, f0, nf, n_frames, h->buf);
+    if (rc != MDS_OK) return rc;
+    h->buf ^= 1;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_k1, h->s_compute));
+  CUDA_TRY(cudaEventRecord(h->ev_t1, h->s_compute));
+  h->timing_valid = true;
+  h->frames_done += n_frames;
+  return MDS_OK;
+}
+
+int mds_rdf_submit(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
+                   int host_is_pinned) {
+  int rc = check_submit_args(h, xyz, n_frames, layout, "mds_rdf_submit");
+  if (rc != MDS_OK) return rc;
+  if (n_frames == 0) return MDS_OK;
+  (void)host_is_pinned;  // cudaMemcpyAsync stages pageable memory itself
+  DeviceGuard guard(h->device);
+  const size_t frame_bytes = (size_t)h->n_atoms * 3 * sizeof(float);
+  const size_t need = std::max<size_t>(16, frame_bytes * (size_t)h->batch_frames);
+  if (h->raw_bytes < need) {
+    CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+    CUDA_TRY(cudaStreamSynchronize(h->s_copy));
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(h->d_raw[b]);
+      h->d_raw[b] = nullptr;
+      CUDA_TRY(cudaMalloc(&h->d_raw[b], need));
+    }
+    h->raw_bytes = need;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_t0, h->s_compute));
+  bool first_kernel = true;
+  for (int64_t f0 = 0; f0 < n_frames; f0 += h->batch_frames) {
+    const int64_t nf = std::min<int64_t>(h->batch_frames, n_frames - f0);
+    const int b = h->buf;
+    // the staging buffer must have been consumed by the pack kernel of two batches ago
+    CUDA_TRY(cudaStreamWaitEvent(h->s_copy, h->ev_raw_free[b], 0));
+    if (layout == MDS_LAYOUT_FRAME_MAJOR_XYZ) {
+      CUDA_TRY(cudaMemcpyAsync(h->d_raw[b], xyz + (size_t)f0 * h->n_atoms * 3, frame_bytes * nf,
+                               cudaMemcpyHostToDevice, h->s_copy));
+    } else {
+      // atom-major: one strided 2-D copy gathers frames [f0, f0+nf) of every atom
+      CUDA_TRY(cudaMemcpy2DAsync(h->d_raw[b], (size_t)nf * 12, xyz + (size_t)f0 * 3,
+                                 (size_t)n_frames * 12, (size_t)nf * 12, (size_t)h->n_atoms,
+                                 cudaMemcpyHostToDevice, h->s_copy));
+    }
+    CUDA_TRY(cudaEventRecord(h->ev_raw_ready[b], h->s_copy));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_raw_ready[b], 0));
+    if (first_kernel) {
+      CUDA_TRY(cudaEventRecord(h->ev_k0, h->s_compute));
+      first_kernel = false;
+    }
+    // inside the staging buffer the batch starts at frame 0 and holds nf frames
+    rc = process_batch(h, h->d_raw[b], layout, 0, nf, nf, b);
+    if (rc != MDS_OK) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_raw_free[b], h->s_compute));
+    h->buf ^= 1;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_k1, h->s_compute));
+  CUDA_TRY(cudaEventRecord(h->ev_t1, h->s_compute));
+  h->timing_valid = true;
+  h->frames_done += n_frames;
+  return MDS_OK;
+}
+
+int mds_rdf_synchronize(mds_rdf_t* h) {
+  if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_synchronize: handle is NULL");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->s_copy));
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  return MDS_OK;
+}
+
+int mds_rdf_counts(mds_rdf_t* h, uint64_t* out, int sync) {
+  if (!h || !out) return fail(MDS_ERR_INVALID, "mds_rdf_counts: NULL argument");
+  DeviceGuard guard(h->device);
+  const size_t bytes = (size_t)h->n_pairs * (size_t)h->nbins * sizeof(uint64_t);
+  CUDA_TRY(cudaMemcpyAsync(out, h->d_counts, bytes, cudaMemcpyDeviceToHost, h->s_compute));
+  if (sync) return mds_rdf_synchronize(h);
+  return MDS_OK;
+}
+
+int mds_rdf_device_counts(mds_rdf_t* h, void** d_counts, void** stream) {
+  if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_device_counts: handle is NULL");
+  if (d_counts) *d_counts = h->d_counts;
+  if (stream) *stream = (void*)h->s_compute;
+  return MDS_OK;
+}
+
+int mds_rdf_reset(mds_rdf_t* h) {
+  if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_reset: handle is NULL");
+  DeviceGuard guard(h->device);
+  const size_t bytes = (size_t)h->n_pairs * (size_t)h->nbins * sizeof(uint64_t);
+  CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, bytes, h->s_compute));
+  CUDA_TRY(cudaMemsetAsync(h->d_general, 0, sizeof(unsigned long long), h->s_compute));
+  h->frames_done = 0;
+  h->launches = 0;
+  h->timing_valid = false;
+  return MDS_OK;
+}
+
+int mds_rdf_stats_get(mds_rdf_t* h, mds_rdf_stats* out) {
+  if (!h || !out) return fail(MDS_ERR_INVALID, "mds_rdf_stats_get: NULL argument");
+  if (out->struct_size != sizeof(mds_rdf_stats))
+    return fail(MDS_ERR_INVALID, "mds_rdf_stats_get: struct_size %u != %zu", out->struct_size,
+                sizeof(mds_rdf_stats));
+  DeviceGuard guard(h->device);
+  int rc = mds_rdf_synchronize(h);
+  if (rc != MDS_OK) return rc;
+  const size_t n = (size_t)h->n_pairs * (size_t)h->nbins;
+  std::vector<unsigned long long> host(n);
+  CUDA_TRY(cudaMemcpy(host.data(), h->d_counts, n * sizeof(unsigned long long),
+                      cudaMemcpyDeviceToHost));
+  double binned = 0;
+  for (auto v : host) binned += (double)v;
+  unsigned long long general = 0;
+  CUDA_TRY(cudaMemcpy(&general, h->d_general, sizeof(general), cudaMemcpyDeviceToHost));
+  out->path = MDS_RDF_PATH_ALLPAIRS;
+  out->frames = h->frames_done;
+  out->pairs_evaluated = h->pairs_per_frame * (double)h->frames_done;
+  out->pairs_allpairs_equiv = out->pairs_evaluated;
+  out->pairs_binned = binned;
+  out->frames_general_minimage = (int64_t)general;
+  out->kernel_launches = h->launches;
+  out->kernel_ms = 0.f;
+  out->submit_ms = 0.f;
+  if (h->timing_valid) {
+    cudaEventElapsedTime(&out->kernel_ms, h->ev_k0, h->ev_k1);
+    cudaEventElapsedTime(&out->submit_ms, h->ev_t0, h->ev_t1);
+  }
+  out->n_pairs = h->n_pairs;
+  out->nbins = h->nbins;
+  out->sm_count = h->sm_count;
+  out->reserved = h->variant;
+  return MDS_OK;
+}
+
+int mds_rdf_threshold_table(mds_rdf_t* h, float* edges, float* s_cut) {
+  if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_threshold_table: handle is NULL");
+  if (edges) {
+    edges[0] = 0.0f;
+    for (int k = 1; k <= h->nbins; ++k) edges[k] = h->edges[k];
+  }
+  if (s_cut) *s_cut = h->s_cut;
+  return MDS_OK;
+}
+
+int mds_rdf_build_threshold_table(float cutoff, int nbins, float* edges, float* s_cut) {
+  if (nbins < 1 || nbins > mds::MDS_MAX_BINS || !(cutoff > 0.f) || !std::isfinite(cutoff))
+    return fail(MDS_ERR_INVALID, "mds_rdf_build_threshold_table: bad cutoff / nbins");
+  std::vector<float> e;
+  float sc = 0.f;
+  build_threshold_table(cutoff, nbins, e, sc);
+  if (edges) {
+    edges[0] = 0.0f;
+    for (int k = 1; k <= nbins; ++k) edges[k] = e[k];
+  }
+  if (s_cut) *s_cut = sc;
+  return MDS_OK;
+}
+
+int mds_bench_shared_atomics(int device, int nbins, int iters, double* spread, double* random,
+                             double* sm_clock_mhz) {
+  int n_dev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n_dev);
+  if (ce != cudaSuccess || device < 0 || device >= n_dev)
+    return fail(MDS_ERR_CUDA, "mds_bench_shared_atomics: no such CUDA device %d", device);
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  float ms0 = 0, ms1 = 0;
+  double l0 = 0, l1 = 0;
+  CUDA_TRY(mds::run_shared_atomic_bench(nbins, iters, 0, prop.multiProcessorCount, &ms0, &l0));
+  CUDA_TRY(mds::run_shared_atomic_bench(nbins, iters, 1, prop.multiProcessorCount, &ms1, &l1));
+  if (spread) *spread = l0;
+  if (random) *random = l1;
+  if (sm_clock_mhz) {
+    // cycles per block / elapsed time of the same launch
+    const double cycles = 1024.0 * (double)iters / l1;
+    *sm_clock_mhz = cycles / ((double)ms1 * 1e3);
+  }
+  return MDS_OK;
+}
+
+}  // extern "C"

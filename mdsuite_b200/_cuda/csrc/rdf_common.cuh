@@ -1,0 +1,191 @@
+// Shared declarations of the sm_100a RDF kernels (all-pairs, pack, cell list).
+//
+// Arithmetic contract (reference utils/linalg.py:84-99 and
+// calculators/radial_distribution_function.py:667-689): float32, every op rounded on its own,
+// no FMA contraction — hence the explicit __f*_rn intrinsics everywhere a rounding counts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mds {
+
+// One unit of work of the all-pairs kernel: rows [i0, i0+i_cnt) of species a against columns
+// [j0, j1) of species b (packed atom indices inside one frame).  When `diag` is set the item
+// belongs to a same-species pair and only col > row contributes.
+struct PairItem {
+  int32_t pair;   // species-pair index (combinations_with_replacement order)
+  int32_t i0;
+  int32_t i_cnt;
+  int32_t j0;
+  int32_t j1;
+  int32_t diag;
+  int32_t pad0, pad1;
+};
+static_assert(sizeof(PairItem) == 32, "PairItem must stay 32 bytes");
+
+struct AllPairsParams {
+  const float4* pos;          // [n_frames][frame_stride] packed positions (x, y, z, species id)
+  int64_t frame_stride;       // float4 elements between frames (>= n_packed, multiple of 1)
+  int32_t n_frames;
+  int32_t n_items;            // items per frame
+  const PairItem* items;      // [n_items], sorted by decreasing cost
+  const float* edges;         // [nbins + 2] threshold table, see "binning" below
+  const uint32_t* frame_flags;  // [n_frames] nonzero: frame is not wrapped -> div/rint minimum image
+  unsigned long long* counts; // [n_pairs_total][nbins] global accumulators
+  unsigned int* work_counter; // zeroed before launch
+  int32_t nbins;
+  int32_t pair_lo;            // first species pair held in shared memory by this launch
+  int32_t pair_cnt;           // number of species pairs held by this launch
+  int32_t hist_in_smem;       // 0: histogram bins live in global memory (very large nbins)
+  float s_cut;                // in-cutoff  <=>  s < s_cut
+  float inv_step;             // float32(nbins / cutoff) * (1 - 2^-20): seeds the bin guess
+  int32_t dense;              // 1: predicated binning (most pairs in cutoff), 0: branch
+  float box[3];
+};
+
+// ---- exact float32 building blocks --------------------------------------------------------
+
+// Minimum image for wrapped coordinates (|d| <= 1.25 box): bit-identical to
+// d - rint(d / box) * box up to sign, 2 ops instead of 4.
+__device__ __forceinline__ float minimg_fast(float d, float box) {
+  const float a = fabsf(d);
+  return fminf(a, __fsub_rn(box, a));
+}
+
+// The reference's literal sequence: RealDiv, Rint, Mul, Sub.
+__device__ __forceinline__ float minimg_general(float d, float box) {
+  const float q = __fdiv_rn(d, box);
+  const float n = rintf(q);
+  return __fsub_rn(d, __fmul_rn(n, box));
+}
+
+// (x*x + y*y) + z*z with materialised products (tf.linalg.norm before the sqrt).
+__device__ __forceinline__ float sq_norm(float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+__device__ __forceinline__ float sqrt_approx(float s) {
+  float d;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(s));
+  return d;
+}
+
+// ---- binning ---------------------------------------------------------------------------------
+// Threshold table (host-built, rdf_api.cu), nbins + 2 floats:
+//   edges[0] = -inf, edges[k] = smallest float32 s that the reference's sqrt +
+//   histogram_fixed_width puts in bin >= k (1 <= k < nbins), edges[nbins] = s_cut = smallest s
+//   with sqrt_rn(s) >= cutoff, edges[nbins + 1] = +inf.
+//   bin k  <=>  edges[k] <= s < edges[k + 1];   "bin" nbins collects everything outside the cutoff.
+//
+// The bin is found with one approximate step and one exact step: k~ = floor(sqrt.approx(s) *
+// inv_step_biased) where inv_step_biased = (nbins / cutoff) * (1 - 2^-20).  The bias is larger
+// than every rounding error of the guess (sqrt.approx 2^-22, the constant 2^-24, the reference's
+// own sqrt rounding 2^-24) and smaller than 1 / MDS_MAX_BINS, so k~ is the exact bin or one
+// below it; a single compare against edges[k~ + 1] settles it.
+constexpr float kBinGuessBias = 1.0f - 9.5367431640625e-07f;  // 1 - 2^-20
+constexpr uint32_t kMagic4 = 0x4B000000u * 4u;                 // 4 * bits(2^23), mod 2^32
+
+// Generic-pointer version for s < s_cut (global-memory histogram fallback).
+__device__ __forceinline__ int bin_of_s(float s, float inv_step_biased,
+                                        const float* __restrict__ edges) {
+  const float f = __fmaf_rz(sqrt_approx(s), inv_step_biased, 8388608.0f);
+  const int k = __float_as_int(f) & 0x7fffff;
+  return k + ((s >= edges[k + 1]) ? 1 : 0);
+}
+
+// Shared-memory paths.  c_edge = smem address of edges[1] minus kMagic4, d_hist = smem address
+// of the pair's hist[0] minus smem address of edges[1]:
+//   a = bits(f) * 4 + c_edge  = &edges[k~ + 1]      h = a + d_hist = &hist[k~]
+//
+// Dense path: branch-free and unpredicated.  The squared distance is clamped to s_cut (NaN and,
+// on diagonal tiles, col <= row pairs clamp to s_cut too), which lands in the overflow slot
+// hist[nbins] that is never merged — so the cutoff test costs one FMNMX and every lane runs the
+// same 9 instructions.
+template <bool DIAG>
+__device__ __forceinline__ void bin_count_dense(float s, float s_cut, float inv_step_biased,
+                                                uint32_t c_edge, uint32_t d_hist, int jg, int ig) {
+  float t = fminf(s, s_cut);  // min.f32 returns the non-NaN operand
+  if (DIAG) t = (jg > ig) ? t : s_cut;
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      ".reg .f32 d, f, hi;\n"
+      ".reg .u32 a, h;\n"
+      "sqrt.approx.ftz.f32 d, %0;\n"
+      "fma.rz.f32 f, d, %1, 0f4B000000;\n"
+      "mov.b32 a, f;\n"
+      "mad.lo.u32 a, a, 4, %2;\n"
+      "ld.shared.f32 hi, [a];\n"
+      "add.u32 h, a, %3;\n"
+      "setp.ge.f32 q, %0, hi;\n"
+      "@q add.u32 h, h, 4;\n"
+      "red.shared.add.u32 [h], 1;\n"
+      "}\n" ::"f"(t),
+      "f"(inv_step_biased), "r"(c_edge), "r"(d_hist)
+      : "memory");
+}
+
+// Sparse path: the same sequence for a pair already known to be inside the cutoff (under a branch).
+__device__ __forceinline__ void bin_count(float s, float inv_step_biased, uint32_t c_edge,
+                                          uint32_t d_hist) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      ".reg .f32 d, f, hi;\n"
+      ".reg .u32 a, h;\n"
+      "sqrt.approx.ftz.f32 d, %0;\n"
+      "fma.rz.f32 f, d, %1, 0f4B000000;\n"
+      "mov.b32 a, f;\n"
+      "mad.lo.u32 a, a, 4, %2;\n"
+      "ld.shared.f32 hi, [a];\n"
+      "add.u32 h, a, %3;\n"
+      "setp.ge.f32 q, %0, hi;\n"
+      "@q add.u32 h, h, 4;\n"
+      "red.shared.add.u32 [h], 1;\n"
+      "}\n" ::"f"(s),
+      "f"(inv_step_biased), "r"(c_edge), "r"(d_hist)
+      : "memory");
+}
+
+// ---- TMA 1-D bulk copy + mbarrier (sm_90+/sm_100a) -----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy, completion signalled on `bar` (bytes % 16 == 0, 16 B aligned).
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+}  // namespace mds

@@ -1,0 +1,74 @@
+// Pack kernel: raw float32 xyz frames (either layout of include/mds_rdf.h) -> the internal
+// per-frame float4 array the pair kernels read.
+//
+// Follows the data preparation of the reference's batch loop:
+//   _format_data  calculators/radial_distribution_function.py:535-563  (species concatenated)
+//   quirk Q1      calculators/radial_distribution_function.py:637-638  (strict '>' drops the atom at
+//                 each species' offset) — in parity mode those atoms are simply not packed
+//   Database.load_data database/simulation_database.py:594-639 produces the atom-major
+//                 (N, C, 3) layout that MDS_LAYOUT_ATOM_MAJOR_XYZ accepts as is.
+// It also classifies every frame: if all coordinates lie in one window of length 1.25 box
+// the 2-op minimum image is bit-identical to the reference's div/rint form;
+// otherwise the pair kernel uses the literal form for that frame.
+#include "rdf_common.cuh"
+#include "rdf_launch.h"
+#include "mds_rdf.h"
+
+namespace mds {
+
+__device__ __forceinline__ uint32_t window_bits(float v, float box) {
+  // bit0: outside [-box/8, 9 box/8]   bit1: outside [-5 box/8, 5 box/8]   (NaN: inside both)
+  uint32_t b = 0;
+  if (v < -0.125f * box || v > 1.125f * box) b |= 1u;
+  if (v < -0.625f * box || v > 0.625f * box) b |= 2u;
+  return b;
+}
+
+__global__ void __launch_bounds__(256) rdf_pack_kernel(const PackParams p) {
+  const long long total = (long long)p.n_frames * p.n_packed;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    long long f, q;
+    if (p.layout == MDS_LAYOUT_ATOM_MAJOR_XYZ) {
+      // consecutive threads walk frames of one atom: contiguous 12 B records in the source
+      q = g / p.n_frames;
+      f = g % p.n_frames;
+    } else {
+      f = g / p.n_packed;
+      q = g % p.n_packed;
+    }
+    const long long a = p.src_index[q];
+    const float* src = (p.layout == MDS_LAYOUT_ATOM_MAJOR_XYZ)
+                           ? p.xyz + (a * p.n_frames_total + p.frame0 + f) * 3
+                           : p.xyz + ((p.frame0 + f) * p.n_atoms + a) * 3;
+    const float x = __ldg(src), y = __ldg(src + 1), z = __ldg(src + 2);
+    p.out[f * p.frame_stride + q] = make_float4(x, y, z, __int_as_float(p.species[q]));
+    const uint32_t bits = window_bits(x, p.box[0]) | window_bits(y, p.box[1]) |
+                          window_bits(z, p.box[2]);
+    if (bits && (p.frame_flags[f] & bits) != bits) atomicOr(p.frame_flags + f, bits);
+  }
+}
+
+cudaError_t launch_pack(const PackParams& p, cudaStream_t stream) {
+  const long long total = (long long)p.n_frames * p.n_packed;
+  if (total <= 0) return cudaSuccess;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  rdf_pack_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+__global__ void rdf_count_general_kernel(const uint32_t* flags, int n, unsigned long long* out) {
+  unsigned int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += ((flags[i] & 3u) == 3u) ? 1u : 0u;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+cudaError_t launch_count_general(const uint32_t* flags, int n, unsigned long long* out,
+                                 cudaStream_t stream) {
+  rdf_count_general_kernel<<<1, 256, 0, stream>>>(flags, n, out);
+  return cudaGetLastError();
+}
+
+}  // namespace mds
