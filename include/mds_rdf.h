@@ -94,6 +94,10 @@ typedef struct mds_rdf_stats {
   int32_t n_pairs;             /* S(S+1)/2 */
   int32_t nbins;
   int32_t sm_count;
+  int32_t variant;             /* kernel variant picked for this handle (tuning aid) */
+  float pair_kernel_ms;        /* sum of pair-kernel launch durations since the previous stats_get */
+  int32_t pair_kernel_launches; /* pair-kernel launches since the previous stats_get */
+  int32_t dense;               /* 1: branch-free binning (most pairs inside the cutoff) */
   int32_t reserved;
 } mds_rdf_stats;
 
@@ -126,6 +130,15 @@ MDS_API int mds_rdf_counts(mds_rdf_t* h, uint64_t* out, int sync);
  * produced on, for a collective over per-GPU handles (the host layer allreduces this buffer in
  * place with NCCL, one ncclAllReduce(sum, uint64) — SURVEY.md §8e). */
 MDS_API int mds_rdf_device_counts(mds_rdf_t* h, void** d_counts, void** stream);
+
+/* Make `stream` (a cudaStream_t as void*, NULL = default stream) wait for everything submitted so
+ * far, without blocking the host — so that events recorded on the caller's stream bracket the
+ * library's work. */
+MDS_API int mds_rdf_join(mds_rdf_t* h, void* stream);
+
+/* The reverse: make the library's stream wait for work already enqueued on `stream` (e.g. a
+ * collective that reads the device counts) before anything submitted or reset afterwards. */
+MDS_API int mds_rdf_wait(mds_rdf_t* h, void* stream);
 
 MDS_API int mds_rdf_synchronize(mds_rdf_t* h);
 MDS_API int mds_rdf_reset(mds_rdf_t* h); /* zero the accumulated counts and statistics */

@@ -30,7 +30,8 @@ LAYOUT_ATOM_MAJOR = 1  # (n_atoms, n_frames, 3) — the reference's positions_te
 
 EXPORTED_SYMBOLS = (
     "mds_rdf_create", "mds_rdf_destroy", "mds_rdf_submit", "mds_rdf_submit_device",
-    "mds_rdf_counts", "mds_rdf_device_counts", "mds_rdf_synchronize", "mds_rdf_reset",
+    "mds_rdf_counts", "mds_rdf_device_counts", "mds_rdf_join", "mds_rdf_wait", "mds_rdf_synchronize",
+    "mds_rdf_reset",
     "mds_rdf_stats_get", "mds_rdf_threshold_table", "mds_rdf_build_threshold_table",
     "mds_bench_shared_atomics",
     "mds_last_error", "mds_abi_version",
@@ -70,6 +71,10 @@ class _Stats(ctypes.Structure):
         ("n_pairs", ctypes.c_int32),
         ("nbins", ctypes.c_int32),
         ("sm_count", ctypes.c_int32),
+        ("variant", ctypes.c_int32),
+        ("pair_kernel_ms", ctypes.c_float),
+        ("pair_kernel_launches", ctypes.c_int32),
+        ("dense", ctypes.c_int32),
         ("reserved", ctypes.c_int32),
     ]
 
@@ -89,6 +94,9 @@ class RDFStats:
     nbins: int
     sm_count: int
     variant: int
+    pair_kernel_ms: float
+    pair_kernel_launches: int
+    dense: int
 
 
 _lib = None
@@ -112,6 +120,8 @@ def load() -> ctypes.CDLL:
     lib.mds_rdf_submit_device.argtypes = [vp, vp, i64, i32, vp]
     lib.mds_rdf_counts.argtypes = [vp, vp, i32]
     lib.mds_rdf_device_counts.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    lib.mds_rdf_join.argtypes = [vp, vp]
+    lib.mds_rdf_wait.argtypes = [vp, vp]
     lib.mds_rdf_synchronize.argtypes = [vp]
     lib.mds_rdf_reset.argtypes = [vp]
     lib.mds_rdf_stats_get.argtypes = [vp, ctypes.POINTER(_Stats)]
@@ -255,6 +265,22 @@ class RDFHandle:
                                                ctypes.c_void_p(stream)), "mds_rdf_submit_device")
         return n_frames
 
+    def join(self, stream: Optional[int] = None):
+        """Make ``stream`` (default: torch's current stream) wait for the submitted work, so
+        events recorded on that stream bracket it.  Does not block the host."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        _check(self._lib.mds_rdf_join(self._h, ctypes.c_void_p(stream)), "mds_rdf_join")
+
+    def wait(self, stream: Optional[int] = None):
+        """Make the library's stream wait for work already enqueued on ``stream`` (default:
+        torch's current stream), e.g. an allreduce over :meth:`device_counts`."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        _check(self._lib.mds_rdf_wait(self._h, ctypes.c_void_p(stream)), "mds_rdf_wait")
+
     def synchronize(self):
         _check(self._lib.mds_rdf_synchronize(self._h), "mds_rdf_synchronize")
         self._keepalive = []
@@ -283,7 +309,8 @@ class RDFHandle:
         self._keepalive = []
         return RDFStats(st.path, st.frames, st.pairs_evaluated, st.pairs_allpairs_equiv,
                         st.pairs_binned, st.frames_general_minimage, st.kernel_launches,
-                        st.kernel_ms, st.submit_ms, st.n_pairs, st.nbins, st.sm_count, st.reserved)
+                        st.kernel_ms, st.submit_ms, st.n_pairs, st.nbins, st.sm_count, st.variant,
+                        st.pair_kernel_ms, st.pair_kernel_launches, st.dense)
 
     def threshold_table(self):
         """(edges[0..nbins] float32, s_cut): the squared-distance thresholds the kernels use."""

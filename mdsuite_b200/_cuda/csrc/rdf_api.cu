@@ -123,6 +123,9 @@ struct mds_rdf {
   cudaEvent_t ev_raw_free[2] = {nullptr, nullptr};   // pack consumed staging buffer
   cudaEvent_t ev_ext = nullptr;                      // caller stream -> compute stream
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+  cudaEvent_t ev_join = nullptr;
+  std::vector<cudaEvent_t> pk_events;  // start/stop pairs around every pair-kernel launch
+  int pk_used = 0;                     // launches of the last submit
   bool timing_valid = false;
   int buf = 0;
   // statistics
@@ -272,7 +275,17 @@ int process_batch(mds_rdf* h, const float* d_xyz, int layout, int64_t frame0, in
       h->work_slot = 0;
     }
     ap.work_counter = h->d_work + h->work_slot++;
+    if ((int)h->pk_events.size() < 2 * (h->pk_used + 1)) {
+      cudaEvent_t a = nullptr, b = nullptr;
+      CUDA_TRY(cudaEventCreate(&a));
+      CUDA_TRY(cudaEventCreate(&b));
+      h->pk_events.push_back(a);
+      h->pk_events.push_back(b);
+    }
+    CUDA_TRY(cudaEventRecord(h->pk_events[2 * h->pk_used], h->s_compute));
     CUDA_TRY(mds::launch_allpairs(ap, h->variant, h->sm_count, h->s_compute, nullptr));
+    CUDA_TRY(cudaEventRecord(h->pk_events[2 * h->pk_used + 1], h->s_compute));
+    h->pk_used += 1;
     h->launches += 1;
   }
   return MDS_OK;
@@ -446,6 +459,7 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_raw_free[b], cudaEventDisableTiming));
   }
   CREATE_TRY(cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming));
+  CREATE_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CREATE_TRY(cudaEventCreate(&h->ev_t0));
   CREATE_TRY(cudaEventCreate(&h->ev_t1));
   CREATE_TRY(cudaEventCreate(&h->ev_k0));
@@ -481,6 +495,8 @@ void mds_rdf_destroy(mds_rdf_t* h) {
     if (h->ev_raw_free[b]) cudaEventDestroy(h->ev_raw_free[b]);
   }
   if (h->ev_ext) cudaEventDestroy(h->ev_ext);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  for (cudaEvent_t e : h->pk_events) cudaEventDestroy(e);
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->ev_k0) cudaEventDestroy(h->ev_k0);
@@ -577,6 +593,22 @@ int mds_rdf_submit(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
   return MDS_OK;
 }
 
+int mds_rdf_join(mds_rdf_t* h, void* stream) {
+  if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_join: handle is NULL");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaEventRecord(h->ev_join, h->s_compute));
+  CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_join, 0));
+  return MDS_OK;
+}
+
+int mds_rdf_wait(mds_rdf_t* h, void* stream) {
+  if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_wait: handle is NULL");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaEventRecord(h->ev_ext, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_ext, 0));
+  return MDS_OK;
+}
+
 int mds_rdf_synchronize(mds_rdf_t* h) {
   if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_synchronize: handle is NULL");
   DeviceGuard guard(h->device);
@@ -645,7 +677,17 @@ int mds_rdf_stats_get(mds_rdf_t* h, mds_rdf_stats* out) {
   out->n_pairs = h->n_pairs;
   out->nbins = h->nbins;
   out->sm_count = h->sm_count;
-  out->reserved = h->variant;
+  out->variant = h->variant;
+  out->pair_kernel_ms = 0.f;
+  out->pair_kernel_launches = h->pk_used;
+  for (int i = 0; i < h->pk_used; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->pk_events[2 * i], h->pk_events[2 * i + 1]);
+    out->pair_kernel_ms += ms;
+  }
+  h->pk_used = 0;  // "since the previous mds_rdf_stats_get"; survives submit and reset
+  out->dense = h->dense ? 1 : 0;
+  out->reserved = 0;
   return MDS_OK;
 }
 
