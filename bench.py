@@ -278,7 +278,9 @@ def run_ours(args):
                            else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        t_wait = time.perf_counter()
+        while sampler.proc is not None and not sampler.rows and time.perf_counter() - t_wait < 5.0:
+            time.sleep(0.05)  # nvidia-smi takes a moment to print its first sample
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()

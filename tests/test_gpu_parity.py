@@ -253,3 +253,24 @@ def test_many_species_multi_pass_and_large_bins():
     got, st = gpu_counts(pos, counts, box, 14.9, 60000)
     want, ev = oracle_counts(pos, counts, box, 14.9, 60000)
     assert_same(got, want, st, ev)
+
+
+def _golden_cases():
+    import json
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "rdf_golden.json")) as fh:
+        return json.load(fh)["cases"]
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_committed_golden_vectors(case):
+    """The fixtures under tests/golden/ (self-generated from the literal NumPy restatement)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    pos, box = make_golden.case_inputs(case)
+    got, _ = gpu_counts(pos, case["counts"], box, case["cutoff"], case["nbins"], parity=True)
+    assert_same(got, np.array(case["counts_parity"], dtype=np.uint64))
+    got, _ = gpu_counts(pos, case["counts"], box, case["cutoff"], case["nbins"], parity=False,
+                        layout=_cuda.LAYOUT_ATOM_MAJOR)
+    assert_same(got, np.array(case["counts_corrected"], dtype=np.uint64))
