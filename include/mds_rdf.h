@@ -140,6 +140,10 @@ MDS_API int mds_rdf_join(mds_rdf_t* h, void* stream);
  * collective that reads the device counts) before anything submitted or reset afterwards. */
 MDS_API int mds_rdf_wait(mds_rdf_t* h, void* stream);
 
+/* Block the host until every host->device copy issued by mds_rdf_submit so far has completed,
+ * i.e. until the submitted host buffers may be overwritten (the kernels may still be running). */
+MDS_API int mds_rdf_wait_host_copies(mds_rdf_t* h);
+
 MDS_API int mds_rdf_synchronize(mds_rdf_t* h);
 MDS_API int mds_rdf_reset(mds_rdf_t* h); /* zero the accumulated counts and statistics */
 MDS_API int mds_rdf_stats_get(mds_rdf_t* h, mds_rdf_stats* out);

@@ -30,7 +30,7 @@ LAYOUT_ATOM_MAJOR = 1  # (n_atoms, n_frames, 3) — the reference's positions_te
 
 EXPORTED_SYMBOLS = (
     "mds_rdf_create", "mds_rdf_destroy", "mds_rdf_submit", "mds_rdf_submit_device",
-    "mds_rdf_counts", "mds_rdf_device_counts", "mds_rdf_join", "mds_rdf_wait", "mds_rdf_synchronize",
+    "mds_rdf_counts", "mds_rdf_device_counts", "mds_rdf_join", "mds_rdf_wait", "mds_rdf_wait_host_copies", "mds_rdf_synchronize",
     "mds_rdf_reset",
     "mds_rdf_stats_get", "mds_rdf_threshold_table", "mds_rdf_build_threshold_table",
     "mds_bench_shared_atomics",
@@ -122,6 +122,7 @@ def load() -> ctypes.CDLL:
     lib.mds_rdf_device_counts.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     lib.mds_rdf_join.argtypes = [vp, vp]
     lib.mds_rdf_wait.argtypes = [vp, vp]
+    lib.mds_rdf_wait_host_copies.argtypes = [vp]
     lib.mds_rdf_synchronize.argtypes = [vp]
     lib.mds_rdf_reset.argtypes = [vp]
     lib.mds_rdf_stats_get.argtypes = [vp, ctypes.POINTER(_Stats)]
@@ -280,6 +281,11 @@ class RDFHandle:
             import torch
             stream = torch.cuda.current_stream(self.device).cuda_stream
         _check(self._lib.mds_rdf_wait(self._h, ctypes.c_void_p(stream)), "mds_rdf_wait")
+
+    def wait_host_copies(self):
+        """Block until the host buffers passed to :meth:`submit` so far may be overwritten."""
+        _check(self._lib.mds_rdf_wait_host_copies(self._h), "mds_rdf_wait_host_copies")
+        self._keepalive = []
 
     def synchronize(self):
         _check(self._lib.mds_rdf_synchronize(self._h), "mds_rdf_synchronize")

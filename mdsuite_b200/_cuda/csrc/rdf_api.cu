@@ -609,6 +609,13 @@ int mds_rdf_wait(mds_rdf_t* h, void* stream) {
   return MDS_OK;
 }
 
+int mds_rdf_wait_host_copies(mds_rdf_t* h) {
+  if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_wait_host_copies: handle is NULL");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->s_copy));
+  return MDS_OK;
+}
+
 int mds_rdf_synchronize(mds_rdf_t* h) {
   if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_synchronize: handle is NULL");
   DeviceGuard guard(h->device);

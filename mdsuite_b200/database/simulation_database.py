@@ -1,0 +1,215 @@
+"""
+Trajectory store feeding the RDF frame batcher.
+
+The reference keeps one HDF5 dataset per ``<species>/<property>`` with shape
+(n_particles, n_configurations, 3), gzip-compressed float32, time on axis 1
+(mdsuite/database/simulation_database.py:333-378, :449-499), so reading ONE configuration touches
+every chunk (SURVEY.md hard part H4).  Neither h5py nor libhdf5 exists in this image, and the GPU
+path wants whole frames, so the native store here is FRAME-MAJOR: one raw little-endian float32
+file per dataset with shape (n_configurations, n_particles, n_dims), memory-mapped for reading,
+appended on ingest, next to a small JSON index.  A reference ``database.hdf5`` is read through
+h5py when h5py is importable (same ``load_frames`` interface, transposed on the fly).
+"""
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+
+@dataclass
+class PropertyInfo:
+    """simulation_database.py:43-62."""
+    name: str
+    n_dims: int
+
+
+@dataclass
+class SpeciesInfo:
+    """simulation_database.py:65-99."""
+    name: str
+    n_particles: int
+    properties: List[PropertyInfo] = field(default_factory=list)
+    mass: float = None
+    charge: float = 0
+
+
+@dataclass
+class TrajectoryMetadata:
+    """simulation_database.py:130-169."""
+    n_configurations: int
+    species_list: List[SpeciesInfo]
+    box_l: list = None
+    sample_rate: int = 1
+    temperature: float = None
+    simulation_time_step: float = None
+
+
+@dataclass
+class TrajectoryChunkData:
+    """A chunk of configurations handed from a file reader to the store
+    (simulation_database.py:172-227): ``data[species][property]`` is (chunk, n_particles, n_dims)."""
+    species_list: List[SpeciesInfo]
+    chunk_size: int
+    data: Dict[str, Dict[str, np.ndarray]] = field(default_factory=dict)
+
+    def add_data(self, array: np.ndarray, config_idx: int, species_name: str, property_name: str):
+        sp = self.data.setdefault(species_name, {})
+        if property_name not in sp:
+            info = next(s for s in self.species_list if s.name == species_name)
+            dims = next(p.n_dims for p in info.properties if p.name == property_name)
+            sp[property_name] = np.zeros((self.chunk_size, info.n_particles, dims), dtype=np.float32)
+        n = array.shape[0]
+        sp[property_name][config_idx:config_idx + n] = array
+
+
+def _file_name(path: str) -> str:
+    return path.replace("/", "__") + ".f32"
+
+
+class Database:
+    """Frame-major trajectory store rooted at ``<experiment>/database/``."""
+
+    def __init__(self, root: str):
+        self.root = root
+        self.index_path = os.path.join(root, "index.json")
+        os.makedirs(root, exist_ok=True)
+        if os.path.exists(self.index_path):
+            with open(self.index_path) as fh:
+                self.index = json.load(fh)
+        else:
+            self.index = {"layout": "frame_major_f32", "n_configurations": 0, "datasets": {}}
+        self._maps: Dict[str, np.memmap] = {}
+
+    # ---- writing ------------------------------------------------------------------------
+    def _save_index(self):
+        tmp = self.index_path + ".tmp"
+        with open(tmp, "w") as fh:
+            json.dump(self.index, fh)
+        os.replace(tmp, self.index_path)
+
+    def initialize_database(self, species_list: Sequence[SpeciesInfo]):
+        """simulation_database.py:420-443."""
+        for sp in species_list:
+            for prop in sp.properties:
+                self.add_dataset(f"{sp.name}/{prop.name}", sp.n_particles, prop.n_dims)
+
+    def add_dataset(self, path: str, n_particles: int, n_dims: int = 3):
+        """simulation_database.py:449-499 (no compression: the GPU path is fed raw frames)."""
+        if path in self.index["datasets"]:
+            return
+        self.index["datasets"][path] = {"n_particles": int(n_particles), "n_dims": int(n_dims),
+                                        "file": _file_name(path), "n_configurations": 0}
+        open(os.path.join(self.root, _file_name(path)), "ab").close()
+        self._save_index()
+
+    def add_data(self, chunk: TrajectoryChunkData):
+        """Append a chunk of configurations (simulation_database.py:333-378).  The reference swaps
+        axes into its atom-major layout here (:365-368); this store keeps frames contiguous."""
+        self._maps.clear()
+        for species_name, props in chunk.data.items():
+            for prop_name, arr in props.items():
+                path = f"{species_name}/{prop_name}"
+                ds = self.index["datasets"][path]
+                a = np.ascontiguousarray(arr, dtype=np.float32)
+                if a.shape[1:] != (ds["n_particles"], ds["n_dims"]):
+                    raise ValueError(f"{path}: chunk shape {a.shape} does not match the dataset")
+                with open(os.path.join(self.root, ds["file"]), "ab") as fh:
+                    a.tofile(fh)
+                ds["n_configurations"] += int(a.shape[0])
+        self.index["n_configurations"] = min(
+            (d["n_configurations"] for d in self.index["datasets"].values()), default=0)
+        self._save_index()
+
+    # ---- reading ------------------------------------------------------------------------
+    def check_existence(self, path: str) -> bool:
+        return path in self.index["datasets"]
+
+    def get_data_size(self, path: str) -> tuple:
+        """(n_particles, n_configurations, n_bytes) — simulation_database.py:668-690."""
+        ds = self.index["datasets"][path]
+        n_bytes = ds["n_particles"] * ds["n_configurations"] * ds["n_dims"] * 4
+        return ds["n_particles"], ds["n_configurations"], n_bytes
+
+    def _map(self, path: str) -> np.memmap:
+        if path not in self._maps:
+            ds = self.index["datasets"][path]
+            shape = (ds["n_configurations"], ds["n_particles"], ds["n_dims"])
+            self._maps[path] = np.memmap(os.path.join(self.root, ds["file"]), dtype=np.float32,
+                                         mode="r", shape=shape)
+        return self._maps[path]
+
+    def load_frames(self, path: str, frames: Sequence[int], out: np.ndarray = None,
+                    atom_selection=None) -> np.ndarray:
+        """(len(frames), n_selected, n_dims) float32 for the given configuration indices, written
+        into ``out`` (e.g. a pinned staging buffer slice) when given."""
+        mm = self._map(path)
+        frames = np.asarray(frames, dtype=np.int64)
+        contiguous = len(frames) > 0 and np.all(np.diff(frames) == 1)
+        src = mm[frames[0]:frames[-1] + 1] if contiguous else mm[frames]
+        if atom_selection is not None and not (isinstance(atom_selection, slice)
+                                               and atom_selection == slice(None)):
+            src = src[:, atom_selection]
+        if out is None:
+            return np.array(src, dtype=np.float32)
+        np.copyto(out, src)
+        return out
+
+    def load_data(self, path_list: Sequence[str], select_slice=np.s_[:]) -> Dict[str, np.ndarray]:
+        """Reference-shaped read (simulation_database.py:594-639): ``select_slice`` indexes
+        (atoms, configurations) and the result is atom-major (n_atoms, n_configurations, 3)."""
+        if not isinstance(select_slice, tuple):
+            select_slice = (select_slice, np.s_[:])
+        atoms_sel, conf_sel = (list(select_slice) + [np.s_[:]])[:2]
+        out = {}
+        for path in path_list:
+            mm = self._map(path)
+            frames = np.arange(mm.shape[0])[conf_sel]
+            data = np.array(mm[frames], dtype=np.float32)[:, atoms_sel]
+            out[path] = np.ascontiguousarray(data.transpose(1, 0, 2))
+        return out
+
+
+class HDF5Database:
+    """Reader for a reference ``database.hdf5`` (atom-major, gzip); needs h5py."""
+
+    def __init__(self, path: str):
+        try:
+            import h5py  # noqa: F401
+        except ImportError as exc:
+            raise ImportError("reading an MDSuite database.hdf5 needs h5py, which is not installed; "
+                              "re-ingest the trajectory into the native frame store") from exc
+        self.path = path
+
+    def check_existence(self, path: str) -> bool:
+        import h5py
+        with h5py.File(self.path, "r") as db:
+            return path in db
+
+    def get_data_size(self, path: str) -> tuple:
+        import h5py
+        with h5py.File(self.path, "r") as db:
+            ds = db[path]
+            return ds.shape[0], ds.shape[1], int(np.prod(ds.shape)) * ds.dtype.itemsize
+
+    def load_frames(self, path: str, frames: Sequence[int], out: np.ndarray = None,
+                    atom_selection=None) -> np.ndarray:
+        import h5py
+        frames = np.asarray(frames, dtype=np.int64)
+        with h5py.File(self.path, "r") as db:
+            ds = db[path]
+            if len(frames) and np.all(np.diff(frames) == 1):
+                data = ds[:, frames[0]:frames[-1] + 1]
+            else:
+                data = ds[:, list(frames)]
+        data = np.asarray(data, dtype=np.float32)
+        if atom_selection is not None:
+            data = data[atom_selection]
+        data = data.transpose(1, 0, 2)
+        if out is None:
+            return np.ascontiguousarray(data)
+        np.copyto(out, data)
+        return out

@@ -1,0 +1,54 @@
+"""
+Multi-GPU plumbing: configurations are the shard unit.
+
+The reference already sums per-batch histograms (calculators/radial_distribution_function.py:
+884-885) and splits the sampled configurations into batches with ``np.array_split`` (:594); here
+the same primitive assigns rank g block g, and ONE collective — an allreduce(sum) of the
+[n_pairs][nbins] 64-bit accumulator, <= 120 KB — combines the partial histograms over
+NVLink/NVSwitch.  There is no other exchange on this path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_configurations(sample_configurations, world_size: int, rank: int) -> np.ndarray:
+    """Block ``rank`` of ``np.array_split(sample_configurations, world_size)`` (may be empty)."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank {rank} / world size {world_size}")
+    return np.array_split(np.asarray(sample_configurations), world_size)[rank]
+
+
+def counts_as_tensor(handle):
+    """The handle's device accumulator viewed as an int64 torch tensor (no copy).  uint64 and
+    int64 sums are the same bits; NCCL has no uint64 reduction in torch."""
+    import torch
+    ptr, _stream = handle.device_counts()
+
+    class _Wrap:
+        __cuda_array_interface__ = {"shape": (handle.n_pairs, handle.nbins), "typestr": "<i8",
+                                    "data": (ptr, False), "version": 3, "strides": None}
+    return torch.as_tensor(_Wrap(), device=f"cuda:{handle.device}")
+
+
+def allreduce_counts(handle, group=None):
+    """In-place sum of the per-GPU histograms over the process group (one NCCL allreduce), ordered
+    after the handle's kernels and before any later work on the handle."""
+    import torch
+    import torch.distributed as dist
+    t = counts_as_tensor(handle)
+    with torch.cuda.device(handle.device):
+        handle.join()  # torch's stream waits for the kernels
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        handle.wait()  # the library's stream waits for the collective
+    return t
+
+
+def allreduce_host_counts(counts: np.ndarray, group=None) -> np.ndarray:
+    """Same reduction for host-resident histograms (gloo); used by CPU tests of the sharding
+    logic and as the path for process groups without a CUDA backend."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(counts).view(np.int64).copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.numpy().view(np.uint64)

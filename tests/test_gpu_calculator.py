@@ -1,0 +1,64 @@
+"""GPU end-to-end: LAMMPS dump -> Project/Experiment -> run.RadialDistributionFunction on the B200,
+against the oracle's histograms and the reference normalisation (configs[0] of BASELINE.json)."""
+import numpy as np
+import pytest
+
+import mdsuite_b200 as mds
+from mdsuite_b200 import synthetic
+from oracle import c_oracle, rdf_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cfg1_nacl_1000_atoms_100_configurations_through_the_calculator(tmp_path):
+    sysm = synthetic.nacl_melt(5, 100, seed=1)
+    dump = tmp_path / "nacl_1000.lammpstraj"
+    synthetic.write_lammps_dump(sysm, str(dump))
+    project = mds.Project("cfg1", storage_path=str(tmp_path))
+    project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal",
+                           simulation_data=str(dump))
+    exp = project.experiments.NaCl
+    calc_out = exp.run.RadialDistributionFunction(number_of_configurations=100, number_of_bins=500,
+                                                  cutoff=10.0, plot=True, frames_per_batch=32)
+    counts, evaluated = c_oracle.rdf_counts_c(sysm.positions, sysm.counts, sysm.box, 10.0, 500,
+                                              layout=c_oracle.FRAME_MAJOR)
+    want = rdf_oracle.normalise(counts, ["Na", "Cl"], sysm.counts, sysm.box, 10.0, 100)
+    assert calc_out.keys() == ["Na_Na", "Na_Cl", "Cl_Cl"]
+    for key in calc_out.keys():
+        got_y, want_y = np.array(calc_out[key]["y"]), np.array(want[key]["y"])
+        assert np.isnan(got_y[0]) or np.isinf(got_y[0])
+        assert np.array_equal(np.isfinite(got_y), np.isfinite(want_y))
+        # north star: g(r) within 1e-6 relative for indices >= 1 (integer counts are bit-exact, so
+        # this is float64 normalisation noise only)
+        assert np.allclose(got_y[1:], want_y[1:], rtol=1e-6, atol=0)
+        assert np.allclose(calc_out[key]["x"], want[key]["x"], rtol=1e-15)
+    # default arguments: cutoff = L/2 - 0.1, bins = int(cutoff / 0.01), every stored configuration
+    second = exp.run.RadialDistributionFunction(number_of_configurations=50, plot=False)
+    cutoff = sysm.box[0] / 2 - 0.1
+    nbins = int(cutoff / 0.01)
+    frames = np.linspace(0, 99, 50, dtype=int)
+    counts, _ = c_oracle.rdf_counts_c(sysm.positions[frames], sysm.counts, sysm.box, cutoff, nbins,
+                                      layout=c_oracle.FRAME_MAJOR)
+    want = rdf_oracle.normalise(counts, ["Na", "Cl"], sysm.counts, sysm.box, cutoff, 50)
+    assert np.allclose(np.array(second["Cl_Cl"]["y"])[1:], np.array(want["Cl_Cl"]["y"])[1:], rtol=1e-6)
+
+
+def test_corrected_mode_ideal_gas_g_of_r_is_one(tmp_path):
+    """cfg5 acceptance: uniform random points, parity=False, g(r) = 1 within Poisson noise."""
+    sysm = synthetic.ideal_gas(20000, 8, seed=5, box_length=100.0)
+    project = mds.Project("cfg5", storage_path=str(tmp_path))
+    exp = project.add_experiment("gas")
+    exp.add_positions(sysm.positions, sysm.species, sysm.box)
+    nbins, cutoff = 200, 25.0
+    comp = exp.run.RadialDistributionFunction(number_of_configurations=8, number_of_bins=nbins,
+                                              cutoff=cutoff, plot=False, parity=False)
+    y = np.array(comp["X_X"]["y"])
+    k = np.arange(nbins)
+    dr = cutoff / nbins
+    shell_exact = 4 * np.pi / 3 * (((k + 1) * dr) ** 3 - (k * dr) ** 3)
+    shell_ref = 4 * np.pi * np.linspace(0, cutoff, nbins) ** 2 * dr
+    n = 20000
+    g = y[5:] * shell_ref[5:] / shell_exact[5:] * (n / (n - 1))
+    expected_pairs = 8 * n * (n - 1) / 2 * shell_exact[5:] / 100.0 ** 3
+    sigma = 1.0 / np.sqrt(expected_pairs)
+    assert np.all(np.abs(g - 1.0) < 5 * sigma + 1e-4)
