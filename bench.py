@@ -234,6 +234,9 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout; the
+        # contract is ONE JSON line there
+        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     sysm, cutoff, nbins, desc = make_workload(args.workload, rank, args.frames)
