@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MDS_RDF_ABI_VERSION 1
+#define MDS_RDF_ABI_VERSION 2
 
 #if defined(MDS_BUILD) && defined(__GNUC__)
 #define MDS_API __attribute__((visibility("default")))
@@ -60,7 +60,8 @@ typedef enum mds_status {
 #define MDS_RDF_PARITY_SKIP_FIRST 0x1u /* reproduce quirk Q1: the atom at each species' offset is
                                           never a row nor a column (strict '>' at :637-638) */
 #define MDS_RDF_PATH_ALLPAIRS 0x2u     /* force the tiled all-pairs kernel */
-#define MDS_RDF_PATH_CELLLIST 0x4u     /* force the cell-list kernel (needs cutoff <= box/3) */
+#define MDS_RDF_PATH_CELLLIST 0x4u     /* force the cell-list kernel (needs cutoff <= box/3.003;
+                                          MDS_ERR_UNSUPPORTED otherwise) */
 /* neither PATH bit set: the library picks per handle from n_atoms, box and cutoff */
 
 /* layouts of the xyz argument (float32) */
@@ -98,6 +99,9 @@ typedef struct mds_rdf_stats {
   float pair_kernel_ms;        /* sum of pair-kernel launch durations since the previous stats_get */
   int32_t pair_kernel_launches; /* pair-kernel launches since the previous stats_get */
   int32_t dense;               /* 1: branch-free binning (most pairs inside the cutoff) */
+  int32_t frames_far;          /* cell path: frames with a coordinate beyond 8 box lengths, which
+                                  were handed to the all-pairs kernel */
+  int32_t cells[3];            /* cell path: cells per dimension (0 on the all-pairs path) */
   int32_t reserved;
 } mds_rdf_stats;
 

@@ -20,7 +20,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmds_rdf.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MDS_OK = 0
 PARITY_SKIP_FIRST = 0x1
 PATH_ALLPAIRS = 0x2
@@ -75,6 +75,8 @@ class _Stats(ctypes.Structure):
         ("pair_kernel_ms", ctypes.c_float),
         ("pair_kernel_launches", ctypes.c_int32),
         ("dense", ctypes.c_int32),
+        ("frames_far", ctypes.c_int32),
+        ("cells", ctypes.c_int32 * 3),
         ("reserved", ctypes.c_int32),
     ]
 
@@ -97,6 +99,12 @@ class RDFStats:
     pair_kernel_ms: float
     pair_kernel_launches: int
     dense: int
+    frames_far: int = 0
+    cells: tuple = (0, 0, 0)
+
+    @property
+    def path_name(self) -> str:
+        return "celllist" if self.path == PATH_CELLLIST else "allpairs"
 
 
 _lib = None
@@ -316,7 +324,8 @@ class RDFHandle:
         return RDFStats(st.path, st.frames, st.pairs_evaluated, st.pairs_allpairs_equiv,
                         st.pairs_binned, st.frames_general_minimage, st.kernel_launches,
                         st.kernel_ms, st.submit_ms, st.n_pairs, st.nbins, st.sm_count, st.variant,
-                        st.pair_kernel_ms, st.pair_kernel_launches, st.dense)
+                        st.pair_kernel_ms, st.pair_kernel_launches, st.dense, st.frames_far,
+                        tuple(st.cells))
 
     def threshold_table(self):
         """(edges[0..nbins] float32, s_cut): the squared-distance thresholds the kernels use."""

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
     for (int k = tid; k < n_edges; k += THREADS) s_edges[k] = p.edges[k];
     for (int k = tid; k < n_hist; k += THREADS) s_hist[k] = 0u;
   }
+  if (p.gate && *p.gate == 0ull) return;  // nothing was handed over by the cell path
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
     // big items first: consecutive indices walk the frames of one item
     const PairItem it = p.items[idx / p.n_frames];
     const int frame = (int)(idx % p.n_frames);
+    if (p.frame_need_bits && !(p.frame_flags[frame] & p.frame_need_bits)) continue;  // CTA-uniform
     const float4* __restrict__ fpos = p.pos + (long long)frame * p.frame_stride;
     const bool fast = ((p.frame_flags[frame] & 3u) != 3u);  // see rdf_pack.cu
 

@@ -105,6 +105,10 @@ struct mds_rdf {
   int pair_group = 1;  // species pairs per launch (shared-memory capacity)
   bool hist_in_smem = true;
   bool dense = true;  // expected in-cutoff fraction is high: predicated binning
+  int path = MDS_RDF_PATH_ALLPAIRS;
+  mds::CellGrid grid = {0, 0, 0, 0, {0, 0, 0}};
+  int64_t off_stride = 0;         // uint32 entries per frame of the cell-offset table
+  uint32_t flush_threshold = 1u << 30;
   // device state
   int32_t* d_src_index = nullptr;
   int32_t* d_species = nullptr;
@@ -117,6 +121,13 @@ struct mds_rdf {
   float4* d_packed[2] = {nullptr, nullptr};
   uint32_t* d_flags[2] = {nullptr, nullptr};
   float* d_raw[2] = {nullptr, nullptr};  // staging for host submits (lazy)
+  // cell-list path only
+  float4* d_sorted[2] = {nullptr, nullptr};
+  uint32_t* d_cell_off[2] = {nullptr, nullptr};
+  int2* d_pair_ab = nullptr;
+  unsigned long long* d_work64 = nullptr;    // ring of 64-bit work counters
+  unsigned long long* d_evaluated = nullptr; // candidate pairs distance-tested by the cell kernel
+  unsigned long long* d_batch_far = nullptr; // [2] far frames of the batch in each buffer
   size_t raw_bytes = 0;
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   cudaEvent_t ev_raw_ready[2] = {nullptr, nullptr};  // H2D of staging buffer done
@@ -219,10 +230,76 @@ int upload_items(mds_rdf* h) {
   return MDS_OK;
 }
 
-// pack one batch that already sits in device memory, then run the pair kernels on it
-int process_batch(mds_rdf* h, const float* d_xyz, int layout, int64_t frame0, int64_t n_frames,
-                  int64_t n_frames_total, int buf) {
-  CUDA_TRY(cudaMemsetAsync(h->d_flags[buf], 0, sizeof(uint32_t) * (size_t)n_frames, h->s_compute));
+mds::AllPairsParams allpairs_params(mds_rdf* h, int buf, int64_t n_frames, int p0, int pc) {
+  mds::AllPairsParams ap;
+  ap.pos = h->d_packed[buf];
+  ap.frame_stride = h->frame_stride;
+  ap.n_frames = (int32_t)n_frames;
+  ap.edges = h->d_edges;
+  ap.frame_flags = h->d_flags[buf];
+  ap.counts = h->d_counts;
+  ap.nbins = h->nbins;
+  ap.pair_lo = p0;
+  ap.pair_cnt = pc;
+  ap.hist_in_smem = h->hist_in_smem ? 1 : 0;
+  ap.s_cut = h->s_cut;
+  ap.inv_step = h->inv_step;
+  ap.dense = h->dense ? 1 : 0;
+  for (int k = 0; k < 3; ++k) ap.box[k] = h->box[k];
+  ap.frame_need_bits = 0;
+  ap.gate = nullptr;
+  ap.items = nullptr;
+  ap.n_items = 0;
+  ap.work_counter = nullptr;
+  return ap;
+}
+
+// item sub-range of a pair group (items are grouped per pair group at create time)
+bool item_range(const mds_rdf* h, int p0, int pc, int* first, int* count) {
+  int lo = -1, hi = -1;
+  for (int i = 0; i < (int)h->items.size(); ++i)
+    if (h->items[i].pair >= p0 && h->items[i].pair < p0 + pc) {
+      if (lo < 0) lo = i;
+      hi = i;
+    }
+  if (lo < 0) return false;
+  *first = lo;
+  *count = hi - lo + 1;
+  return true;
+}
+
+int next_work_slot(mds_rdf* h) {
+  if (h->work_slot >= WORK_RING) {
+    cudaError_t e = cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int) * WORK_RING, h->s_compute);
+    if (e == cudaSuccess && h->d_work64)
+      e = cudaMemsetAsync(h->d_work64, 0, sizeof(unsigned long long) * WORK_RING, h->s_compute);
+    if (e != cudaSuccess) return -1;
+    h->work_slot = 0;
+  }
+  return h->work_slot++;
+}
+
+int timed_launch_begin(mds_rdf* h) {
+  if ((int)h->pk_events.size() < 2 * (h->pk_used + 1)) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    h->pk_events.push_back(a);
+    h->pk_events.push_back(b);
+  }
+  CUDA_TRY(cudaEventRecord(h->pk_events[2 * h->pk_used], h->s_compute));
+  return MDS_OK;
+}
+
+int timed_launch_end(mds_rdf* h) {
+  CUDA_TRY(cudaEventRecord(h->pk_events[2 * h->pk_used + 1], h->s_compute));
+  h->pk_used += 1;
+  h->launches += 1;
+  return MDS_OK;
+}
+
+mds::PackParams pack_params(mds_rdf* h, const float* d_xyz, int layout, int64_t frame0,
+                            int64_t n_frames, int64_t n_frames_total, int buf) {
   mds::PackParams pp;
   pp.xyz = d_xyz;
   pp.layout = layout;
@@ -237,58 +314,105 @@ int process_batch(mds_rdf* h, const float* d_xyz, int layout, int64_t frame0, in
   pp.frame_stride = h->frame_stride;
   pp.frame_flags = h->d_flags[buf];
   for (int k = 0; k < 3; ++k) pp.box[k] = h->box[k];
+  return pp;
+}
+
+// all-pairs path: pack one batch that already sits in device memory, then run the pair kernels
+int process_batch_allpairs(mds_rdf* h, const float* d_xyz, int layout, int64_t frame0,
+                           int64_t n_frames, int64_t n_frames_total, int buf) {
+  CUDA_TRY(cudaMemsetAsync(h->d_flags[buf], 0, sizeof(uint32_t) * (size_t)n_frames, h->s_compute));
+  const mds::PackParams pp = pack_params(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf);
   CUDA_TRY(mds::launch_pack(pp, h->s_compute));
-  CUDA_TRY(mds::launch_count_general(h->d_flags[buf], (int)n_frames, h->d_general, h->s_compute));
+  CUDA_TRY(mds::launch_count_general(h->d_flags[buf], (int)n_frames, h->d_general, nullptr,
+                                     h->s_compute));
   h->launches += 2;
   if (h->items.empty()) return MDS_OK;
-
   for (int p0 = 0; p0 < h->n_pairs; p0 += h->pair_group) {
     const int pc = std::min(h->pair_group, h->n_pairs - p0);
-    // items are shared by all groups; a launch only sees the ones of its pairs
-    mds::AllPairsParams ap;
-    ap.pos = h->d_packed[buf];
-    ap.frame_stride = h->frame_stride;
-    ap.n_frames = (int32_t)n_frames;
-    ap.edges = h->d_edges;
-    ap.frame_flags = h->d_flags[buf];
-    ap.counts = h->d_counts;
-    ap.nbins = h->nbins;
-    ap.pair_lo = p0;
-    ap.pair_cnt = pc;
-    ap.hist_in_smem = h->hist_in_smem ? 1 : 0;
-    ap.s_cut = h->s_cut;
-    ap.inv_step = h->inv_step;
-    ap.dense = h->dense ? 1 : 0;
-    for (int k = 0; k < 3; ++k) ap.box[k] = h->box[k];
-    // item sub-range of this pair group (items are regrouped per pair group at create time)
-    int first = -1, last = -1;
-    for (int i = 0; i < (int)h->items.size(); ++i)
-      if (h->items[i].pair >= p0 && h->items[i].pair < p0 + pc) {
-        if (first < 0) first = i;
-        last = i;
-      }
-    if (first < 0) continue;
+    mds::AllPairsParams ap = allpairs_params(h, buf, n_frames, p0, pc);
+    int first = 0, count = 0;
+    if (!item_range(h, p0, pc, &first, &count)) continue;
     ap.items = h->d_items + first;
-    ap.n_items = last - first + 1;
-    if (h->work_slot >= WORK_RING) {
-      CUDA_TRY(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int) * WORK_RING, h->s_compute));
-      h->work_slot = 0;
-    }
-    ap.work_counter = h->d_work + h->work_slot++;
-    if ((int)h->pk_events.size() < 2 * (h->pk_used + 1)) {
-      cudaEvent_t a = nullptr, b = nullptr;
-      CUDA_TRY(cudaEventCreate(&a));
-      CUDA_TRY(cudaEventCreate(&b));
-      h->pk_events.push_back(a);
-      h->pk_events.push_back(b);
-    }
-    CUDA_TRY(cudaEventRecord(h->pk_events[2 * h->pk_used], h->s_compute));
+    ap.n_items = count;
+    const int slot = next_work_slot(h);
+    if (slot < 0) return fail(MDS_ERR_CUDA, "work-counter reset failed");
+    ap.work_counter = h->d_work + slot;
+    int rc = timed_launch_begin(h);
+    if (rc != MDS_OK) return rc;
     CUDA_TRY(mds::launch_allpairs(ap, h->variant, h->sm_count, h->s_compute, nullptr));
-    CUDA_TRY(cudaEventRecord(h->pk_events[2 * h->pk_used + 1], h->s_compute));
-    h->pk_used += 1;
+    rc = timed_launch_end(h);
+    if (rc != MDS_OK) return rc;
+  }
+  return MDS_OK;
+}
+
+// cell-list path: pack + counting sort by (species, cell), then the cell pair kernel; frames the
+// pack kernel flagged MDS_FRAME_FAR go through the all-pairs kernel (gated: normally a no-op)
+int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t frame0,
+                        int64_t n_frames, int64_t n_frames_total, int buf) {
+  CUDA_TRY(cudaMemsetAsync(h->d_flags[buf], 0, sizeof(uint32_t) * (size_t)n_frames, h->s_compute));
+  const mds::PackParams pp = pack_params(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf);
+  CUDA_TRY(mds::launch_cell_build(pp, h->grid, h->n_species, h->d_cell_off[buf], h->off_stride,
+                                  h->d_sorted[buf], h->s_compute));
+  CUDA_TRY(mds::launch_count_general(h->d_flags[buf], (int)n_frames, h->d_general,
+                                     h->d_batch_far + buf, h->s_compute));
+  h->launches += 4;
+  if (h->n_packed == 0) return MDS_OK;
+  for (int p0 = 0; p0 < h->n_pairs; p0 += h->pair_group) {
+    const int pc = std::min(h->pair_group, h->n_pairs - p0);
+    mds::CellsParams cp;
+    cp.spos = h->d_sorted[buf];
+    cp.frame_stride = h->frame_stride;
+    cp.n_frames = (int32_t)n_frames;
+    cp.cell_off = h->d_cell_off[buf];
+    cp.off_stride = h->off_stride;
+    cp.frame_flags = h->d_flags[buf];
+    cp.nx = h->grid.nx; cp.ny = h->grid.ny; cp.nz = h->grid.nz; cp.nc = h->grid.nc;
+    cp.pair_ab = h->d_pair_ab;
+    cp.edges = h->d_edges;
+    cp.counts = h->d_counts;
+    cp.evaluated = h->d_evaluated;
+    cp.nbins = h->nbins;
+    cp.pair_lo = p0;
+    cp.pair_cnt = pc;
+    cp.hist_in_smem = h->hist_in_smem ? 1 : 0;
+    cp.s_cut = h->s_cut;
+    cp.inv_step = h->inv_step;
+    for (int k = 0; k < 3; ++k) cp.box[k] = h->box[k];
+    cp.flush_threshold = h->flush_threshold;
+    const int slot = next_work_slot(h);
+    if (slot < 0) return fail(MDS_ERR_CUDA, "work-counter reset failed");
+    cp.work_counter = h->d_work64 + slot;
+    int rc = timed_launch_begin(h);
+    if (rc != MDS_OK) return rc;
+    CUDA_TRY(mds::launch_cells(cp, h->sm_count, h->s_compute, nullptr));
+    rc = timed_launch_end(h);
+    if (rc != MDS_OK) return rc;
+  }
+  if (h->items.empty()) return MDS_OK;
+  for (int p0 = 0; p0 < h->n_pairs; p0 += h->pair_group) {
+    const int pc = std::min(h->pair_group, h->n_pairs - p0);
+    mds::AllPairsParams ap = allpairs_params(h, buf, n_frames, p0, pc);
+    int first = 0, count = 0;
+    if (!item_range(h, p0, pc, &first, &count)) continue;
+    ap.items = h->d_items + first;
+    ap.n_items = count;
+    ap.frame_need_bits = mds::MDS_FRAME_FAR;
+    ap.gate = h->d_batch_far + buf;
+    const int slot = next_work_slot(h);
+    if (slot < 0) return fail(MDS_ERR_CUDA, "work-counter reset failed");
+    ap.work_counter = h->d_work + slot;
+    CUDA_TRY(mds::launch_allpairs(ap, h->variant, h->sm_count, h->s_compute, nullptr));
     h->launches += 1;
   }
   return MDS_OK;
+}
+
+int process_batch(mds_rdf* h, const float* d_xyz, int layout, int64_t frame0, int64_t n_frames,
+                  int64_t n_frames_total, int buf) {
+  return h->path == MDS_RDF_PATH_CELLLIST
+             ? process_batch_cells(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf)
+             : process_batch_allpairs(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf);
 }
 
 }  // namespace
@@ -317,8 +441,6 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
       return fail(MDS_ERR_INVALID, "mds_rdf_create: box[%d] must be finite and > 0", k);
   if ((cfg->flags & MDS_RDF_PATH_ALLPAIRS) && (cfg->flags & MDS_RDF_PATH_CELLLIST))
     return fail(MDS_ERR_INVALID, "mds_rdf_create: both PATH flags set");
-  if (cfg->flags & MDS_RDF_PATH_CELLLIST)
-    return fail(MDS_ERR_UNSUPPORTED, "mds_rdf_create: cell-list path not built yet");
   int64_t n_atoms = 0;
   for (int s = 0; s < cfg->n_species; ++s) {
     if (cfg->counts[s] < 0) return fail(MDS_ERR_INVALID, "mds_rdf_create: counts[%d] < 0", s);
@@ -388,16 +510,58 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   build_threshold_table(h->cutoff, h->nbins, h->edges, h->s_cut);
   h->inv_step = (float)((double)h->nbins / (double)h->cutoff * (double)mds::kBinGuessBias);
 
+  // ---- path: all-pairs tiles or cell list ------------------------------------------------
+  // Cell width >= 1.001 x cutoff, at least 3 cells per dimension so that the 27
+  // neighbours of a cell are distinct, at most 128 per dimension.
+  {
+    int n[3];
+    bool cell_ok = true;
+    for (int k = 0; k < 3; ++k) {
+      const double w_min = (double)h->cutoff * 1.001;
+      n[k] = (int)std::min(128.0, std::floor((double)h->box[k] / w_min));
+      if (n[k] < 3) cell_ok = false;
+    }
+    const long long nc = cell_ok ? (long long)n[0] * n[1] * n[2] : 0;
+    const bool forced_cells = (cfg->flags & MDS_RDF_PATH_CELLLIST) != 0;
+    const bool forced_all = (cfg->flags & MDS_RDF_PATH_ALLPAIRS) != 0;
+    if (forced_cells && !cell_ok) {
+      delete h;
+      return fail(MDS_ERR_UNSUPPORTED,
+                  "mds_rdf_create: cell-list path needs cutoff <= box / 3.003 in every dimension "
+                  "(cutoff %g, box %g %g %g)", (double)cfg->cutoff, (double)cfg->box[0],
+                  (double)cfg->box[1], (double)cfg->box[2]);
+    }
+    // the cell kernel tests ~27/nc of all pairs at roughly half the all-pairs kernel's rate
+    const bool auto_cells = cell_ok && nc >= 64 && h->n_packed >= 1024;
+    h->path = (forced_cells || (!forced_all && auto_cells)) ? MDS_RDF_PATH_CELLLIST
+                                                            : MDS_RDF_PATH_ALLPAIRS;
+    if (h->path == MDS_RDF_PATH_CELLLIST) {
+      h->grid.nx = n[0]; h->grid.ny = n[1]; h->grid.nz = n[2];
+      h->grid.nc = (int)nc;
+      for (int k = 0; k < 3; ++k) h->grid.box[k] = h->box[k];
+      h->off_stride = (((int64_t)h->n_species * nc + 1) + 3) & ~3LL;
+    }
+    if (const char* env = getenv("MDS_RDF_FLUSH_THRESHOLD")) {
+      const long long v = atoll(env);
+      if (v >= 64 && v <= (1LL << 30)) h->flush_threshold = (uint32_t)v;
+    }
+  }
+  const bool cells = h->path == MDS_RDF_PATH_CELLLIST;
+
   // how many species pairs fit in shared memory next to the threshold table
   const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
   const size_t target = std::min<size_t>(smem_cap, 100 * 1024);  // keep >= 2 CTAs per SM if possible
+  auto smem_need = [&](int pairs) {
+    // the all-pairs kernel also serves the cell path's fallback launches: size for the larger
+    const size_t a = mds::allpairs_smem_bytes(h->nbins, pairs, true);
+    return cells ? std::max(a, mds::cells_smem_bytes(h->nbins, pairs, true)) : a;
+  };
   h->hist_in_smem = true;
   h->pair_group = h->n_pairs;
-  while (h->pair_group > 1 && mds::allpairs_smem_bytes(h->nbins, h->pair_group, true) > target)
-    --h->pair_group;
-  if (mds::allpairs_smem_bytes(h->nbins, h->pair_group, true) > target) {
+  while (h->pair_group > 1 && smem_need(h->pair_group) > target) --h->pair_group;
+  if (smem_need(h->pair_group) > target) {
     // a single pair does not fit the 2-CTA budget: allow the full opt-in size, then give up on smem
-    if (mds::allpairs_smem_bytes(h->nbins, 1, true) > smem_cap) {
+    if (smem_need(1) > smem_cap) {
       h->hist_in_smem = false;
       h->pair_group = h->n_pairs;
     }
@@ -413,7 +577,7 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   h->variant = pick_variant(h);
   int bf = cfg->max_frames_in_flight;
   if (bf <= 0) {
-    const int64_t per_frame = h->frame_stride * 16;
+    const int64_t per_frame = h->frame_stride * 16 * (cells ? 2 : 1) + h->off_stride * 4;
     bf = (int)std::min<int64_t>(4096, std::max<int64_t>(1, (128LL << 20) / per_frame));
   }
   h->batch_frames = bf;
@@ -448,8 +612,25 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   const size_t n_counts = (size_t)h->n_pairs * (size_t)h->nbins;
   CREATE_TRY(cudaMalloc(&h->d_counts, n_counts * sizeof(unsigned long long)));
   CREATE_TRY(cudaMemset(h->d_counts, 0, n_counts * sizeof(unsigned long long)));
-  CREATE_TRY(cudaMalloc(&h->d_general, sizeof(unsigned long long)));
-  CREATE_TRY(cudaMemset(h->d_general, 0, sizeof(unsigned long long)));
+  CREATE_TRY(cudaMalloc(&h->d_general, 2 * sizeof(unsigned long long)));
+  CREATE_TRY(cudaMemset(h->d_general, 0, 2 * sizeof(unsigned long long)));
+  if (cells) {
+    std::vector<int2> ab;
+    for (int a = 0; a < h->n_species; ++a)
+      for (int b = a; b < h->n_species; ++b) ab.push_back(make_int2(a, b));
+    CREATE_TRY(cudaMalloc(&h->d_pair_ab, ab.size() * sizeof(int2)));
+    CREATE_TRY(cudaMemcpy(h->d_pair_ab, ab.data(), ab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMalloc(&h->d_work64, sizeof(unsigned long long) * WORK_RING));
+    CREATE_TRY(cudaMemset(h->d_work64, 0, sizeof(unsigned long long) * WORK_RING));
+    CREATE_TRY(cudaMalloc(&h->d_evaluated, sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemset(h->d_evaluated, 0, sizeof(unsigned long long)));
+    CREATE_TRY(cudaMalloc(&h->d_batch_far, 2 * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemset(h->d_batch_far, 0, 2 * sizeof(unsigned long long)));
+    for (int b = 0; b < 2; ++b) {
+      CREATE_TRY(cudaMalloc(&h->d_sorted[b], (size_t)h->frame_stride * 16 * (size_t)bf));
+      CREATE_TRY(cudaMalloc(&h->d_cell_off[b], (size_t)h->off_stride * 4 * (size_t)bf));
+    }
+  }
   CREATE_TRY(cudaMalloc(&h->d_work, sizeof(unsigned int) * WORK_RING));
   CREATE_TRY(cudaMemset(h->d_work, 0, sizeof(unsigned int) * WORK_RING));
   for (int b = 0; b < 2; ++b) {
@@ -487,10 +668,16 @@ void mds_rdf_destroy(mds_rdf_t* h) {
   cudaFree(h->d_counts);
   cudaFree(h->d_general);
   cudaFree(h->d_work);
+  cudaFree(h->d_pair_ab);
+  cudaFree(h->d_work64);
+  cudaFree(h->d_evaluated);
+  cudaFree(h->d_batch_far);
   for (int b = 0; b < 2; ++b) {
     cudaFree(h->d_packed[b]);
     cudaFree(h->d_flags[b]);
     cudaFree(h->d_raw[b]);
+    cudaFree(h->d_sorted[b]);
+    cudaFree(h->d_cell_off[b]);
     if (h->ev_raw_ready[b]) cudaEventDestroy(h->ev_raw_ready[b]);
     if (h->ev_raw_free[b]) cudaEventDestroy(h->ev_raw_free[b]);
   }
@@ -645,7 +832,9 @@ int mds_rdf_reset(mds_rdf_t* h) {
   DeviceGuard guard(h->device);
   const size_t bytes = (size_t)h->n_pairs * (size_t)h->nbins * sizeof(uint64_t);
   CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, bytes, h->s_compute));
-  CUDA_TRY(cudaMemsetAsync(h->d_general, 0, sizeof(unsigned long long), h->s_compute));
+  CUDA_TRY(cudaMemsetAsync(h->d_general, 0, 2 * sizeof(unsigned long long), h->s_compute));
+  if (h->d_evaluated)
+    CUDA_TRY(cudaMemsetAsync(h->d_evaluated, 0, sizeof(unsigned long long), h->s_compute));
   h->frames_done = 0;
   h->launches = 0;
   h->timing_valid = false;
@@ -666,14 +855,21 @@ int mds_rdf_stats_get(mds_rdf_t* h, mds_rdf_stats* out) {
                       cudaMemcpyDeviceToHost));
   double binned = 0;
   for (auto v : host) binned += (double)v;
-  unsigned long long general = 0;
-  CUDA_TRY(cudaMemcpy(&general, h->d_general, sizeof(general), cudaMemcpyDeviceToHost));
-  out->path = MDS_RDF_PATH_ALLPAIRS;
+  unsigned long long general[2] = {0, 0};
+  CUDA_TRY(cudaMemcpy(general, h->d_general, sizeof(general), cudaMemcpyDeviceToHost));
+  out->path = h->path;
   out->frames = h->frames_done;
-  out->pairs_evaluated = h->pairs_per_frame * (double)h->frames_done;
-  out->pairs_allpairs_equiv = out->pairs_evaluated;
+  out->pairs_allpairs_equiv = h->pairs_per_frame * (double)h->frames_done;
+  if (h->path == MDS_RDF_PATH_CELLLIST) {
+    unsigned long long ev = 0;
+    CUDA_TRY(cudaMemcpy(&ev, h->d_evaluated, sizeof(ev), cudaMemcpyDeviceToHost));
+    // candidates tested by the cell kernel + every pair of the frames the all-pairs kernel took
+    out->pairs_evaluated = (double)ev + h->pairs_per_frame * (double)general[1];
+  } else {
+    out->pairs_evaluated = out->pairs_allpairs_equiv;
+  }
   out->pairs_binned = binned;
-  out->frames_general_minimage = (int64_t)general;
+  out->frames_general_minimage = (int64_t)general[0];
   out->kernel_launches = h->launches;
   out->kernel_ms = 0.f;
   out->submit_ms = 0.f;
@@ -694,6 +890,10 @@ int mds_rdf_stats_get(mds_rdf_t* h, mds_rdf_stats* out) {
   }
   h->pk_used = 0;  // "since the previous mds_rdf_stats_get"; survives submit and reset
   out->dense = h->dense ? 1 : 0;
+  out->frames_far = (int32_t)general[1];
+  out->cells[0] = h->grid.nx;
+  out->cells[1] = h->grid.ny;
+  out->cells[2] = h->grid.nz;
   out->reserved = 0;
   return MDS_OK;
 }

@@ -41,7 +41,18 @@ struct AllPairsParams {
   float inv_step;             // float32(nbins / cutoff) * (1 - 2^-20): seeds the bin guess
   int32_t dense;              // 1: predicated binning (most pairs in cutoff), 0: branch
   float box[3];
+  uint32_t frame_need_bits;   // nonzero: only frames whose flags have one of these bits
+  const unsigned long long* gate;  // non-null: the whole launch is a no-op when *gate == 0
 };
+
+// frame classification of the pack kernels
+__device__ __forceinline__ uint32_t window_bits(float v, float box) {
+  // bit0: outside [-box/8, 9 box/8]   bit1: outside [-5 box/8, 5 box/8]   (NaN: inside both)
+  uint32_t b = 0;
+  if (v < -0.125f * box || v > 1.125f * box) b |= 1u;
+  if (v < -0.625f * box || v > 0.625f * box) b |= 2u;
+  return b;
+}
 
 // ---- exact float32 building blocks --------------------------------------------------------
 

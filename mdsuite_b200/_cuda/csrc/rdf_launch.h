@@ -34,8 +34,44 @@ struct PackParams {
   float box[3];
 };
 cudaError_t launch_pack(const PackParams& p, cudaStream_t stream);
+// out[0] += frames on the general minimum-image path, out[1] += frames flagged MDS_FRAME_FAR,
+// *batch_far (nullable) = frames flagged MDS_FRAME_FAR in this batch
 cudaError_t launch_count_general(const uint32_t* flags, int n, unsigned long long* out,
-                                 cudaStream_t stream);
+                                 unsigned long long* batch_far, cudaStream_t stream);
+
+// frame_flags bits written by the pack kernels
+constexpr uint32_t MDS_FRAME_OUT_A = 1u;  // a coordinate outside [-L/8, 9L/8]
+constexpr uint32_t MDS_FRAME_OUT_B = 2u;  // a coordinate outside [-5L/8, 5L/8]
+constexpr uint32_t MDS_FRAME_FAR = 4u;    // a coordinate beyond 8 box lengths: cell path declines
+
+// ---- rdf_cells.cu ----
+struct CellGrid {
+  int nx, ny, nz, nc;  // cells per dimension, nc = nx * ny * nz (each >= 3)
+  float box[3];
+};
+struct CellsParams {
+  const float4* spos;         // [n_frames][frame_stride] atoms sorted by (species, cell)
+  int64_t frame_stride;
+  int32_t n_frames;
+  const uint32_t* cell_off;   // [n_frames][off_stride]: offsets of key = species * nc + cell
+  int64_t off_stride;         // >= n_species * nc + 1
+  const uint32_t* frame_flags;
+  int32_t nx, ny, nz, nc;
+  const int2* pair_ab;        // [n_pairs_total] species (a, b) of every pair, a <= b
+  const float* edges;
+  unsigned long long* counts;     // [n_pairs_total][nbins]
+  unsigned long long* evaluated;  // += candidate pairs distance-tested
+  unsigned long long* work_counter;  // zeroed before launch
+  int32_t nbins, pair_lo, pair_cnt, hist_in_smem;
+  float s_cut, inv_step;
+  float box[3];
+  uint32_t flush_threshold;   // candidate pairs per CTA between histogram flushes (<= 2^30)
+};
+size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem);
+cudaError_t launch_cell_build(const PackParams& pp, const CellGrid& g, int n_species,
+                              uint32_t* cell_off, int64_t off_stride, float4* sorted,
+                              cudaStream_t stream);
+cudaError_t launch_cells(const CellsParams& p, int sm_count, cudaStream_t stream, int* grid_out);
 
 // ---- microbench.cu ----
 cudaError_t run_shared_atomic_bench(int nbins, int iters, int mode, int sm_count, float* ms,

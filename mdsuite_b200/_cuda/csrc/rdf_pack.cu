@@ -16,14 +16,6 @@
 
 namespace mds {
 
-__device__ __forceinline__ uint32_t window_bits(float v, float box) {
-  // bit0: outside [-box/8, 9 box/8]   bit1: outside [-5 box/8, 5 box/8]   (NaN: inside both)
-  uint32_t b = 0;
-  if (v < -0.125f * box || v > 1.125f * box) b |= 1u;
-  if (v < -0.625f * box || v > 0.625f * box) b |= 2u;
-  return b;
-}
-
 __global__ void __launch_bounds__(256) rdf_pack_kernel(const PackParams p) {
   const long long total = (long long)p.n_frames * p.n_packed;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
@@ -58,16 +50,35 @@ cudaError_t launch_pack(const PackParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-__global__ void rdf_count_general_kernel(const uint32_t* flags, int n, unsigned long long* out) {
-  unsigned int c = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) c += ((flags[i] & 3u) == 3u) ? 1u : 0u;
+__global__ void __launch_bounds__(256) rdf_count_general_kernel(const uint32_t* flags, int n,
+                                                                unsigned long long* out,
+                                                                unsigned long long* batch_far) {
+  __shared__ unsigned int s_c, s_far;
+  if (threadIdx.x == 0) { s_c = 0; s_far = 0; }
+  __syncthreads();
+  unsigned int c = 0, far = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t f = flags[i];
+    c += ((f & 3u) == 3u) ? 1u : 0u;
+    far += (f & MDS_FRAME_FAR) ? 1u : 0u;
+  }
   c = __reduce_add_sync(0xffffffffu, c);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+  far = __reduce_add_sync(0xffffffffu, far);
+  if ((threadIdx.x & 31) == 0) {
+    if (c) atomicAdd(&s_c, c);
+    if (far) atomicAdd(&s_far, far);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_c) atomicAdd(out, (unsigned long long)s_c);
+    if (s_far) atomicAdd(out + 1, (unsigned long long)s_far);
+    if (batch_far) *batch_far = s_far;  // gate of the all-pairs fallback launch of this batch
+  }
 }
 
 cudaError_t launch_count_general(const uint32_t* flags, int n, unsigned long long* out,
-                                 cudaStream_t stream) {
-  rdf_count_general_kernel<<<1, 256, 0, stream>>>(flags, n, out);
+                                 unsigned long long* batch_far, cudaStream_t stream) {
+  rdf_count_general_kernel<<<1, 256, 0, stream>>>(flags, n, out, batch_far);
   return cudaGetLastError();
 }
 

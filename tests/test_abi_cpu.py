@@ -28,9 +28,22 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_the_header_layout():
+    """sizeof() of the header's structs, as gcc lays them out, equals the ctypes mirrors."""
     import ctypes
-    assert ctypes.sizeof(_cuda._Config) == 48
-    assert ctypes.sizeof(_cuda._Stats) == 96
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "sz.c")
+        with open(src, "w") as fh:
+            fh.write('#include <stdio.h>\n#include "mds_rdf.h"\nint main(void){printf("%zu %zu %d\\n",'
+                     'sizeof(mds_rdf_config), sizeof(mds_rdf_stats), MDS_RDF_ABI_VERSION);return 0;}\n')
+        exe = os.path.join(tmp, "sz")
+        subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), src, "-o", exe])
+        cfg, st, ver = map(int, subprocess.check_output([exe]).split())
+    assert ctypes.sizeof(_cuda._Config) == cfg == 48
+    assert ctypes.sizeof(_cuda._Stats) == st == 112
+    assert ver == _cuda.ABI_VERSION
 
 
 @pytest.mark.parametrize("cutoff,nbins", [(10.0, 500), (37.699999999999996, 3769), (3.0, 300),
