@@ -12,8 +12,9 @@
 //
 // Layout: one work item = (frame, species pair, row tile of THREADS*R atoms, column range).
 // Each thread keeps R row atoms in registers and walks the column range through a
-// double-buffered shared-memory tile that one elected thread fills with cp.async.bulk (TMA 1-D)
-// and an mbarrier; every column atom is one broadcast LDS.128 for R pair evaluations.
+// double-buffered shared-memory tile (quad blocks: x[4] y[4] z[4]) that one elected thread fills
+// with cp.async.bulk (TMA 1-D) and an mbarrier; three broadcast LDS.128 bring four column atoms,
+// and each (row, column pair) is evaluated with the packed FADD2 / FMUL2 ops of sm_100a.
 // In-cutoff pairs are binned against the squared-distance threshold table and counted with a
 // shared-memory atomic; the CTA's histogram is merged into the global uint64 counts once, at
 // the end (or before 2^31 increments could overflow a 32-bit bin).
@@ -22,8 +23,12 @@
 
 namespace mds {
 
-constexpr int TJ = 512;  // column atoms per shared-memory tile (8 KB per stage)
+constexpr int TJ = 512;                          // column atoms per shared-memory tile
+constexpr int TJ_F4 = TJ / 4 * 3;                // float4 rows per tile stage (quad blocks), 6 KB
 
+// One tile of columns (quad blocks in shared memory) against the R register rows of a thread.
+// Every block of four columns is three broadcast LDS.128; each (row, column pair) goes through
+// the packed FADD2 / FMUL2 sequence of pair2_s.
 template <int R, bool FAST, bool DIAG, bool HIST_SMEM, bool DENSE>
 __device__ __forceinline__ void pair_tile(const float4* __restrict__ jt, int cnt, int jbase,
                                           const float (&xi)[R], const float (&yi)[R],
@@ -32,40 +37,28 @@ __device__ __forceinline__ void pair_tile(const float4* __restrict__ jt, int cnt
                                           uint32_t c_edge, uint32_t d_hist,
                                           const float* __restrict__ edges_g,
                                           unsigned long long* hist_g) {
-#pragma unroll 2
-  for (int jj = 0; jj < cnt; ++jj) {
-    const float4 pj = jt[jj];
-    float s[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float dx = __fsub_rn(pj.x, xi[r]);
-      const float dy = __fsub_rn(pj.y, yi[r]);
-      const float dz = __fsub_rn(pj.z, zi[r]);
-      float mx, my, mz;
-      if (FAST) {
-        mx = minimg_fast(dx, bx);
-        my = minimg_fast(dy, by);
-        mz = minimg_fast(dz, bz);
-      } else {
-        mx = minimg_general(dx, bx);
-        my = minimg_general(dy, by);
-        mz = minimg_general(dz, bz);
-      }
-      s[r] = sq_norm(mx, my, mz);
-    }
+#pragma unroll 1
+  for (int jj = 0; jj < cnt; jj += 4, jt += 3) {
+    const float4 X = jt[0], Y = jt[1], Z = jt[2];
     const int jg = jbase + jj;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (HIST_SMEM && DENSE) {
-        bin_count_dense<DIAG>(s[r], s_cut, inv_step, c_edge, d_hist, jg, ig[r]);
-      } else {
-        bool in = s[r] < s_cut;  // false for NaN (padding rows, NaN input)
-        if (DIAG) in = in && (jg > ig[r]);
-        if (in) {
-          if (HIST_SMEM) {
-            bin_count(s[r], inv_step, c_edge, d_hist);
-          } else {
-            atomicAdd(hist_g + bin_of_s(s[r], inv_step, edges_g), 1ull);
+      float s[4];
+      pair2_s<FAST>(X.x, X.y, Y.x, Y.y, Z.x, Z.y, xi[r], yi[r], zi[r], bx, by, bz, s[0], s[1]);
+      pair2_s<FAST>(X.z, X.w, Y.z, Y.w, Z.z, Z.w, xi[r], yi[r], zi[r], bx, by, bz, s[2], s[3]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (HIST_SMEM && DENSE) {
+          bin_count_dense<DIAG>(s[c], s_cut, inv_step, c_edge, d_hist, jg + c, ig[r]);
+        } else {
+          bool in = s[c] < s_cut;  // false for NaN (padding rows / columns, NaN input)
+          if (DIAG) in = in && (jg + c > ig[r]);
+          if (in) {
+            if (HIST_SMEM) {
+              bin_count(s[c], inv_step, c_edge, d_hist);
+            } else {
+              atomicAdd(hist_g + bin_of_s(s[c], inv_step, edges_g), 1ull);
+            }
           }
         }
       }
@@ -96,8 +89,8 @@ __device__ __forceinline__ void merge_hist(uint32_t* s_hist, const AllPairsParam
 template <int THREADS, int R, int MINB, bool HIST_SMEM>
 __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPairsParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4* jt = reinterpret_cast<float4*>(smem_raw);                  // [2][TJ]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(jt + 2 * TJ);         // [2]
+  float4* jt = reinterpret_cast<float4*>(smem_raw);                  // [2][TJ_F4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(jt + 2 * TJ_F4);      // [2]
   volatile int* s_item = reinterpret_cast<volatile int*>(bars + 2);  // 16 B slot
   float* s_edges = reinterpret_cast<float*>(bars + 4);
   const int n_edges = p.nbins + 2;
@@ -115,10 +108,16 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_fence_init();
+    // The two address constants of the binning sequence go through shared memory so that ptxas
+    // sees opaque registers: folded into the address arithmetic as known constants they cost two
+    // extra integer instructions per pair (LEA + IADD3 with the split magic constant).
+    s_item[1] = (int)(smem_u32(s_edges + 1) - kMagic4);
+    s_item[2] = (int)(smem_u32(s_hist) - smem_u32(s_edges + 1));
   }
   __syncthreads();
 
-  const uint32_t edges1_sa = smem_u32(s_edges + 1);
+  const uint32_t c_edge = (uint32_t)s_item[1];
+  const uint32_t hist0_rel = (uint32_t)s_item[2];
   const float bx = p.box[0], by = p.box[1], bz = p.box[2];
   const float s_cut = p.s_cut, inv_step = p.inv_step;
   const bool dense = HIST_SMEM && (p.dense != 0);
@@ -136,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
     const PairItem it = p.items[idx / p.n_frames];
     const int frame = (int)(idx % p.n_frames);
     if (p.frame_need_bits && !(p.frame_flags[frame] & p.frame_need_bits)) continue;  // CTA-uniform
-    const float4* __restrict__ fpos = p.pos + (long long)frame * p.frame_stride;
+    const float* __restrict__ fpos = p.pos + (long long)frame * p.frame_stride * 3;
     const bool fast = ((p.frame_flags[frame] & 3u) != 3u);  // see rdf_pack.cu
 
     float xi[R], yi[R], zi[R];
@@ -146,39 +145,38 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
       const int li = tid + r * THREADS;
       ig[r] = it.i0 + li;
       if (li < it.i_cnt) {
-        const float4 v = __ldg(fpos + ig[r]);
-        xi[r] = v.x; yi[r] = v.y; zi[r] = v.z;
+        const float* q = fpos + (ig[r] >> 2) * QUAD_FLOATS + (ig[r] & 3);
+        xi[r] = __ldg(q); yi[r] = __ldg(q + 4); zi[r] = __ldg(q + 8);
       } else {
         xi[r] = yi[r] = zi[r] = __int_as_float(0x7fc00000);  // NaN: never in cutoff
       }
     }
 
-    const uint32_t c_edge = edges1_sa - kMagic4;
-    const uint32_t d_hist = smem_u32(s_hist + (it.pair - p.pair_lo) * hist_stride) - edges1_sa;
+    const uint32_t d_hist = hist0_rel + (uint32_t)((it.pair - p.pair_lo) * hist_stride) * 4u;
     unsigned long long* hist_g = p.counts + (long long)it.pair * p.nbins;
     const int n_cols = it.j1 - it.j0;
     const int n_tiles = (n_cols + TJ - 1) / TJ;
 
     if (tid == 0) {
-      const uint32_t bytes = (uint32_t)min(TJ, n_cols) * 16u;
+      const uint32_t bytes = (uint32_t)min(TJ, n_cols) * 12u;  // j0, j1 are multiples of 4
       fence_proxy_async();
       mbar_expect_tx(&bars[0], bytes);
-      tma_load_1d(jt, fpos + it.j0, bytes, &bars[0]);
+      tma_load_1d(jt, fpos + (long long)it.j0 * 3, bytes, &bars[0]);
     }
     for (int t = 0; t < n_tiles; ++t) {
       const int st = t & 1;
       if (tid == 0 && t + 1 < n_tiles) {
         const int nb = it.j0 + (t + 1) * TJ;
-        const uint32_t bytes = (uint32_t)min(TJ, it.j1 - nb) * 16u;
+        const uint32_t bytes = (uint32_t)min(TJ, it.j1 - nb) * 12u;
         fence_proxy_async();
         mbar_expect_tx(&bars[st ^ 1], bytes);
-        tma_load_1d(jt + (st ^ 1) * TJ, fpos + nb, bytes, &bars[st ^ 1]);
+        tma_load_1d(jt + (st ^ 1) * TJ_F4, fpos + (long long)nb * 3, bytes, &bars[st ^ 1]);
       }
       if (st == 0) { mbar_wait(&bars[0], ph0); ph0 ^= 1u; }
       else         { mbar_wait(&bars[1], ph1); ph1 ^= 1u; }
       const int jbase = it.j0 + t * TJ;
       const int cnt = min(TJ, it.j1 - jbase);
-      const float4* tile = jt + st * TJ;
+      const float4* tile = jt + st * TJ_F4;
       const bool diag = it.diag && (jbase < it.i0 + it.i_cnt);
 #define MDS_TILE(FASTV, DIAGV, DENSEV)                                                         \
   pair_tile<R, FASTV, DIAGV, HIST_SMEM, DENSEV>(tile, cnt, jbase, xi, yi, zi, ig, bx, by, bz,     \
@@ -212,7 +210,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
 // ---- host-side launch table ----------------------------------------------------------------
 
 size_t allpairs_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem) {
-  size_t b = 2 * TJ * sizeof(float4) + 4 * sizeof(uint64_t);
+  size_t b = 2 * TJ_F4 * sizeof(float4) + 4 * sizeof(uint64_t);
   if (hist_in_smem) {
     b += (size_t)((nbins + 2 + 3) & ~3) * sizeof(float);
     b += (size_t)pair_cnt * (size_t)(nbins + 1) * sizeof(uint32_t);

@@ -93,7 +93,8 @@ struct mds_rdf {
   int sm_count = 0;
   // derived
   int64_t n_atoms = 0;   // raw atoms per frame
-  int32_t n_packed = 0;  // atoms per frame after dropping the Q1 atoms
+  int32_t n_packed = 0;  // packed slots per frame: Q1 atoms dropped, species padded to multiples of 4
+  int32_t n_real = 0;    // packed slots that hold an atom
   int64_t frame_stride = 0;
   int n_pairs = 0;
   double pairs_per_frame = 0;  // the reference's (row, col) count per frame for this mode
@@ -118,7 +119,8 @@ struct mds_rdf {
   unsigned long long* d_general = nullptr;
   unsigned int* d_work = nullptr;  // ring of work counters
   int work_slot = 0;
-  float4* d_packed[2] = {nullptr, nullptr};
+  float* d_packed[2] = {nullptr, nullptr};   // quad-block positions, 12 B per slot
+  uint32_t* d_rank[2] = {nullptr, nullptr};  // cell-list path: rank of each atom in its cell
   uint32_t* d_flags[2] = {nullptr, nullptr};
   float* d_raw[2] = {nullptr, nullptr};  // staging for host submits (lazy)
   // cell-list path only
@@ -169,12 +171,17 @@ void build_items(mds_rdf* h, int tile_rows, int64_t frames_hint) {
   std::vector<mds::PairItem> items;
   for (int a = 0; a < h->n_species; ++a) {
     for (int b = a; b < h->n_species; ++b, ++pair) {
+      // segments start at multiples of 4 and are NaN-padded to multiples of 4, so column ranges
+      // can always be whole quad blocks; the diagonal block starts AT the row tile (col > row
+      // is applied per pair inside the kernel)
       const int a0 = h->poff[a], a1 = a0 + h->pcnt[a];
-      const int b0 = h->poff[b], b1 = b0 + h->pcnt[b];
+      const int b0 = h->poff[b], b1 = b0 + ((h->pcnt[b] + 3) & ~3);
+      if (h->pcnt[a] == 0 || h->pcnt[b] == 0) continue;
+      if (a == b && h->pcnt[a] < 2) continue;
       for (int i0 = a0; i0 < a1; i0 += tile_rows) {
         const int i_cnt = std::min(tile_rows, a1 - i0);
-        const int j0 = (a == b) ? i0 + 1 : b0;
-        const int j1 = (a == b) ? a1 : b1;
+        const int j0 = (a == b) ? i0 : b0;
+        const int j1 = b1;
         if (j0 >= j1) continue;
         items.push_back({pair, i0, i_cnt, j0, j1, (a == b) ? 1 : 0, 0, 0});
       }
@@ -314,6 +321,15 @@ mds::PackParams pack_params(mds_rdf* h, const float* d_xyz, int layout, int64_t 
   pp.frame_stride = h->frame_stride;
   pp.frame_flags = h->d_flags[buf];
   for (int k = 0; k < 3; ++k) pp.box[k] = h->box[k];
+  pp.cell_off = nullptr;
+  pp.off_stride = 0;
+  pp.rank = nullptr;
+  pp.grid = h->grid;
+  if (h->path == MDS_RDF_PATH_CELLLIST) {
+    pp.cell_off = h->d_cell_off[buf];
+    pp.off_stride = h->off_stride;
+    pp.rank = h->d_rank[buf];
+  }
   return pp;
 }
 
@@ -352,12 +368,11 @@ int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t fram
                         int64_t n_frames, int64_t n_frames_total, int buf) {
   CUDA_TRY(cudaMemsetAsync(h->d_flags[buf], 0, sizeof(uint32_t) * (size_t)n_frames, h->s_compute));
   const mds::PackParams pp = pack_params(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf);
-  CUDA_TRY(mds::launch_cell_build(pp, h->grid, h->n_species, h->d_cell_off[buf], h->off_stride,
-                                  h->d_sorted[buf], h->s_compute));
+  CUDA_TRY(mds::launch_cell_build(pp, h->n_species, h->d_sorted[buf], h->s_compute));
   CUDA_TRY(mds::launch_count_general(h->d_flags[buf], (int)n_frames, h->d_general,
                                      h->d_batch_far + buf, h->s_compute));
   h->launches += 4;
-  if (h->n_packed == 0) return MDS_OK;
+  if (h->n_real == 0) return MDS_OK;
   for (int p0 = 0; p0 < h->n_pairs; p0 += h->pair_group) {
     const int pc = std::min(h->pair_group, h->n_pairs - p0);
     mds::CellsParams cp;
@@ -490,13 +505,18 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   int64_t off = 0;
   h->pairs_per_frame = 0;
   for (int s = 0; s < h->n_species; ++s) {
-    h->poff.push_back((int32_t)src_index.size());
+    h->poff.push_back((int32_t)src_index.size());  // a multiple of 4
     const int64_t n = std::max<int64_t>(0, h->counts[s] - first);
     h->pcnt.push_back((int32_t)n);
     for (int64_t i = 0; i < n; ++i) {
       src_index.push_back((int32_t)(off + first + i));
       species.push_back(s);
     }
+    while (src_index.size() & 3) {  // NaN padding slots
+      src_index.push_back(-1);
+      species.push_back(s);
+    }
+    h->n_real += (int32_t)n;
     off += h->counts[s];
   }
   for (int a = 0; a < h->n_species; ++a)
@@ -504,8 +524,8 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
       h->pairs_per_frame += (a == b) ? 0.5 * (double)h->pcnt[a] * (double)(h->pcnt[a] - 1)
                                      : (double)h->pcnt[a] * (double)h->pcnt[b];
   h->n_packed = (int32_t)src_index.size();
-  h->frame_stride = ((int64_t)h->n_packed + 7) & ~7LL;  // 128 B aligned frames
-  if (h->frame_stride == 0) h->frame_stride = 8;
+  h->frame_stride = ((int64_t)h->n_packed + 31) & ~31LL;  // 384 B aligned frames
+  if (h->frame_stride == 0) h->frame_stride = 32;
 
   build_threshold_table(h->cutoff, h->nbins, h->edges, h->s_cut);
   h->inv_step = (float)((double)h->nbins / (double)h->cutoff * (double)mds::kBinGuessBias);
@@ -532,7 +552,7 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
                   (double)cfg->box[1], (double)cfg->box[2]);
     }
     // the cell kernel tests ~27/nc of all pairs at roughly half the all-pairs kernel's rate
-    const bool auto_cells = cell_ok && nc >= 64 && h->n_packed >= 1024;
+    const bool auto_cells = cell_ok && nc >= 64 && h->n_real >= 1024;
     h->path = (forced_cells || (!forced_all && auto_cells)) ? MDS_RDF_PATH_CELLLIST
                                                             : MDS_RDF_PATH_ALLPAIRS;
     if (h->path == MDS_RDF_PATH_CELLLIST) {
@@ -577,7 +597,7 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   h->variant = pick_variant(h);
   int bf = cfg->max_frames_in_flight;
   if (bf <= 0) {
-    const int64_t per_frame = h->frame_stride * 16 * (cells ? 2 : 1) + h->off_stride * 4;
+    const int64_t per_frame = h->frame_stride * (cells ? 12 + 4 + 16 : 12) + h->off_stride * 4;
     bf = (int)std::min<int64_t>(4096, std::max<int64_t>(1, (128LL << 20) / per_frame));
   }
   h->batch_frames = bf;
@@ -628,13 +648,14 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
     CREATE_TRY(cudaMemset(h->d_batch_far, 0, 2 * sizeof(unsigned long long)));
     for (int b = 0; b < 2; ++b) {
       CREATE_TRY(cudaMalloc(&h->d_sorted[b], (size_t)h->frame_stride * 16 * (size_t)bf));
+      CREATE_TRY(cudaMalloc(&h->d_rank[b], (size_t)h->frame_stride * 4 * (size_t)bf));
       CREATE_TRY(cudaMalloc(&h->d_cell_off[b], (size_t)h->off_stride * 4 * (size_t)bf));
     }
   }
   CREATE_TRY(cudaMalloc(&h->d_work, sizeof(unsigned int) * WORK_RING));
   CREATE_TRY(cudaMemset(h->d_work, 0, sizeof(unsigned int) * WORK_RING));
   for (int b = 0; b < 2; ++b) {
-    CREATE_TRY(cudaMalloc(&h->d_packed[b], (size_t)h->frame_stride * 16 * (size_t)bf));
+    CREATE_TRY(cudaMalloc(&h->d_packed[b], (size_t)h->frame_stride * 12 * (size_t)bf));
     CREATE_TRY(cudaMalloc(&h->d_flags[b], sizeof(uint32_t) * (size_t)bf));
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_raw_ready[b], cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_raw_free[b], cudaEventDisableTiming));
@@ -677,6 +698,7 @@ void mds_rdf_destroy(mds_rdf_t* h) {
     cudaFree(h->d_flags[b]);
     cudaFree(h->d_raw[b]);
     cudaFree(h->d_sorted[b]);
+    cudaFree(h->d_rank[b]);
     cudaFree(h->d_cell_off[b]);
     if (h->ev_raw_ready[b]) cudaEventDestroy(h->ev_raw_ready[b]);
     if (h->ev_raw_free[b]) cudaEventDestroy(h->ev_raw_free[b]);

@@ -12,8 +12,8 @@
 // flagged by the pack kernel and handed to the all-pairs kernel instead.
 //
 // Per batch of frames:
-//   rdf_cell_pack_kernel   raw xyz -> float4 (x, y, z, rank in cell); per-(frame, species, cell)
-//                          counts with one global atomic per atom; frame classification
+//   rdf_pack_kernel        (rdf_pack.cu) raw xyz -> quad-block positions; per-(frame, species,
+//                          cell) counts and ranks with one global atomic per atom; frame flags
 //   rdf_cell_scan_kernel   exclusive scan of the counts of a frame -> cell offsets (one CTA/frame)
 //   rdf_cell_scatter_kernel counting-sort scatter -> atoms ordered by (species, cell), x fastest
 //   rdf_cells_kernel       persistent warps; one work item = (frame, species pair, cell): the
@@ -28,52 +28,6 @@
 #include "mds_rdf.h"
 
 namespace mds {
-
-// ---- cell assignment (shared by pack and scatter; exact IEEE ops so it is reproducible) -------
-__device__ __forceinline__ int cell_coord(float x, float box, int n) {
-  float u = __fdiv_rn(x, box);
-  u = __fsub_rn(u, floorf(u));                        // [0, 1]; NaN / inf -> NaN
-  const int c = __float2int_rz(__fmul_rn(u, (float)n));  // NaN -> 0
-  return min(max(c, 0), n - 1);
-}
-
-__device__ __forceinline__ int cell_of(float x, float y, float z, const CellGrid& g) {
-  const int cx = cell_coord(x, g.box[0], g.nx);
-  const int cy = cell_coord(y, g.box[1], g.ny);
-  const int cz = cell_coord(z, g.box[2], g.nz);
-  return (cz * g.ny + cy) * g.nx + cx;
-}
-
-__global__ void __launch_bounds__(256) rdf_cell_pack_kernel(const PackParams p, const CellGrid g,
-                                                            uint32_t* cell_off,
-                                                            int64_t off_stride) {
-  const long long total = (long long)p.n_frames * p.n_packed;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    long long f, q;
-    if (p.layout == MDS_LAYOUT_ATOM_MAJOR_XYZ) {
-      q = t / p.n_frames;
-      f = t % p.n_frames;
-    } else {
-      f = t / p.n_packed;
-      q = t % p.n_packed;
-    }
-    const long long a = p.src_index[q];
-    const float* src = (p.layout == MDS_LAYOUT_ATOM_MAJOR_XYZ)
-                           ? p.xyz + (a * p.n_frames_total + p.frame0 + f) * 3
-                           : p.xyz + ((p.frame0 + f) * p.n_atoms + a) * 3;
-    const float x = __ldg(src), y = __ldg(src + 1), z = __ldg(src + 2);
-    const int key = p.species[q] * g.nc + cell_of(x, y, z, g);
-    const uint32_t rank = atomicAdd(cell_off + f * off_stride + key, 1u);
-    p.out[f * p.frame_stride + q] = make_float4(x, y, z, __uint_as_float(rank));
-    uint32_t bits = window_bits(x, p.box[0]) | window_bits(y, p.box[1]) | window_bits(z, p.box[2]);
-    // bit2: a coordinate further than 8 box lengths out (or infinite): the cell margin no longer
-    // covers float32 rounding of the reference's own arithmetic -> all-pairs kernel for this frame
-    if (fabsf(x) > 8.0f * p.box[0] || fabsf(y) > 8.0f * p.box[1] || fabsf(z) > 8.0f * p.box[2])
-      bits |= MDS_FRAME_FAR;
-    if (bits && (p.frame_flags[f] & bits) != bits) atomicOr(p.frame_flags + f, bits);
-  }
-}
 
 // Exclusive scan of the n_keys counts of one frame (in place) + total at [n_keys].
 __global__ void __launch_bounds__(1024) rdf_cell_scan_kernel(uint32_t* cell_off, int64_t off_stride,
@@ -121,22 +75,19 @@ __global__ void __launch_bounds__(1024) rdf_cell_scan_kernel(uint32_t* cell_off,
   if (threadIdx.x == 0) a[n_keys] = carry;
 }
 
-__global__ void __launch_bounds__(256) rdf_cell_scatter_kernel(const float4* __restrict__ packed,
-                                                               float4* __restrict__ sorted,
-                                                               int64_t frame_stride,
-                                                               const int32_t* __restrict__ species,
-                                                               int32_t n_packed, int64_t n_frames,
-                                                               const uint32_t* __restrict__ cell_off,
-                                                               int64_t off_stride, const CellGrid g) {
-  const long long total = n_frames * n_packed;
+__global__ void __launch_bounds__(256) rdf_cell_scatter_kernel(const PackParams p,
+                                                               float4* __restrict__ sorted) {
+  const long long total = (long long)p.n_frames * p.n_packed;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (long long)gridDim.x * blockDim.x) {
-    const long long f = t / n_packed;
-    const int q = (int)(t % n_packed);
-    const float4 v = packed[f * frame_stride + q];
-    const int key = species[q] * g.nc + cell_of(v.x, v.y, v.z, g);
-    const uint32_t pos = cell_off[f * off_stride + key] + __float_as_uint(v.w);
-    sorted[f * frame_stride + pos] = make_float4(v.x, v.y, v.z, __int_as_float(q));
+    const long long f = t / p.n_packed;
+    const int q = (int)(t % p.n_packed);
+    if (p.src_index[q] < 0) continue;  // padding slot
+    const float* src = p.out + (f * p.frame_stride + (q & ~3)) * 3 + (q & 3);
+    const float x = src[0], y = src[4], z = src[8];
+    const int key = p.species[q] * p.grid.nc + cell_of(x, y, z, p.grid);
+    const uint32_t pos = p.cell_off[f * p.off_stride + key] + p.rank[f * p.frame_stride + q];
+    sorted[f * p.frame_stride + pos] = make_float4(x, y, z, __int_as_float(q));
   }
 }
 
@@ -148,11 +99,12 @@ constexpr int CH = 32;         // column atoms per staged chunk: one float4 per 
 constexpr int MAX_SPANS = 20;  // >= 18 (9 cell rows x 2 pieces when the x window wraps)
 constexpr int RMAX = 4;        // rows per lane: one pass covers 8 * RMAX = 32 rows of a cell
 
-// One chunk of staged columns against the register rows of a warp.  Lane layout: row group
-// rg = lane & 7 (rows rg, rg + 8, ...), column phase ph = lane >> 3 (columns ph, ph + 4, ...):
-// one LDS.128 with 4 distinct addresses serves R pair evaluations per lane.
+// One chunk of staged columns (quad blocks in the warp's shared tile) against the register rows
+// of a warp.  Lane layout: row group rg = lane & 7 (rows rg, rg + 8, ...), column phase
+// ph = lane >> 3 (column pairs 2 ph, 2 ph + 8, ...): three LDS.64 with 4 distinct addresses serve
+// 2 R pair evaluations per lane through the packed FADD2 / FMUL2 sequence of pair2_s.
 template <int R, bool FAST, bool DIAG, bool HIST_SMEM>
-__device__ __forceinline__ void cell_chunk(const float4* __restrict__ tile, int cnt, int q0, int ph,
+__device__ __forceinline__ void cell_chunk(const float* __restrict__ tl, int cnt, int q0, int ph,
                                            const float (&xi)[RMAX], const float (&yi)[RMAX],
                                            const float (&zi)[RMAX], const int (&il)[RMAX],
                                            float bx, float by, float bz, float s_cut,
@@ -160,35 +112,25 @@ __device__ __forceinline__ void cell_chunk(const float4* __restrict__ tile, int 
                                            const float* __restrict__ edges_g,
                                            unsigned long long* hist_g) {
 #pragma unroll 2
-  for (int jj = ph; jj < cnt; jj += 4) {
-    const float4 pj = tile[jj];
-    float s[R];
+  for (int c0 = ph * 2; c0 < cnt; c0 += 8) {
+    const float* b = tl + (c0 >> 2) * QUAD_FLOATS + (c0 & 2);
+    const float2 X = *reinterpret_cast<const float2*>(b);
+    const float2 Y = *reinterpret_cast<const float2*>(b + 4);
+    const float2 Z = *reinterpret_cast<const float2*>(b + 8);
+    const int q = q0 + c0;  // position in the column stream; the own cell comes first
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const float dx = __fsub_rn(pj.x, xi[r]);
-      const float dy = __fsub_rn(pj.y, yi[r]);
-      const float dz = __fsub_rn(pj.z, zi[r]);
-      float mx, my, mz;
-      if (FAST) {
-        mx = minimg_fast(dx, bx);
-        my = minimg_fast(dy, by);
-        mz = minimg_fast(dz, bz);
-      } else {
-        mx = minimg_general(dx, bx);
-        my = minimg_general(dy, by);
-        mz = minimg_general(dz, bz);
-      }
-      s[r] = sq_norm(mx, my, mz);
-    }
-    const int q = q0 + jj;  // position in the column stream; the own cell comes first
+      float s[2];
+      pair2_s<FAST>(X.x, X.y, Y.x, Y.y, Z.x, Z.y, xi[r], yi[r], zi[r], bx, by, bz, s[0], s[1]);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (HIST_SMEM) {
-        bin_count_dense<DIAG>(s[r], s_cut, inv_step, c_edge, d_hist, q, il[r]);
-      } else {
-        bool in = s[r] < s_cut;  // false for NaN (padding rows, NaN input)
-        if (DIAG) in = in && (q > il[r]);
-        if (in) atomicAdd(hist_g + bin_of_s(s[r], inv_step, edges_g), 1ull);
+      for (int c = 0; c < 2; ++c) {
+        if (HIST_SMEM) {
+          bin_count_dense<DIAG>(s[c], s_cut, inv_step, c_edge, d_hist, q + c, il[r]);
+        } else {
+          bool in = s[c] < s_cut;  // false for NaN (padding rows / columns, NaN input)
+          if (DIAG) in = in && (q + c > il[r]);
+          if (in) atomicAdd(hist_g + bin_of_s(s[c], inv_step, edges_g), 1ull);
+        }
       }
     }
   }
@@ -212,8 +154,8 @@ __device__ __forceinline__ void flush_hist_warp(uint32_t* s_hist, const CellsPar
 template <bool HIST_SMEM>
 __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4* tiles = reinterpret_cast<float4*>(smem_raw);                       // [WARPS][2][CH]
-  int* span_tab = reinterpret_cast<int*>(tiles + CELL_WARPS * 2 * CH);       // [WARPS][2][MAX_SPANS]
+  float* tiles = reinterpret_cast<float*>(smem_raw);                // [WARPS][2][CH * 3] quad blocks
+  int* span_tab = reinterpret_cast<int*>(tiles + CELL_WARPS * 2 * CH * 3);   // [WARPS][2][MAX_SPANS]
   uint32_t* s_evals = reinterpret_cast<uint32_t*>(span_tab + CELL_WARPS * 2 * MAX_SPANS);  // [4]
   float* s_edges = reinterpret_cast<float*>(s_evals + 4);
   const int n_edges = p.nbins + 2;
@@ -226,14 +168,22 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
     for (int k = tid; k < n_edges; k += CELL_THREADS) s_edges[k] = p.edges[k];
     for (int k = tid; k < p.pair_cnt * hist_stride; k += CELL_THREADS) s_hist[k] = 0u;
   }
-  if (tid == 0) s_evals[0] = 0u;
+  if (tid == 0) {
+    s_evals[0] = 0u;
+    // address constants of the binning sequence, made opaque to ptxas (see rdf_allpairs.cu)
+    s_evals[1] = smem_u32(s_edges + 1) - kMagic4;
+    s_evals[2] = smem_u32(s_hist) - smem_u32(s_edges + 1);
+  }
   __syncthreads();
 
-  float4* tile = tiles + warp * 2 * CH;
+  float* tile = tiles + warp * 2 * CH * 3;
+  const int st_off = (lane >> 2) * QUAD_FLOATS + (lane & 3);  // this lane's slot in a staged chunk
+  const float4 nan4 = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
+                                  __int_as_float(0x7fc00000), 0.f);
   int* t_qend = span_tab + warp * 2 * MAX_SPANS;
   int* t_off = t_qend + MAX_SPANS;
-  const uint32_t edges1_sa = smem_u32(s_edges + 1);
-  const uint32_t c_edge = edges1_sa - kMagic4;
+  const uint32_t c_edge = *reinterpret_cast<volatile uint32_t*>(s_evals + 1);
+  const uint32_t hist0_rel = *reinterpret_cast<volatile uint32_t*>(s_evals + 2);
   const float bx = p.box[0], by = p.box[1], bz = p.box[2];
   const float s_cut = p.s_cut, inv_step = p.inv_step;
   const int nx = p.nx, ny = p.ny, nz = p.nz, nc = p.nc;
@@ -320,7 +270,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
       }
       __syncwarp();
 
-      const uint32_t d_hist = smem_u32(s_hist + pr * hist_stride) - edges1_sa;
+      const uint32_t d_hist = hist0_rel + (uint32_t)(pr * hist_stride) * 4u;
       unsigned long long* hist_g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
 
       // ---- row passes of up to 32 atoms of the cell ----
@@ -342,7 +292,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
         // same species: columns q <= row are masked, so the stream starts at the pass's own block
         const int qs = same ? rp : 0;
         int k = 0;
-        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 nxt = nan4;  // slots past the end of the stream hold NaN atoms (never in cutoff)
         {
           const int q = qs + lane;
           if (q < total) {
@@ -351,18 +301,19 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
           }
         }
         __syncwarp();
-        tile[lane] = nxt;
+        tile[st_off] = nxt.x; tile[st_off + 4] = nxt.y; tile[st_off + 8] = nxt.z;
         __syncwarp();
         int st = 0;
         for (int q0 = qs; q0 < total; q0 += CH, st ^= 1) {
           const int cnt = min(CH, total - q0);
           const int qn = q0 + CH + lane;
-          const bool have = qn < total;
-          if (have) {
+          const bool more = q0 + CH < total;  // warp-uniform: another chunk follows
+          nxt = nan4;
+          if (qn < total) {
             while (qn >= t_qend[k]) ++k;
             nxt = __ldg(fpos + t_off[k] + qn);
           }
-          const float4* tl = tile + st * CH;
+          const float* tl = tile + st * CH * 3;
           const bool diag = same && (q0 < rp + 8 * RMAX);
 #define MDS_CHUNK(RV, FASTV, DIAGV)                                                             \
   cell_chunk<RV, FASTV, DIAGV, HIST_SMEM>(tl, cnt, q0, ph, xi, yi, zi, il, bx, by, bz, s_cut,       \
@@ -381,7 +332,10 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
           }
 #undef MDS_CHUNK_R
 #undef MDS_CHUNK
-          if (have) tile[(st ^ 1) * CH + lane] = nxt;
+          if (more) {
+            float* o = tile + (st ^ 1) * CH * 3 + st_off;
+            o[0] = nxt.x; o[4] = nxt.y; o[8] = nxt.z;
+          }
           __syncwarp();
           if (HIST_SMEM) {
             unpublished += (uint32_t)(cnt * nr);
@@ -425,7 +379,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
 // ---- host-side launchers ------------------------------------------------------------------
 
 size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem) {
-  size_t b = (size_t)CELL_WARPS * 2 * CH * sizeof(float4) +
+  size_t b = (size_t)CELL_WARPS * 2 * CH * 3 * sizeof(float) +
              (size_t)CELL_WARPS * 2 * MAX_SPANS * sizeof(int) + 4 * sizeof(uint32_t);
   if (hist_in_smem) {
     b += (size_t)((nbins + 2 + 3) & ~3) * sizeof(float);
@@ -434,21 +388,21 @@ size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem) {
   return b;
 }
 
-cudaError_t launch_cell_build(const PackParams& pp, const CellGrid& g, int n_species,
-                              uint32_t* cell_off, int64_t off_stride, float4* sorted,
+cudaError_t launch_cell_build(const PackParams& pp, int n_species, float4* sorted,
                               cudaStream_t stream) {
   const long long total = (long long)pp.n_frames * pp.n_packed;
   if (total <= 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(cell_off, 0, sizeof(uint32_t) * (size_t)off_stride * (size_t)pp.n_frames,
+  cudaError_t e = cudaMemsetAsync(pp.cell_off, 0,
+                                  sizeof(uint32_t) * (size_t)pp.off_stride * (size_t)pp.n_frames,
                                   stream);
   if (e != cudaSuccess) return e;
+  e = launch_pack(pp, stream);  // quad-block positions + per-cell counts and ranks + frame flags
+  if (e != cudaSuccess) return e;
+  rdf_cell_scan_kernel<<<(unsigned)pp.n_frames, 1024, 0, stream>>>(pp.cell_off, pp.off_stride,
+                                                                   n_species * pp.grid.nc);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 64) blocks = 148 * 64;
-  rdf_cell_pack_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pp, g, cell_off, off_stride);
-  rdf_cell_scan_kernel<<<(unsigned)pp.n_frames, 1024, 0, stream>>>(cell_off, off_stride,
-                                                                   n_species * g.nc);
-  rdf_cell_scatter_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
-      pp.out, sorted, pp.frame_stride, pp.species, pp.n_packed, pp.n_frames, cell_off, off_stride, g);
+  rdf_cell_scatter_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pp, sorted);
   return cudaGetLastError();
 }
 

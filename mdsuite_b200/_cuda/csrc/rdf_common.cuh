@@ -23,9 +23,16 @@ struct PairItem {
 };
 static_assert(sizeof(PairItem) == 32, "PairItem must stay 32 bytes");
 
+// Packed position layout ("quad blocks", SoA in groups of four atoms, 12 B per atom):
+//   float pos[n_frames][frame_stride / 4][3][4]   block b = atoms 4b .. 4b+3: x[4], y[4], z[4]
+// One LDS.128 of a block row yields two aligned register pairs (x0,x1), (x2,x3) for the packed
+// FADD2 / FMUL2 instructions of sm_100a.  Species segments start at multiples of 4 and are
+// padded with NaN atoms (never inside the cutoff).
+constexpr int QUAD_FLOATS = 12;  // floats per block of four atoms
+
 struct AllPairsParams {
-  const float4* pos;          // [n_frames][frame_stride] packed positions (x, y, z, species id)
-  int64_t frame_stride;       // float4 elements between frames (>= n_packed, multiple of 1)
+  const float* pos;           // [n_frames][frame_stride / 4][3][4] quad-block positions
+  int64_t frame_stride;       // atom slots between frames (multiple of 4)
   int32_t n_frames;
   int32_t n_items;            // items per frame
   const PairItem* items;      // [n_items], sorted by decreasing cost
@@ -73,6 +80,80 @@ __device__ __forceinline__ float minimg_general(float d, float box) {
 // (x*x + y*y) + z*z with materialised products (tf.linalg.norm before the sqrt).
 __device__ __forceinline__ float sq_norm(float x, float y, float z) {
   return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// ---- cell assignment of the cell-list path (exact IEEE ops so it is reproducible) -----------
+__device__ __forceinline__ int cell_coord(float x, float box, int n) {
+  float u = __fdiv_rn(x, box);
+  u = __fsub_rn(u, floorf(u));                            // [0, 1]; NaN / inf -> NaN
+  const int c = __float2int_rz(__fmul_rn(u, (float)n));   // NaN -> 0
+  return min(max(c, 0), n - 1);
+}
+template <typename Grid>
+__device__ __forceinline__ int cell_of(float x, float y, float z, const Grid& g) {
+  const int cx = cell_coord(x, g.box[0], g.nx);
+  const int cy = cell_coord(y, g.box[1], g.ny);
+  const int cz = cell_coord(z, g.box[2], g.nz);
+  return (cz * g.ny + cy) * g.nx + cx;
+}
+
+// ---- packed float32 pairs (sm_100a FADD2 / FMUL2: two IEEE-rounded ops per issue slot) ------
+// ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 (observed with CUDA 12.9,
+// even with -fmad=false), which would break the reference's separately rounded products — so
+// packed ops are used for the subtractions and the squares only, and the two additions of
+// (x*x + y*y) + z*z stay scalar add.rn.f32.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// Squared minimum-image distances of ONE row atom (xi, yi, zi) against TWO column atoms, every
+// op rounded exactly as in the scalar building blocks above.  Per pair: 1.5 FADD2 (differences)
+// + 1.5 FADD2 (box - |d|, abs/neg are operand modifiers) + 3 FMNMX + 1.5 FMUL2 + 2 FADD.
+template <bool FAST>
+__device__ __forceinline__ void pair2_s(float xj0, float xj1, float yj0, float yj1, float zj0,
+                                        float zj1, float xi, float yi, float zi, float bx, float by,
+                                        float bz, float& s0, float& s1) {
+  float dx0, dx1, dy0, dy1, dz0, dz1;
+  unpack2(sub2(pack2(xj0, xj1), pack2(xi, xi)), dx0, dx1);
+  unpack2(sub2(pack2(yj0, yj1), pack2(yi, yi)), dy0, dy1);
+  unpack2(sub2(pack2(zj0, zj1), pack2(zi, zi)), dz0, dz1);
+  float mx0, mx1, my0, my1, mz0, mz1;
+  if (FAST) {
+    float tx0, tx1, ty0, ty1, tz0, tz1;
+    unpack2(sub2(pack2(bx, bx), pack2(fabsf(dx0), fabsf(dx1))), tx0, tx1);
+    unpack2(sub2(pack2(by, by), pack2(fabsf(dy0), fabsf(dy1))), ty0, ty1);
+    unpack2(sub2(pack2(bz, bz), pack2(fabsf(dz0), fabsf(dz1))), tz0, tz1);
+    mx0 = fminf(fabsf(dx0), tx0); mx1 = fminf(fabsf(dx1), tx1);
+    my0 = fminf(fabsf(dy0), ty0); my1 = fminf(fabsf(dy1), ty1);
+    mz0 = fminf(fabsf(dz0), tz0); mz1 = fminf(fabsf(dz1), tz1);
+  } else {
+    mx0 = minimg_general(dx0, bx); mx1 = minimg_general(dx1, bx);
+    my0 = minimg_general(dy0, by); my1 = minimg_general(dy1, by);
+    mz0 = minimg_general(dz0, bz); mz1 = minimg_general(dz1, bz);
+  }
+  float xx0, xx1, yy0, yy1, zz0, zz1;
+  const f32x2 mx = pack2(mx0, mx1), my = pack2(my0, my1), mz = pack2(mz0, mz1);
+  unpack2(mul2(mx, mx), xx0, xx1);
+  unpack2(mul2(my, my), yy0, yy1);
+  unpack2(mul2(mz, mz), zz0, zz1);
+  s0 = __fadd_rn(__fadd_rn(xx0, yy0), zz0);
+  s1 = __fadd_rn(__fadd_rn(xx1, yy1), zz1);
 }
 
 __device__ __forceinline__ float sqrt_approx(float s) {

@@ -18,6 +18,10 @@ int allpairs_variant_tile(int variant);  // rows per work item of a variant, -1 
 constexpr int ALLPAIRS_N_VARIANTS = 6;
 
 // ---- rdf_pack.cu ----
+struct CellGrid {
+  int nx, ny, nz, nc;  // cells per dimension, nc = nx * ny * nz (each >= 3)
+  float box[3];
+};
 struct PackParams {
   const float* xyz;        // raw input, layout below
   int layout;              // MDS_LAYOUT_*
@@ -25,11 +29,16 @@ struct PackParams {
   int64_t n_frames;        // frames in this batch
   int64_t frame0;          // first frame of the batch inside the raw buffer (atom-major only)
   int64_t n_frames_total;  // frames in the raw buffer (stride of the atom-major layout)
-  const int32_t* src_index;  // [n_packed] raw atom index of each packed atom
-  const int32_t* species;    // [n_packed] species id of each packed atom
-  int32_t n_packed;
-  float4* out;             // [n_frames][frame_stride]
-  int64_t frame_stride;
+  const int32_t* src_index;  // [n_packed] raw atom index of each packed slot, -1: padding
+  const int32_t* species;    // [n_packed] species id of each packed slot
+  int32_t n_packed;        // packed slots per frame (species segments padded to multiples of 4)
+  float* out;              // [n_frames][frame_stride / 4][3][4] quad blocks
+  int64_t frame_stride;    // atom slots between frames
+  // cell-list path only (cell_off == nullptr otherwise)
+  uint32_t* cell_off;      // [n_frames][off_stride] zeroed counts of key = species * nc + cell
+  int64_t off_stride;
+  uint32_t* rank;          // [n_frames][frame_stride] rank of the atom inside its (species, cell)
+  CellGrid grid;
   uint32_t* frame_flags;   // [n_frames], zeroed by the kernel's caller
   float box[3];
 };
@@ -45,10 +54,6 @@ constexpr uint32_t MDS_FRAME_OUT_B = 2u;  // a coordinate outside [-5L/8, 5L/8]
 constexpr uint32_t MDS_FRAME_FAR = 4u;    // a coordinate beyond 8 box lengths: cell path declines
 
 // ---- rdf_cells.cu ----
-struct CellGrid {
-  int nx, ny, nz, nc;  // cells per dimension, nc = nx * ny * nz (each >= 3)
-  float box[3];
-};
 struct CellsParams {
   const float4* spos;         // [n_frames][frame_stride] atoms sorted by (species, cell)
   int64_t frame_stride;
@@ -68,8 +73,8 @@ struct CellsParams {
   uint32_t flush_threshold;   // candidate pairs per CTA between histogram flushes (<= 2^30)
 };
 size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem);
-cudaError_t launch_cell_build(const PackParams& pp, const CellGrid& g, int n_species,
-                              uint32_t* cell_off, int64_t off_stride, float4* sorted,
+// pp must have cell_off / rank / grid set: pack + count, scan, scatter into `sorted`
+cudaError_t launch_cell_build(const PackParams& pp, int n_species, float4* sorted,
                               cudaStream_t stream);
 cudaError_t launch_cells(const CellsParams& p, int sm_count, cudaStream_t stream, int* grid_out);
 

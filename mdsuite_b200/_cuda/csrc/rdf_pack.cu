@@ -1,5 +1,6 @@
 // Pack kernel: raw float32 xyz frames (either layout of include/mds_rdf.h) -> the internal
-// per-frame float4 array the pair kernels read.
+// per-frame quad-block array the pair kernels read (rdf_common.cuh: x[4] y[4] z[4] per four
+// atoms, 12 B per atom; species segments padded to multiples of four with NaN atoms).
 //
 // Follows the data preparation of the reference's batch loop:
 //   _format_data  calculators/radial_distribution_function.py:535-563  (species concatenated)
@@ -29,14 +30,28 @@ __global__ void __launch_bounds__(256) rdf_pack_kernel(const PackParams p) {
       f = g / p.n_packed;
       q = g % p.n_packed;
     }
+    float* dst = p.out + (f * p.frame_stride + (q & ~3LL)) * 3 + (q & 3);
     const long long a = p.src_index[q];
+    if (a < 0) {  // padding slot at the end of a species segment: never inside the cutoff
+      const float nan = __int_as_float(0x7fc00000);
+      dst[0] = nan; dst[4] = nan; dst[8] = nan;
+      continue;
+    }
     const float* src = (p.layout == MDS_LAYOUT_ATOM_MAJOR_XYZ)
                            ? p.xyz + (a * p.n_frames_total + p.frame0 + f) * 3
                            : p.xyz + ((p.frame0 + f) * p.n_atoms + a) * 3;
     const float x = __ldg(src), y = __ldg(src + 1), z = __ldg(src + 2);
-    p.out[f * p.frame_stride + q] = make_float4(x, y, z, __int_as_float(p.species[q]));
-    const uint32_t bits = window_bits(x, p.box[0]) | window_bits(y, p.box[1]) |
-                          window_bits(z, p.box[2]);
+    dst[0] = x; dst[4] = y; dst[8] = z;
+    uint32_t bits = window_bits(x, p.box[0]) | window_bits(y, p.box[1]) | window_bits(z, p.box[2]);
+    if (p.cell_off) {
+      // cell-list path: one global atomic per atom gives its rank inside (species, cell)
+      const int key = p.species[q] * p.grid.nc + cell_of(x, y, z, p.grid);
+      p.rank[f * p.frame_stride + q] = atomicAdd(p.cell_off + f * p.off_stride + key, 1u);
+      // a coordinate further than 8 box lengths out (or infinite): the cell margin no longer
+      // covers the float32 rounding of the reference's own arithmetic -> all-pairs for this frame
+      if (fabsf(x) > 8.0f * p.box[0] || fabsf(y) > 8.0f * p.box[1] || fabsf(z) > 8.0f * p.box[2])
+        bits |= MDS_FRAME_FAR;
+    }
     if (bits && (p.frame_flags[f] & bits) != bits) atomicOr(p.frame_flags + f, bits);
   }
 }

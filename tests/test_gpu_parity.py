@@ -49,7 +49,9 @@ def assert_same(got, want, st=None, ev=None):
     assert diff.size == 0, f"{len(diff)} bins differ, first: {diff[:5].tolist()} " \
                            f"got {got[tuple(diff[0])]} want {want[tuple(diff[0])]}"
     if st is not None and ev is not None:
-        assert st.pairs_evaluated == ev
+        assert st.pairs_allpairs_equiv == ev
+        if st.path == _cuda.PATH_ALLPAIRS:
+            assert st.pairs_evaluated == ev
         assert st.pairs_binned == float(want.sum())
 
 
