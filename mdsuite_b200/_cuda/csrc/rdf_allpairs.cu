@@ -23,6 +23,9 @@
 
 namespace mds {
 
+#ifndef MDS_COND
+#define MDS_COND false
+#endif
 constexpr int TJ = 512;                          // column atoms per shared-memory tile
 constexpr int TJ_F4 = TJ / 4 * 3;                // float4 rows per tile stage (quad blocks), 6 KB
 
@@ -34,9 +37,11 @@ __device__ __forceinline__ void pair_tile(const float4* __restrict__ jt, int cnt
                                           const float (&xi)[R], const float (&yi)[R],
                                           const float (&zi)[R], const int (&ig)[R], float bx,
                                           float by, float bz, float s_cut, float inv_step,
-                                          uint32_t c_edge, uint32_t d_hist,
+                                          float inv_hi, uint32_t c_edge, uint32_t c_hist,
+                                          uint32_t four,
                                           const float* __restrict__ edges_g,
                                           unsigned long long* hist_g) {
+  float hi = 0.f;  // last table entry a lane looked up (see bin_count_dense)
 #pragma unroll 1
   for (int jj = 0; jj < cnt; jj += 4, jt += 3) {
     const float4 X = jt[0], Y = jt[1], Z = jt[2];
@@ -49,13 +54,14 @@ __device__ __forceinline__ void pair_tile(const float4* __restrict__ jt, int cnt
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (HIST_SMEM && DENSE) {
-          bin_count_dense<DIAG>(s[c], s_cut, inv_step, c_edge, d_hist, jg + c, ig[r]);
+          bin_count_dense<DIAG, MDS_COND>(s[c], s_cut, inv_step, inv_hi, c_edge, c_hist, four, jg + c,
+                                      ig[r], hi);
         } else {
           bool in = s[c] < s_cut;  // false for NaN (padding rows / columns, NaN input)
           if (DIAG) in = in && (jg + c > ig[r]);
           if (in) {
             if (HIST_SMEM) {
-              bin_count(s[c], inv_step, c_edge, d_hist);
+              bin_count(s[c], inv_step, c_edge, c_hist, four);
             } else {
               atomicAdd(hist_g + bin_of_s(s[c], inv_step, edges_g), 1ull);
             }
@@ -91,8 +97,8 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* jt = reinterpret_cast<float4*>(smem_raw);                  // [2][TJ_F4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(jt + 2 * TJ_F4);      // [2]
-  volatile int* s_item = reinterpret_cast<volatile int*>(bars + 2);  // 16 B slot
-  float* s_edges = reinterpret_cast<float*>(bars + 4);
+  volatile int* s_item = reinterpret_cast<volatile int*>(bars + 2);  // 32 B: item + constants
+  float* s_edges = reinterpret_cast<float*>(bars + 6);
   const int n_edges = p.nbins + 2;
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_edges + ((n_edges + 3) & ~3));
   const int hist_stride = p.nbins + 1;  // slot nbins of every pair is the out-of-cutoff sink
@@ -112,14 +118,19 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
     // sees opaque registers: folded into the address arithmetic as known constants they cost two
     // extra integer instructions per pair (LEA + IADD3 with the split magic constant).
     s_item[1] = (int)(smem_u32(s_edges + 1) - kMagic4);
-    s_item[2] = (int)(smem_u32(s_hist) - smem_u32(s_edges + 1));
+    s_item[2] = (int)(smem_u32(s_hist) - kMagic4);
+    s_item[4] = 4;
+    s_item[5] = 4;
   }
   __syncthreads();
 
   const uint32_t c_edge = (uint32_t)s_item[1];
-  const uint32_t hist0_rel = (uint32_t)s_item[2];
+  const uint32_t hist0 = (uint32_t)s_item[2];
+  // read through a lane-dependent address so that ptxas keeps it in a vector register (as a
+  // uniform register it would need a MOV in front of every IMAD that also takes c_edge / c_hist)
+  const uint32_t four = (uint32_t)s_item[4 + (tid & 1)];
   const float bx = p.box[0], by = p.box[1], bz = p.box[2];
-  const float s_cut = p.s_cut, inv_step = p.inv_step;
+  const float s_cut = p.s_cut, inv_step = p.inv_step, inv_hi = p.inv_step_hi;
   const bool dense = HIST_SMEM && (p.dense != 0);
   const long long total = (long long)p.n_items * (long long)p.n_frames;
   uint32_t ph0 = 0, ph1 = 0;
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
       }
     }
 
-    const uint32_t d_hist = hist0_rel + (uint32_t)((it.pair - p.pair_lo) * hist_stride) * 4u;
+    const uint32_t c_hist = hist0 + (uint32_t)((it.pair - p.pair_lo) * hist_stride) * 4u;
     unsigned long long* hist_g = p.counts + (long long)it.pair * p.nbins;
     const int n_cols = it.j1 - it.j0;
     const int n_tiles = (n_cols + TJ - 1) / TJ;
@@ -180,7 +191,8 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
       const bool diag = it.diag && (jbase < it.i0 + it.i_cnt);
 #define MDS_TILE(FASTV, DIAGV, DENSEV)                                                         \
   pair_tile<R, FASTV, DIAGV, HIST_SMEM, DENSEV>(tile, cnt, jbase, xi, yi, zi, ig, bx, by, bz,     \
-                                                s_cut, inv_step, c_edge, d_hist, p.edges, hist_g)
+                                                s_cut, inv_step, inv_hi, c_edge, c_hist, four, p.edges, \
+                                                hist_g)
       if (dense) {
         if (fast) { if (diag) MDS_TILE(true, true, true); else MDS_TILE(true, false, true); }
         else      { if (diag) MDS_TILE(false, true, true); else MDS_TILE(false, false, true); }
@@ -210,7 +222,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
 // ---- host-side launch table ----------------------------------------------------------------
 
 size_t allpairs_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem) {
-  size_t b = 2 * TJ_F4 * sizeof(float4) + 4 * sizeof(uint64_t);
+  size_t b = 2 * TJ_F4 * sizeof(float4) + 6 * sizeof(uint64_t);
   if (hist_in_smem) {
     b += (size_t)((nbins + 2 + 3) & ~3) * sizeof(float);
     b += (size_t)pair_cnt * (size_t)(nbins + 1) * sizeof(uint32_t);

@@ -99,7 +99,7 @@ struct mds_rdf {
   int n_pairs = 0;
   double pairs_per_frame = 0;  // the reference's (row, col) count per frame for this mode
   std::vector<float> edges;
-  float s_cut = 0.f, inv_step = 0.f;
+  float s_cut = 0.f, inv_step = 0.f, inv_step_hi = 0.f;
   std::vector<int32_t> poff, pcnt;  // packed offsets / counts per species
   int variant = 2;
   std::vector<mds::PairItem> items;
@@ -251,6 +251,7 @@ mds::AllPairsParams allpairs_params(mds_rdf* h, int buf, int64_t n_frames, int p
   ap.hist_in_smem = h->hist_in_smem ? 1 : 0;
   ap.s_cut = h->s_cut;
   ap.inv_step = h->inv_step;
+  ap.inv_step_hi = h->inv_step_hi;
   ap.dense = h->dense ? 1 : 0;
   for (int k = 0; k < 3; ++k) ap.box[k] = h->box[k];
   ap.frame_need_bits = 0;
@@ -529,6 +530,7 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
 
   build_threshold_table(h->cutoff, h->nbins, h->edges, h->s_cut);
   h->inv_step = (float)((double)h->nbins / (double)h->cutoff * (double)mds::kBinGuessBias);
+  h->inv_step_hi = (float)((double)h->nbins / (double)h->cutoff / (double)mds::kBinGuessBias);
 
   // ---- path: all-pairs tiles or cell list ------------------------------------------------
   // Cell width >= 1.001 x cutoff, at least 3 cells per dimension so that the 27

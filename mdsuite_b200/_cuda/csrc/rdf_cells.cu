@@ -108,10 +108,11 @@ __device__ __forceinline__ void cell_chunk(const float* __restrict__ tl, int cnt
                                            const float (&xi)[RMAX], const float (&yi)[RMAX],
                                            const float (&zi)[RMAX], const int (&il)[RMAX],
                                            float bx, float by, float bz, float s_cut,
-                                           float inv_step, uint32_t c_edge, uint32_t d_hist,
-                                           const float* __restrict__ edges_g,
+                                           float inv_step, uint32_t c_edge, uint32_t c_hist,
+                                           uint32_t four, const float* __restrict__ edges_g,
                                            unsigned long long* hist_g) {
-#pragma unroll 2
+  float hi = 0.f;
+#pragma unroll 1
   for (int c0 = ph * 2; c0 < cnt; c0 += 8) {
     const float* b = tl + (c0 >> 2) * QUAD_FLOATS + (c0 & 2);
     const float2 X = *reinterpret_cast<const float2*>(b);
@@ -125,7 +126,8 @@ __device__ __forceinline__ void cell_chunk(const float* __restrict__ tl, int cnt
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         if (HIST_SMEM) {
-          bin_count_dense<DIAG>(s[c], s_cut, inv_step, c_edge, d_hist, q + c, il[r]);
+          bin_count_dense<DIAG, false>(s[c], s_cut, inv_step, 0.f, c_edge, c_hist, four, q + c,
+                                       il[r], hi);
         } else {
           bool in = s[c] < s_cut;  // false for NaN (padding rows / columns, NaN input)
           if (DIAG) in = in && (q + c > il[r]);
@@ -133,6 +135,70 @@ __device__ __forceinline__ void cell_chunk(const float* __restrict__ tl, int cnt
         }
       }
     }
+  }
+}
+
+// Everything a warp needs to walk the column stream of its current work item.
+struct WarpStream {
+  float* tile;             // [2][CH * 3] this warp's staging tile (quad blocks)
+  const int* t_qend;       // span table: stream position where span k ends ...
+  const int* t_off;        // ... and (first sorted index of span k) - (stream position of its start)
+  const float4* fpos;      // sorted atoms of the frame
+  int total;               // stream length
+  int lane, ph, st_off;
+  float bx, by, bz, s_cut, inv_step;
+  uint32_t c_edge, c_hist, four;
+  const float* edges_g;
+  unsigned long long* hist_g;
+};
+
+// Columns [qs, qe) of the stream against the register rows of the warp: lanes gather 32 columns
+// at a time (one LDG.128 each, issued a whole chunk ahead of its use), transpose them into the
+// quad-block tile, and every lane then evaluates its (row group, column phase) share.  Only the
+// chunks below diag_end (the pass's own block of the own cell) need the col > row mask.
+template <int R, bool FAST, bool HIST_SMEM>
+__device__ __forceinline__ void cell_stream(const WarpStream& w, int qs, int qe, int diag_end,
+                                            const float (&xi)[RMAX], const float (&yi)[RMAX],
+                                            const float (&zi)[RMAX], const int (&il)[RMAX]) {
+  const float4 nan4 = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
+                                  __int_as_float(0x7fc00000), 0.f);
+  int k = 0, cur_end = w.t_qend[0], cur_off = w.t_off[0];
+  auto fetch = [&](int q) {
+    float4 v = nan4;  // slots past the end hold NaN atoms (never inside the cutoff)
+    if (q < qe) {
+      while (q >= cur_end) {
+        ++k;
+        cur_end = w.t_qend[k];
+        cur_off = w.t_off[k];
+      }
+      v = __ldg(w.fpos + cur_off + q);
+    }
+    return v;
+  };
+  float4 nxt = fetch(qs + w.lane);
+  __syncwarp();  // the previous stream's readers are done with the tile
+  w.tile[w.st_off] = nxt.x; w.tile[w.st_off + 4] = nxt.y; w.tile[w.st_off + 8] = nxt.z;
+  __syncwarp();
+  int st = 0;
+#pragma unroll 1
+  for (int q0 = qs; q0 < qe; q0 += CH, st ^= 1) {
+    const int cnt = min(CH, qe - q0);
+    nxt = fetch(q0 + CH + w.lane);
+    const float* tl = w.tile + st * (CH * 3);
+    if (q0 < diag_end)  // one chunk per pass: always the RMAX body (idle row slots hold NaN),
+                        // so the masked variant exists once instead of once per R
+      cell_chunk<RMAX, FAST, true, HIST_SMEM>(tl, cnt, q0, w.ph, xi, yi, zi, il, w.bx, w.by, w.bz,
+                                              w.s_cut, w.inv_step, w.c_edge, w.c_hist, w.four,
+                                              w.edges_g, w.hist_g);
+    else
+      cell_chunk<R, FAST, false, HIST_SMEM>(tl, cnt, q0, w.ph, xi, yi, zi, il, w.bx, w.by, w.bz,
+                                            w.s_cut, w.inv_step, w.c_edge, w.c_hist, w.four,
+                                            w.edges_g, w.hist_g);
+    if (q0 + CH < qe) {  // warp-uniform: another chunk follows
+      float* o = w.tile + (st ^ 1) * (CH * 3) + w.st_off;
+      o[0] = nxt.x; o[4] = nxt.y; o[8] = nxt.z;
+    }
+    __syncwarp();
   }
 }
 
@@ -152,12 +218,12 @@ __device__ __forceinline__ void flush_hist_warp(uint32_t* s_hist, const CellsPar
 }
 
 template <bool HIST_SMEM>
-__global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsParams p) {
+__global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tiles = reinterpret_cast<float*>(smem_raw);                // [WARPS][2][CH * 3] quad blocks
   int* span_tab = reinterpret_cast<int*>(tiles + CELL_WARPS * 2 * CH * 3);   // [WARPS][2][MAX_SPANS]
-  uint32_t* s_evals = reinterpret_cast<uint32_t*>(span_tab + CELL_WARPS * 2 * MAX_SPANS);  // [4]
-  float* s_edges = reinterpret_cast<float*>(s_evals + 4);
+  uint32_t* s_evals = reinterpret_cast<uint32_t*>(span_tab + CELL_WARPS * 2 * MAX_SPANS);  // [8]
+  float* s_edges = reinterpret_cast<float*>(s_evals + 8);
   const int n_edges = p.nbins + 2;
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_edges + ((n_edges + 3) & ~3));
   const int hist_stride = p.nbins + 1;
@@ -172,7 +238,9 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
     s_evals[0] = 0u;
     // address constants of the binning sequence, made opaque to ptxas (see rdf_allpairs.cu)
     s_evals[1] = smem_u32(s_edges + 1) - kMagic4;
-    s_evals[2] = smem_u32(s_hist) - smem_u32(s_edges + 1);
+    s_evals[2] = smem_u32(s_hist) - kMagic4;
+    s_evals[4] = 4u;
+    s_evals[5] = 4u;
   }
   __syncthreads();
 
@@ -183,7 +251,8 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
   int* t_qend = span_tab + warp * 2 * MAX_SPANS;
   int* t_off = t_qend + MAX_SPANS;
   const uint32_t c_edge = *reinterpret_cast<volatile uint32_t*>(s_evals + 1);
-  const uint32_t hist0_rel = *reinterpret_cast<volatile uint32_t*>(s_evals + 2);
+  const uint32_t hist0 = *reinterpret_cast<volatile uint32_t*>(s_evals + 2);
+  const uint32_t four = *reinterpret_cast<volatile uint32_t*>(s_evals + 4 + (lane & 1));
   const float bx = p.box[0], by = p.box[1], bz = p.box[2];
   const float s_cut = p.s_cut, inv_step = p.inv_step;
   const int nx = p.nx, ny = p.ny, nz = p.nz, nc = p.nc;
@@ -192,6 +261,20 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
   const uint32_t publish_every = max(1u, p.flush_threshold >> 6);
   unsigned long long evaluated = 0;  // warp-uniform statistics
   uint32_t unpublished = 0;          // candidate pairs since this warp last told the CTA
+
+  WarpStream ws;
+  ws.tile = tile;
+  ws.t_qend = t_qend;
+  ws.t_off = t_off;
+  ws.lane = lane;
+  ws.ph = ph;
+  ws.st_off = st_off;
+  ws.bx = bx; ws.by = by; ws.bz = bz;
+  ws.s_cut = s_cut;
+  ws.inv_step = inv_step;
+  ws.c_edge = c_edge;
+  ws.four = four;
+  ws.edges_g = p.edges;
 
   unsigned long long nxt_raw = 0;
   if (lane == 0) nxt_raw = atomicAdd(p.work_counter, 1ull);
@@ -270,8 +353,10 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
       }
       __syncwarp();
 
-      const uint32_t d_hist = hist0_rel + (uint32_t)(pr * hist_stride) * 4u;
-      unsigned long long* hist_g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
+      ws.fpos = fpos;
+      ws.total = total;
+      ws.c_hist = hist0 + (uint32_t)(pr * hist_stride) * 4u;
+      ws.hist_g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
 
       // ---- row passes of up to 32 atoms of the cell ----
       for (int rp = 0; rp < n; rp += 8 * RMAX) {
@@ -290,55 +375,25 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
           }
         }
         // same species: columns q <= row are masked, so the stream starts at the pass's own block
+        // and only that block needs the mask
         const int qs = same ? rp : 0;
-        int k = 0;
-        float4 nxt = nan4;  // slots past the end of the stream hold NaN atoms (never in cutoff)
-        {
-          const int q = qs + lane;
-          if (q < total) {
-            while (q >= t_qend[k]) ++k;
-            nxt = __ldg(fpos + t_off[k] + q);
-          }
-        }
-        __syncwarp();
-        tile[st_off] = nxt.x; tile[st_off + 4] = nxt.y; tile[st_off + 8] = nxt.z;
-        __syncwarp();
-        int st = 0;
-        for (int q0 = qs; q0 < total; q0 += CH, st ^= 1) {
-          const int cnt = min(CH, total - q0);
-          const int qn = q0 + CH + lane;
-          const bool more = q0 + CH < total;  // warp-uniform: another chunk follows
-          nxt = nan4;
-          if (qn < total) {
-            while (qn >= t_qend[k]) ++k;
-            nxt = __ldg(fpos + t_off[k] + qn);
-          }
-          const float* tl = tile + st * CH * 3;
-          const bool diag = same && (q0 < rp + 8 * RMAX);
-#define MDS_CHUNK(RV, FASTV, DIAGV)                                                             \
-  cell_chunk<RV, FASTV, DIAGV, HIST_SMEM>(tl, cnt, q0, ph, xi, yi, zi, il, bx, by, bz, s_cut,       \
-                                          inv_step, c_edge, d_hist, p.edges, hist_g)
-#define MDS_CHUNK_R(RV)                                                                         \
-  do { if (diag) MDS_CHUNK(RV, true, true); else MDS_CHUNK(RV, true, false); } while (0)
+        const int diag_end = same ? rp + 8 * RMAX : 0;
+        // sub-ranges keep the evaluation counter of the histogram-flush logic fine-grained even
+        // for absurdly crowded neighbourhoods (normally one range = the whole stream)
+        for (int qa = qs; qa < total; qa += (1 << 20)) {
+          const int qe = min(total, qa + (1 << 20));
           if (fast) {
             switch (R) {
-              case 1: MDS_CHUNK_R(1); break;
-              case 2: MDS_CHUNK_R(2); break;
-              case 3: MDS_CHUNK_R(3); break;
-              default: MDS_CHUNK_R(4); break;
+              case 1: cell_stream<1, true, HIST_SMEM>(ws, qa, qe, diag_end, xi, yi, zi, il); break;
+              case 2: cell_stream<2, true, HIST_SMEM>(ws, qa, qe, diag_end, xi, yi, zi, il); break;
+              case 3: cell_stream<3, true, HIST_SMEM>(ws, qa, qe, diag_end, xi, yi, zi, il); break;
+              default: cell_stream<4, true, HIST_SMEM>(ws, qa, qe, diag_end, xi, yi, zi, il); break;
             }
           } else {
-            if (diag) MDS_CHUNK(RMAX, false, true); else MDS_CHUNK(RMAX, false, false);
+            cell_stream<RMAX, false, HIST_SMEM>(ws, qa, qe, diag_end, xi, yi, zi, il);
           }
-#undef MDS_CHUNK_R
-#undef MDS_CHUNK
-          if (more) {
-            float* o = tile + (st ^ 1) * CH * 3 + st_off;
-            o[0] = nxt.x; o[4] = nxt.y; o[8] = nxt.z;
-          }
-          __syncwarp();
           if (HIST_SMEM) {
-            unpublished += (uint32_t)(cnt * nr);
+            unpublished += (uint32_t)(qe - qa) * (uint32_t)nr;
             if (unpublished >= publish_every) {
               uint32_t old = 0;
               if (lane == 0) old = atomicAdd(s_evals, unpublished);
@@ -380,7 +435,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 3) rdf_cells_kernel(const CellsP
 
 size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem) {
   size_t b = (size_t)CELL_WARPS * 2 * CH * 3 * sizeof(float) +
-             (size_t)CELL_WARPS * 2 * MAX_SPANS * sizeof(int) + 4 * sizeof(uint32_t);
+             (size_t)CELL_WARPS * 2 * MAX_SPANS * sizeof(int) + 8 * sizeof(uint32_t);
   if (hist_in_smem) {
     b += (size_t)((nbins + 2 + 3) & ~3) * sizeof(float);
     b += (size_t)pair_cnt * (size_t)(nbins + 1) * sizeof(uint32_t);

@@ -45,7 +45,8 @@ struct AllPairsParams {
   int32_t pair_cnt;           // number of species pairs held by this launch
   int32_t hist_in_smem;       // 0: histogram bins live in global memory (very large nbins)
   float s_cut;                // in-cutoff  <=>  s < s_cut
-  float inv_step;             // float32(nbins / cutoff) * (1 - 2^-20): seeds the bin guess
+  float inv_step;             // float32(nbins / cutoff * (1 - 2^-20)): seeds the bin guess k~ <= k
+  float inv_step_hi;          // float32(nbins / cutoff * (1 + 2^-20)): the opposite guess k^ >= k
   int32_t dense;              // 1: predicated binning (most pairs in cutoff), 0: branch
   float box[3];
   uint32_t frame_need_bits;   // nonzero: only frames whose flags have one of these bits
@@ -185,57 +186,94 @@ __device__ __forceinline__ int bin_of_s(float s, float inv_step_biased,
   return k + ((s >= edges[k + 1]) ? 1 : 0);
 }
 
-// Shared-memory paths.  c_edge = smem address of edges[1] minus kMagic4, d_hist = smem address
-// of the pair's hist[0] minus smem address of edges[1]:
-//   a = bits(f) * 4 + c_edge  = &edges[k~ + 1]      h = a + d_hist = &hist[k~]
+// Shared-memory paths.  c_edge = smem address of edges[1] minus kMagic4, c_hist = smem address
+// of the pair's hist[0] minus kMagic4, four = the constant 4 in a register ptxas cannot see
+// through (read back from shared memory): with it the two address computations stay IMADs on the
+// FMA pipe instead of LEA / IADD3 on the half-rate ALU pipe, which ncu shows as the busiest one.
+//   e = bits(f) * 4 + c_edge = &edges[k~ + 1]      h = bits(f) * 4 + c_hist = &hist[k~]
 //
 // Dense path: branch-free and unpredicated.  The squared distance is clamped to s_cut (NaN and,
 // on diagonal tiles, col <= row pairs clamp to s_cut too), which lands in the overflow slot
 // hist[nbins] that is never merged — so the cutoff test costs one FMNMX and every lane runs the
-// same 9 instructions.
-template <bool DIAG>
-__device__ __forceinline__ void bin_count_dense(float s, float s_cut, float inv_step_biased,
-                                                uint32_t c_edge, uint32_t d_hist, int jg, int ig) {
+// same instructions.
+//
+// COND = true adds a second guess with the opposite bias, k^ = floor(sqrt.approx(s) * inv_hi) with
+// inv_hi = (nbins / cutoff) * (1 + 2^-20) >= the exact quotient: k~ <= k <= k^, so when the two
+// agree (all but ~k * 2^-19 of the lanes) the bin is settled without touching the table and the
+// LDS is predicated off.  It trades one FFMA + one ISETP for ~2.5 shared-memory wavefronts per
+// warp (32 random table addresses conflict on banks) — worth it where the LSU data pipe is the
+// limiter (all-pairs kernel, most pairs inside the cutoff), not where it is idle (cell kernel).
+// `hi` is carried by the caller between calls: a lane that skips the load keeps a stale value,
+// which the AND with p makes irrelevant (declaring it inside the asm block makes ptxas spill it).
+template <bool DIAG, bool COND>
+__device__ __forceinline__ void bin_count_dense(float s, float s_cut, float inv_lo, float inv_hi,
+                                                uint32_t c_edge, uint32_t c_hist, uint32_t four,
+                                                int jg, int ig, float& hi) {
   float t = fminf(s, s_cut);  // min.f32 returns the non-NaN operand
   if (DIAG) t = (jg > ig) ? t : s_cut;
-  asm volatile(
-      "{\n"
-      ".reg .pred q;\n"
-      ".reg .f32 d, f, hi;\n"
-      ".reg .u32 a, h;\n"
-      "sqrt.approx.ftz.f32 d, %0;\n"
-      "fma.rz.f32 f, d, %1, 0f4B000000;\n"
-      "mov.b32 a, f;\n"
-      "mad.lo.u32 a, a, 4, %2;\n"
-      "ld.shared.f32 hi, [a];\n"
-      "add.u32 h, a, %3;\n"
-      "setp.ge.f32 q, %0, hi;\n"
-      "@q add.u32 h, h, 4;\n"
-      "red.shared.add.u32 [h], 1;\n"
-      "}\n" ::"f"(t),
-      "f"(inv_step_biased), "r"(c_edge), "r"(d_hist)
-      : "memory");
+  if (COND) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .f32 d, f, g;\n"
+        ".reg .u32 a, b, e, h;\n"
+        "sqrt.approx.ftz.f32 d, %1;\n"
+        "fma.rz.f32 f, d, %2, 0f4B000000;\n"
+        "fma.rz.f32 g, d, %3, 0f4B000000;\n"
+        "mov.b32 a, f;\n"
+        "mov.b32 b, g;\n"
+        "setp.ne.u32 p, a, b;\n"
+        "mad.lo.u32 e, a, %6, %4;\n"
+        "mad.lo.u32 h, a, %6, %5;\n"
+        "@p ld.shared.f32 %0, [e];\n"
+        "setp.ge.and.f32 q, %1, %0, p;\n"
+        "@q add.u32 h, h, 4;\n"
+        "red.shared.add.u32 [h], 1;\n"
+        "}\n"
+        : "+f"(hi)
+        : "f"(t), "f"(inv_lo), "f"(inv_hi), "r"(c_edge), "r"(c_hist), "r"(four)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        ".reg .f32 d, f, hi;\n"
+        ".reg .u32 a, e, h;\n"
+        "sqrt.approx.ftz.f32 d, %0;\n"
+        "fma.rz.f32 f, d, %1, 0f4B000000;\n"
+        "mov.b32 a, f;\n"
+        "mad.lo.u32 e, a, %4, %2;\n"
+        "mad.lo.u32 h, a, %4, %3;\n"
+        "ld.shared.f32 hi, [e];\n"
+        "setp.ge.f32 q, %0, hi;\n"
+        "@q add.u32 h, h, 4;\n"
+        "red.shared.add.u32 [h], 1;\n"
+        "}\n" ::"f"(t),
+        "f"(inv_lo), "r"(c_edge), "r"(c_hist), "r"(four)
+        : "memory");
+  }
 }
 
-// Sparse path: the same sequence for a pair already known to be inside the cutoff (under a branch).
-__device__ __forceinline__ void bin_count(float s, float inv_step_biased, uint32_t c_edge,
-                                          uint32_t d_hist) {
+// Sparse path: the unconditional sequence for a pair already known to be inside the cutoff (under
+// a branch).
+__device__ __forceinline__ void bin_count(float s, float inv_lo, uint32_t c_edge, uint32_t c_hist,
+                                          uint32_t four) {
   asm volatile(
       "{\n"
       ".reg .pred q;\n"
       ".reg .f32 d, f, hi;\n"
-      ".reg .u32 a, h;\n"
+      ".reg .u32 a, e, h;\n"
       "sqrt.approx.ftz.f32 d, %0;\n"
       "fma.rz.f32 f, d, %1, 0f4B000000;\n"
       "mov.b32 a, f;\n"
-      "mad.lo.u32 a, a, 4, %2;\n"
-      "ld.shared.f32 hi, [a];\n"
-      "add.u32 h, a, %3;\n"
+      "mad.lo.u32 e, a, %4, %2;\n"
+      "mad.lo.u32 h, a, %4, %3;\n"
+      "ld.shared.f32 hi, [e];\n"
       "setp.ge.f32 q, %0, hi;\n"
       "@q add.u32 h, h, 4;\n"
       "red.shared.add.u32 [h], 1;\n"
       "}\n" ::"f"(s),
-      "f"(inv_step_biased), "r"(c_edge), "r"(d_hist)
+      "f"(inv_lo), "r"(c_edge), "r"(c_hist), "r"(four)
       : "memory");
 }
 
