@@ -32,7 +32,10 @@ constexpr int TJ_F4 = TJ / 4 * 3;                // float4 rows per tile stage (
 // One tile of columns (quad blocks in shared memory) against the R register rows of a thread.
 // Every block of four columns is three broadcast LDS.128; each (row, column pair) goes through
 // the packed FADD2 / FMUL2 sequence of pair2_s.
-template <int R, bool FAST, bool DIAG, bool HIST_SMEM, bool DENSE>
+// RA <= R is the number of row registers that can hold a counted pair for these columns: row
+// tiles at the end of a species fill fewer than R registers, and below the diagonal whole
+// registers are masked — they are skipped instead of being evaluated into the sink.
+template <int R, int RA, bool FAST, bool DIAG, bool HIST_SMEM, bool DENSE>
 __device__ __forceinline__ void pair_tile(const float4* __restrict__ jt, int cnt, int jbase,
                                           const float (&xi)[R], const float (&yi)[R],
                                           const float (&zi)[R], const int (&ig)[R], float bx,
@@ -47,7 +50,7 @@ __device__ __forceinline__ void pair_tile(const float4* __restrict__ jt, int cnt
     const float4 X = jt[0], Y = jt[1], Z = jt[2];
     const int jg = jbase + jj;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < RA; ++r) {
       float s[4];
       pair2_s<FAST>(X.x, X.y, Y.x, Y.y, Z.x, Z.y, xi[r], yi[r], zi[r], bx, by, bz, s[0], s[1]);
       pair2_s<FAST>(X.z, X.w, Y.z, Y.w, Z.z, Z.w, xi[r], yi[r], zi[r], bx, by, bz, s[2], s[3]);
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
     }
 
     const uint32_t c_hist = hist0 + (uint32_t)((it.pair - p.pair_lo) * hist_stride) * 4u;
+    const int r_item = min(R, (it.i_cnt + THREADS - 1) / THREADS);  // row registers in use
     unsigned long long* hist_g = p.counts + (long long)it.pair * p.nbins;
     const int n_cols = it.j1 - it.j0;
     const int n_tiles = (n_cols + TJ - 1) / TJ;
@@ -188,18 +192,44 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
       const int jbase = it.j0 + t * TJ;
       const int cnt = min(TJ, it.j1 - jbase);
       const float4* tile = jt + st * TJ_F4;
-      const bool diag = it.diag && (jbase < it.i0 + it.i_cnt);
-#define MDS_TILE(FASTV, DIAGV, DENSEV)                                                         \
-  pair_tile<R, FASTV, DIAGV, HIST_SMEM, DENSEV>(tile, cnt, jbase, xi, yi, zi, ig, bx, by, bz,     \
-                                                s_cut, inv_step, inv_hi, c_edge, c_hist, four, p.edges, \
-                                                hist_g)
-      if (dense) {
-        if (fast) { if (diag) MDS_TILE(true, true, true); else MDS_TILE(true, false, true); }
-        else      { if (diag) MDS_TILE(false, true, true); else MDS_TILE(false, false, true); }
-      } else {
-        if (fast) { if (diag) MDS_TILE(true, true, false); else MDS_TILE(true, false, false); }
-        else      { if (diag) MDS_TILE(false, true, false); else MDS_TILE(false, false, false); }
+      // Segments of THREADS columns: row register r holds rows [i0 + r THREADS, i0 + (r+1) THREADS),
+      // so on a same-species item the columns of segment g = (col - i0) / THREADS can only pair
+      // (col > row) with registers r <= g, and need the mask only while g < r_item.
+#define MDS_TILE(RAV, FASTV, DIAGV, DENSEV)                                                    \
+  pair_tile<R, RAV, FASTV, DIAGV, HIST_SMEM, DENSEV>(seg, scnt, sbase, xi, yi, zi, ig, bx, by, bz, \
+                                                     s_cut, inv_step, inv_hi, c_edge, c_hist,   \
+                                                     four, p.edges, hist_g)
+#define MDS_TILE_FD(RAV)                                                                       \
+  do {                                                                                         \
+    if (dense) { if (dg) MDS_TILE(RAV, true, true, true); else MDS_TILE(RAV, true, false, true); } \
+    else { if (dg) MDS_TILE(RAV, true, true, false); else MDS_TILE(RAV, true, false, false); }  \
+  } while (0)
+      const int seg_cols = (it.diag && jbase < it.i0 + r_item * THREADS) ? THREADS : TJ;
+      for (int c0 = 0; c0 < cnt; c0 += seg_cols) {
+        const float4* seg = tile + (c0 >> 2) * 3;
+        const int scnt = min(seg_cols, cnt - c0);
+        const int sbase = jbase + c0;
+        int ra = r_item;
+        bool dg = false;
+        if (it.diag) {
+          const int g = (sbase - it.i0) / THREADS;
+          ra = min(r_item, g + 1);
+          dg = g < r_item;
+        }
+        if (!fast) {  // literal minimum image (rare): always the full-R bodies
+          if (dense) { if (dg) MDS_TILE(R, false, true, true); else MDS_TILE(R, false, false, true); }
+          else { if (dg) MDS_TILE(R, false, true, false); else MDS_TILE(R, false, false, false); }
+        } else if (R >= 4 && ra >= 4) {
+          MDS_TILE_FD(R >= 4 ? 4 : R);
+        } else if (R >= 3 && ra == 3) {
+          MDS_TILE_FD(R >= 3 ? 3 : R);
+        } else if (R >= 2 && ra == 2) {
+          MDS_TILE_FD(R >= 2 ? 2 : R);
+        } else {
+          MDS_TILE_FD(1);
+        }
       }
+#undef MDS_TILE_FD
 #undef MDS_TILE
       __syncthreads();  // tile `st` fully consumed before it is refilled two iterations later
     }
