@@ -66,6 +66,21 @@ def make_workload(name: str, rank: int, frames: int):
         sysm = synthetic.ideal_gas(50000, frames, seed=5 + 1000 * rank)
         cutoff, nbins = 49.9, 1000
         desc = f"cfg5: 50k-atom ideal gas, {frames} configurations, cutoff 49.9, 1000 bins"
+    elif name == "cfg5_rc10":
+        sysm = synthetic.ideal_gas(50000, frames, seed=5 + 1000 * rank)
+        cutoff, nbins = 10.0, 1000
+        desc = (f"cfg5: 50k-atom ideal gas, {frames} configurations, cutoff 10, 1000 bins "
+                f"(cell-list path)")
+    elif name == "cfg3":
+        sysm = synthetic.lj_fluid(46, frames, seed=3 + 1000 * rank)
+        cutoff, nbins = 3.0, 300
+        desc = (f"cfg3: {sysm.n_atoms}-atom LJ fluid (46^3, rho*=0.8442), {frames} configurations "
+                f"per GPU, cutoff 3.0 sigma, 300 bins, cell-list path, parity mode")
+    elif name == "cfg4":
+        sysm = synthetic.spc_water(69, frames, seed=4 + 1000 * rank)
+        cutoff, nbins = 8.0, 800
+        desc = (f"cfg4: {sysm.n_atoms}-atom SPC water (69^3 molecules), {frames} configurations "
+                f"per GPU, cutoff 8 A, 800 bins, 3 species pairs, cell-list path, parity mode")
     else:
         raise SystemExit(f"unknown workload {name}")
     return sysm, cutoff, nbins, desc
@@ -219,6 +234,42 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------------
+def cell_list_probe(device: int, fp32_peak: float, frames: int = 160):
+    """cfg3-shaped (97k-atom LJ fluid, cutoff 3 sigma, 300 bins) frames resident in HBM through the
+    cell-list kernel: candidate-pair rate against the same FP32 roofline, the all-pairs-equivalent
+    rate, and a parity gate against the all-pairs kernel on the same frames."""
+    import torch
+    from mdsuite_b200 import _cuda, synthetic
+    sysm = synthetic.lj_fluid(46, 4, seed=3)
+    base = torch.from_numpy(sysm.positions).cuda(device)
+    pos = base.repeat((frames + 3) // 4, 1, 1)[:frames].contiguous()
+    best = None
+    with _cuda.RDFHandle(sysm.counts, 300, 3.0, sysm.box, device=device) as h:
+        for _ in range(4):
+            h.reset()
+            h.submit_device(pos)
+            st = h.stats()
+            if best is None or st.pair_kernel_ms < best[0]:
+                best = (st.pair_kernel_ms, st.submit_ms)
+        h.reset()
+        h.submit_device(base)
+        cells = h.counts()
+    with _cuda.RDFHandle(sysm.counts, 300, 3.0, sysm.box, device=device, path="allpairs") as h:
+        h.submit_device(base)
+        allp = h.counts()
+    cand = st.pairs_evaluated / (best[0] * 1e-3)
+    return {
+        "workload": f"cfg3-shaped: {sysm.n_atoms}-atom LJ fluid, cutoff 3.0, 300 bins, {frames} frames "
+                    f"resident in HBM, best of 4",
+        "kernel": "rdf_cells_kernel", "cells": list(st.cells),
+        "candidate_pair_evals_per_s": cand, "frac_of_fp32_roofline": cand * FLOP_PER_PAIR / fp32_peak,
+        "binned_over_candidates": st.pairs_binned / st.pairs_evaluated,
+        "allpairs_equivalent_per_s": st.pairs_allpairs_equiv / (best[1] * 1e-3),
+        "us_per_frame": best[1] * 1e3 / frames,
+        "bins_differing_vs_allpairs_kernel": int((cells != allp).sum()),
+    }
+
+
 def run_ours(args):
     import torch
     from mdsuite_b200 import _cuda
@@ -332,8 +383,11 @@ def run_ours(args):
     fp32_peak = sm_count * 128 * f_max  # non-FMA FP32 issue, op/s
     launches = max(1, st.pair_kernel_launches)
     avg_launch_s = st.pair_kernel_ms * 1e-3 / launches
-    pairs_per_launch = pairs_per_step * args.steps / launches
+    # pairs the pair kernel distance-tested per launch: every reference pair on the all-pairs
+    # path, the candidates of adjacent cells on the cell-list path
+    pairs_per_launch = st.pairs_evaluated * args.steps / launches
     kernel_rate = pairs_per_launch / avg_launch_s
+    kernel_name = "rdf_cells_kernel" if st.path == _cuda.PATH_CELLLIST else "rdf_allpairs_kernel"
     achieved = kernel_rate * FLOP_PER_PAIR
     kernel_share = st.pair_kernel_ms / ms if world == 1 else None
     atom = {}
@@ -350,19 +404,24 @@ def run_ours(args):
                 "frac": kernel_rate / atomic_peak_pairs}
     except Exception as exc:  # noqa: BLE001
         atom = {"error": str(exc)}
+    # DRAM bytes per launch from the committed ncu --set full capture of this kernel
+    # (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per frame of the capture)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
             with open(tpath) as fh:
-                traffic = json.load(fh).get(args.workload)
-        except (OSError, ValueError):
+                per_frame = json.load(fh).get(args.workload, {}).get("dram_bytes_per_frame")
+            if per_frame is not None:
+                traffic = per_frame * n_frames * args.steps / launches
+        except (OSError, ValueError, AttributeError):
             traffic = None
     roofline = {
-        "bound": "fp32", "kernel": "rdf_allpairs_kernel", "achieved": achieved / 1e12,
+        "bound": "fp32", "kernel": kernel_name, "achieved": achieved / 1e12,
         "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
         "traffic": traffic, "pair_evals_per_s": kernel_rate,
         "pair_evals_per_s_peak": fp32_peak / FLOP_PER_PAIR, "flop_per_pair": FLOP_PER_PAIR,
+        "allpairs_equivalent_per_s": pairs_per_step * args.steps / launches / avg_launch_s,
         "launches_timed": st.pair_kernel_launches, "avg_launch_ms": avg_launch_s * 1e3,
         "kernel_share_of_step": kernel_share,
         "peak_source": f"{sm_count} SMs x 128 lanes x sm_max_mhz from {peaks_src} (non-FMA issue rate)",
@@ -373,6 +432,14 @@ def run_ours(args):
                 "achieved_gbs": 12.0 * n_atoms * n_frames * args.steps / launches / avg_launch_s / 1e9,
                 "peak_gbs": peaks.get("hbm_gbs")},
     }
+
+    # ---- the other kernel of the path: a short cell-list measurement (rank 0, N = 1 only) ----
+    cell_list = None
+    if world == 1 and st.path != _cuda.PATH_CELLLIST and not args.no_cell_probe:
+        try:
+            cell_list = cell_list_probe(local_rank, fp32_peak)
+        except Exception as exc:  # noqa: BLE001
+            cell_list = {"error": str(exc)}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------
     cpu_baseline = None
@@ -409,13 +476,14 @@ def run_ours(args):
                          f"{16 * n_atoms * n_frames / 1e6:.0f} MB packed per step vs 126 MB L2",
                    "parallelism": f"frames sharded over {world} GPU(s), 1 NCCL allreduce/step"
                    if world > 1 else "1 GPU"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "cell_list_path": cell_list, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "h2d_bytes_per_step": int(12 * n_atoms * n_frames),
                 "d2h_bytes_per_step": int(8 * n_pairs * nbins)},
         "gpu_launches": int(st.kernel_launches * args.steps),
         "clocks": clocks, "parity": parity,
-        "kernel_variant": {"variant": st.variant, "dense": st.dense},
+        "kernel_variant": {"path": st.path_name, "variant": st.variant, "dense": st.dense,
+                           "cells": list(st.cells)},
     }
     print(json.dumps(line))
     handle.close()
@@ -432,9 +500,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--frames", type=int, default=1000, help="configurations per GPU per step")
-    ap.add_argument("--cpu-frames", type=int, default=4,
+    ap.add_argument("--cpu-frames", type=int, default=12,
                     help="configurations timed by the op-by-op CPU baseline (x8 for the C port)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cell-probe", action="store_true",
+                    help="skip the short cfg3-shaped cell-list measurement added at N=1")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")
