@@ -95,14 +95,18 @@ __global__ void __launch_bounds__(256) rdf_cell_scatter_kernel(const PackParams 
 
 constexpr int CELL_THREADS = 256;
 constexpr int CELL_WARPS = CELL_THREADS / 32;
-constexpr int CH = 32;         // column atoms per staged chunk: one float4 per lane
+constexpr int CH = 32;         // column atoms per staged chunk: CH / 32 float4 loads per lane
+constexpr int CPL = CH / 32;   // columns staged per lane and chunk
 constexpr int MAX_SPANS = 20;  // >= 18 (9 cell rows x 2 pieces when the x window wraps)
-constexpr int RMAX = 4;        // rows per lane: one pass covers 8 * RMAX = 32 rows of a cell
+constexpr int RG = 8;          // row groups per warp (lanes with the same lane % RG share rows)
+constexpr int PH = 32 / RG;    // column phases per warp
+constexpr int RMAX = 4;        // rows per lane: one pass covers RG * RMAX = 32 rows of a cell
 
 // One chunk of staged columns (quad blocks in the warp's shared tile) against the register rows
-// of a warp.  Lane layout: row group rg = lane & 7 (rows rg, rg + 8, ...), column phase
-// ph = lane >> 3 (column pairs 2 ph, 2 ph + 8, ...): three LDS.64 with 4 distinct addresses serve
-// 2 R pair evaluations per lane through the packed FADD2 / FMUL2 sequence of pair2_s.
+// of a warp.  Lane layout: row group rg = lane % RG (rows rg, rg + RG, ...), column phase
+// ph = lane / RG (column pairs 2 ph, 2 ph + 2 PH, ...): three LDS.64 with PH distinct addresses
+// serve 2 R pair evaluations per lane through the packed FADD2 / FMUL2 sequence of pair2_s.
+// With RG = 4 a cell of n atoms occupies 4 ceil(n / 4) row slots, i.e. at most 3 idle ones.
 template <int R, bool FAST, bool DIAG, bool HIST_SMEM>
 __device__ __forceinline__ void cell_chunk(const float* __restrict__ tl, int cnt, int q0, int ph,
                                            const float (&xi)[RMAX], const float (&yi)[RMAX],
@@ -113,7 +117,7 @@ __device__ __forceinline__ void cell_chunk(const float* __restrict__ tl, int cnt
                                            unsigned long long* hist_g) {
   float hi = 0.f;
 #pragma unroll 1
-  for (int c0 = ph * 2; c0 < cnt; c0 += 8) {
+  for (int c0 = ph * 2; c0 < cnt; c0 += 2 * PH) {
     const float* b = tl + (c0 >> 2) * QUAD_FLOATS + (c0 & 2);
     const float2 X = *reinterpret_cast<const float2*>(b);
     const float2 Y = *reinterpret_cast<const float2*>(b + 4);
@@ -154,16 +158,16 @@ struct WarpStream {
 
 // Columns [qs, qe) of the stream against the register rows of the warp: lanes gather 32 columns
 // at a time (one LDG.128 each, issued a whole chunk ahead of its use), transpose them into the
-// quad-block tile, and every lane then evaluates its (row group, column phase) share.  Only the
-// chunks below diag_end (the pass's own block of the own cell) need the col > row mask.
-template <int R, bool FAST, bool HIST_SMEM>
-__device__ __forceinline__ void cell_stream(const WarpStream& w, int qs, int qe, int diag_end,
+// quad-block tile, and every lane then evaluates its (row group, column phase) share.  DIAG
+// applies the col > row mask (only the pass's own block of the own cell needs it).
+template <int R, bool FAST, bool DIAG, bool HIST_SMEM>
+__device__ __forceinline__ void cell_stream(const WarpStream& w, int qs, int qe,
                                             const float (&xi)[RMAX], const float (&yi)[RMAX],
                                             const float (&zi)[RMAX], const int (&il)[RMAX]) {
   const float4 nan4 = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
                                   __int_as_float(0x7fc00000), 0.f);
   int k = 0, cur_end = w.t_qend[0], cur_off = w.t_off[0];
-  auto fetch = [&](int q) {
+  auto fetch = [&](int q) {  // q is visited in increasing order
     float4 v = nan4;  // slots past the end hold NaN atoms (never inside the cutoff)
     if (q < qe) {
       while (q >= cur_end) {
@@ -175,29 +179,30 @@ __device__ __forceinline__ void cell_stream(const WarpStream& w, int qs, int qe,
     }
     return v;
   };
-  float4 nxt = fetch(qs + w.lane);
+  auto stage = [&](float* t, const float4 (&v)[CPL]) {
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {  // column lane + 32 u -> quad block 8 u + lane / 4
+      float* o = t + u * (8 * QUAD_FLOATS) + w.st_off;
+      o[0] = v[u].x; o[4] = v[u].y; o[8] = v[u].z;
+    }
+  };
+  float4 nxt[CPL];
+#pragma unroll
+  for (int u = 0; u < CPL; ++u) nxt[u] = fetch(qs + 32 * u + w.lane);
   __syncwarp();  // the previous stream's readers are done with the tile
-  w.tile[w.st_off] = nxt.x; w.tile[w.st_off + 4] = nxt.y; w.tile[w.st_off + 8] = nxt.z;
+  stage(w.tile, nxt);
   __syncwarp();
   int st = 0;
 #pragma unroll 1
   for (int q0 = qs; q0 < qe; q0 += CH, st ^= 1) {
     const int cnt = min(CH, qe - q0);
-    nxt = fetch(q0 + CH + w.lane);
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) nxt[u] = fetch(q0 + CH + 32 * u + w.lane);
     const float* tl = w.tile + st * (CH * 3);
-    if (q0 < diag_end)  // one chunk per pass: always the RMAX body (idle row slots hold NaN),
-                        // so the masked variant exists once instead of once per R
-      cell_chunk<RMAX, FAST, true, HIST_SMEM>(tl, cnt, q0, w.ph, xi, yi, zi, il, w.bx, w.by, w.bz,
-                                              w.s_cut, w.inv_step, w.c_edge, w.c_hist, w.four,
-                                              w.edges_g, w.hist_g);
-    else
-      cell_chunk<R, FAST, false, HIST_SMEM>(tl, cnt, q0, w.ph, xi, yi, zi, il, w.bx, w.by, w.bz,
-                                            w.s_cut, w.inv_step, w.c_edge, w.c_hist, w.four,
-                                            w.edges_g, w.hist_g);
-    if (q0 + CH < qe) {  // warp-uniform: another chunk follows
-      float* o = w.tile + (st ^ 1) * (CH * 3) + w.st_off;
-      o[0] = nxt.x; o[4] = nxt.y; o[8] = nxt.z;
-    }
+    cell_chunk<R, FAST, DIAG, HIST_SMEM>(tl, cnt, q0, w.ph, xi, yi, zi, il, w.bx, w.by, w.bz,
+                                         w.s_cut, w.inv_step, w.c_edge, w.c_hist, w.four,
+                                         w.edges_g, w.hist_g);
+    if (q0 + CH < qe) stage(w.tile + (st ^ 1) * (CH * 3), nxt);  // warp-uniform condition
     __syncwarp();
   }
 }
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsP
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_edges + ((n_edges + 3) & ~3));
   const int hist_stride = p.nbins + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rg = lane & 7, ph = lane >> 3;
+  const int rg = lane % RG, ph = lane / RG;
 
   if (HIST_SMEM) {
     for (int k = tid; k < n_edges; k += CELL_THREADS) s_edges[k] = p.edges[k];
@@ -359,14 +364,14 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsP
       ws.hist_g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
 
       // ---- row passes of up to 32 atoms of the cell ----
-      for (int rp = 0; rp < n; rp += 8 * RMAX) {
-        const int nr = min(8 * RMAX, n - rp);
-        const int R = fast ? (nr + 7) >> 3 : RMAX;
+      for (int rp = 0; rp < n; rp += RG * RMAX) {
+        const int nr = min(RG * RMAX, n - rp);
+        const int R = fast ? (nr + RG - 1) / RG : RMAX;
         float xi[RMAX], yi[RMAX], zi[RMAX];
         int il[RMAX];
 #pragma unroll
         for (int r = 0; r < RMAX; ++r) {
-          il[r] = rp + rg + 8 * r;
+          il[r] = rp + rg + RG * r;
           if (il[r] < n) {
             const float4 v = __ldg(fpos + r0 + il[r]);
             xi[r] = v.x; yi[r] = v.y; zi[r] = v.z;
@@ -377,20 +382,36 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsP
         // same species: columns q <= row are masked, so the stream starts at the pass's own block
         // and only that block needs the mask
         const int qs = same ? rp : 0;
-        const int diag_end = same ? rp + 8 * RMAX : 0;
         // sub-ranges keep the evaluation counter of the histogram-flush logic fine-grained even
         // for absurdly crowded neighbourhoods (normally one range = the whole stream)
         for (int qa = qs; qa < total; qa += (1 << 20)) {
           const int qe = min(total, qa + (1 << 20));
-          if (fast) {
-            switch (R) {
-              case 1: cell_stream<1, true, HIST_SMEM>(ws, qa, qe, diag_end, xi, yi, zi, il); break;
-              case 2: cell_stream<2, true, HIST_SMEM>(ws, qa, qe, diag_end, xi, yi, zi, il); break;
-              case 3: cell_stream<3, true, HIST_SMEM>(ws, qa, qe, diag_end, xi, yi, zi, il); break;
-              default: cell_stream<4, true, HIST_SMEM>(ws, qa, qe, diag_end, xi, yi, zi, il); break;
+          int q1 = qa;
+          if (same && qa == qs) {
+            // the pass's own block of the own cell: the only columns that need the col > row
+            // mask.  One masked body for every R (idle row slots hold NaN) keeps the code small —
+            // the kernel is sensitive to instruction-cache footprint.
+            q1 = min(qe, qa + RG * RMAX);
+            if (fast) cell_stream<RMAX, true, true, HIST_SMEM>(ws, qa, q1, xi, yi, zi, il);
+            else      cell_stream<RMAX, false, true, HIST_SMEM>(ws, qa, q1, xi, yi, zi, il);
+          }
+          if (q1 < qe) {
+            if (fast) {
+              switch (R) {
+#define MDS_STREAM(RV) cell_stream<RV, true, false, HIST_SMEM>(ws, q1, qe, xi, yi, zi, il)
+                case 1: MDS_STREAM(1); break;
+                case 2: MDS_STREAM(RMAX >= 2 ? 2 : RMAX); break;
+                case 3: MDS_STREAM(RMAX >= 3 ? 3 : RMAX); break;
+                case 4: MDS_STREAM(RMAX >= 4 ? 4 : RMAX); break;
+                case 5: MDS_STREAM(RMAX >= 5 ? 5 : RMAX); break;
+                case 6: MDS_STREAM(RMAX >= 6 ? 6 : RMAX); break;
+                case 7: MDS_STREAM(RMAX >= 7 ? 7 : RMAX); break;
+                default: MDS_STREAM(RMAX); break;
+#undef MDS_STREAM
+              }
+            } else {
+              cell_stream<RMAX, false, false, HIST_SMEM>(ws, q1, qe, xi, yi, zi, il);
             }
-          } else {
-            cell_stream<RMAX, false, HIST_SMEM>(ws, qa, qe, diag_end, xi, yi, zi, il);
           }
           if (HIST_SMEM) {
             unpublished += (uint32_t)(qe - qa) * (uint32_t)nr;

@@ -279,7 +279,10 @@ class RadialDistributionFunction(Calculator):
                 if fpb is None:
                     mm = MemoryManager(data_path=paths, database=self.experiment.database, device=dev,
                                        free_memory=None if torch.cuda.is_available() else 2 ** 30)
-                    fpb = min(mm.get_batch_size()[0], 1024)
+                    # at most 256 MB per pinned ring buffer: enough frames to hide launch latency,
+                    # bounded host memory for million-atom systems
+                    fpb = min(mm.get_batch_size()[0], 1024,
+                              max(1, (256 << 20) // (12 * max(1, sum(particles)))))
                     if self.override_n_batches:
                         fpb = max(1, int(np.ceil(len(shard) / self.override_n_batches)))
                 b = FrameBatcher(self.experiment.database, paths, particles, h, fpb, selections,
@@ -301,12 +304,20 @@ class RadialDistributionFunction(Calculator):
                 h.close()
         elapsed = time.perf_counter() - t0
         self.counts = total
-        evaluated = sum(s.pairs_evaluated for s in stats) * (world if dist is not None else 1)
-        self.run_stats = {"pairs_evaluated": evaluated, "seconds": elapsed, "devices": devices,
+        scale = world if dist is not None else 1
+        evaluated = sum(s.pairs_evaluated for s in stats) * scale
+        equivalent = sum(getattr(s, "pairs_allpairs_equiv", s.pairs_evaluated) for s in stats) * scale
+        self.run_stats = {"pairs_evaluated": evaluated, "pairs_allpairs_equivalent": equivalent,
+                          "seconds": elapsed, "devices": devices,
                           "world_size": world, "frames": int(len(frames)),
+                          "path": getattr(stats[0], "path_name", "allpairs") if stats else None,
+                          "cells": tuple(getattr(stats[0], "cells", (0, 0, 0))) if stats else None,
+                          "frames_far": sum(getattr(s, "frames_far", 0) for s in stats),
                           "frames_general_minimage": sum(s.frames_general_minimage for s in stats)}
-        log.info(f"RDF: {evaluated:.3e} pair evaluations in {elapsed:.3f} s "
-                 f"({evaluated / max(elapsed, 1e-12):.3e} pair evals/s) on {len(devices) * world} GPU(s)")
+        log.info(f"RDF ({self.run_stats['path']}): {evaluated:.3e} pair evaluations "
+                 f"({equivalent:.3e} all-pairs equivalent) in {elapsed:.3f} s "
+                 f"({equivalent / max(elapsed, 1e-12):.3e} equivalent pair evals/s) on "
+                 f"{len(devices) * world} GPU(s)")
         if (total >= np.uint64(2 ** 31)).any():
             log.warning("RDF: a histogram bin exceeds 2^31-1; the reference's int32 accumulators "
                         "(quirk Q5) would have wrapped here")

@@ -62,3 +62,25 @@ def test_corrected_mode_ideal_gas_g_of_r_is_one(tmp_path):
     expected_pairs = 8 * n * (n - 1) / 2 * shell_exact[5:] / 100.0 ** 3
     sigma = 1.0 / np.sqrt(expected_pairs)
     assert np.all(np.abs(g - 1.0) < 5 * sigma + 1e-4)
+
+
+def test_cell_list_path_through_the_calculator_matches_all_pairs(tmp_path):
+    """A system with cutoff << box: the library picks the cell-list kernel on its own; the result
+    must equal the forced all-pairs run bit for bit (same integer counts -> same g(r))."""
+    sysm = synthetic.lj_fluid(20, 6, seed=8)  # 8000 atoms, L = 21.2
+    project = mds.Project("cells", storage_path=str(tmp_path))
+    exp = project.add_experiment("lj")
+    exp.add_positions(sysm.positions, sysm.species, sysm.box)
+    exp2 = project.add_experiment("lj_allpairs")  # separate experiment: the results cache keys on
+    exp2.add_positions(sysm.positions, sysm.species, sysm.box)  # the reference's Args only
+    auto = exp.run.RadialDistributionFunction(number_of_configurations=6, number_of_bins=300,
+                                              cutoff=3.0, plot=False)
+    forced = exp2.run.RadialDistributionFunction(number_of_configurations=6, number_of_bins=300,
+                                                 cutoff=3.0, plot=False, path="allpairs")
+    counts, _ = c_oracle.rdf_counts_c(sysm.positions, sysm.counts, sysm.box, 3.0, 300,
+                                      layout=c_oracle.FRAME_MAJOR)
+    want = rdf_oracle.normalise(counts, ["Ar"], sysm.counts, sysm.box, 3.0, 6)
+    for out in (auto, forced):
+        y = np.array(out["Ar_Ar"]["y"])
+        assert np.allclose(y[1:], np.array(want["Ar_Ar"]["y"])[1:], rtol=1e-6, atol=0)
+    assert np.array_equal(np.array(auto["Ar_Ar"]["y"])[1:], np.array(forced["Ar_Ar"]["y"])[1:])
