@@ -227,7 +227,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -287,7 +287,10 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout; the
         # contract is ONE JSON line there
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")
+        if "BENCH_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     sysm, cutoff, nbins, desc = make_workload(args.workload, rank, args.frames)
@@ -485,14 +488,38 @@ def run_ours(args):
         "kernel_variant": {"path": st.path_name, "variant": st.variant, "dense": st.dense,
                            "cells": list(st.cells)},
     }
-    print(json.dumps(line))
+    emit(line)
     handle.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner with the image's
+    NCCL_DEBUG=VERSION, torchrun notices) write there too, so file descriptor 1 is pointed at
+    stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
