@@ -1,0 +1,89 @@
+/*
+ * mds_io.h — C ABI of the native trajectory ingestion (host code, no CUDA).
+ *
+ * Replaces the pure-Python text parsing of the reference on the way INTO the trajectory store
+ * (SURVEY.md §8f rank 2):
+ *   mdsuite/file_io/lammps_trajectory_files.py:103-146   header analysis, n_configs from the line
+ *                                                        count, species of the first configuration
+ *   mdsuite/file_io/tabular_text_files.py:160-220        per configuration: skip 9 header lines,
+ *                                                        split n_particles lines, sort by the id
+ *                                                        column (utils/meta_functions.py:519-527),
+ *                                                        slice property columns
+ * The reference turns every token into float64 (NumPy's correctly rounded string conversion) and
+ * stores float32 (h5py dataset dtype, database/simulation_database.py:491-497); this library
+ * returns float32((double) token) — the same two roundings.
+ *
+ * Conventions as in mds_rdf.h: plain C, 0 / negative status, thread-local error string.
+ */
+#ifndef MDS_IO_H
+#define MDS_IO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDS_IO_ABI_VERSION 1
+
+#if defined(MDS_BUILD) && defined(__GNUC__)
+#define MDS_IO_API __attribute__((visibility("default")))
+#else
+#define MDS_IO_API
+#endif
+
+#define MDS_IO_OK 0
+#define MDS_IO_ERR_INVALID (-1)
+#define MDS_IO_ERR_IO (-2)
+#define MDS_IO_ERR_FORMAT (-3)
+#define MDS_IO_ERR_NOMEM (-4)
+
+typedef struct mds_dump mds_dump_t;
+
+typedef struct mds_dump_info {
+  uint32_t struct_size;
+  int32_t n_columns;        /* per-atom columns named on the "ITEM: ATOMS" line */
+  int64_t n_atoms;          /* header line 4 */
+  int64_t n_configurations; /* total lines / (n_atoms + 9), must divide */
+  int64_t file_bytes;
+  int64_t timestep0;        /* header line 2 of the first configuration */
+  int64_t timestep1;        /* ... of the second one (== timestep0 if there is only one) */
+  double box_lo[3];         /* header lines 6-8 */
+  double box_hi[3];
+  int32_t id_column;        /* index of "id", -1 if absent */
+  int32_t species_column;   /* index of "element", else "type", else -1 */
+} mds_dump_info;
+
+/* mmap the dump, read the first header and index the configurations with n_threads threads
+ * (<= 0: hardware concurrency). */
+MDS_IO_API int mds_dump_open(mds_dump_t** out, const char* path, int n_threads);
+MDS_IO_API void mds_dump_close(mds_dump_t* h);
+MDS_IO_API int mds_dump_info_get(mds_dump_t* h, mds_dump_info* out);
+/* name of per-atom column idx into buf (NUL terminated, truncated to buf_len) */
+MDS_IO_API int mds_dump_column_name(mds_dump_t* h, int idx, char* buf, int buf_len);
+/* Labels of column `column` for the first configuration, atoms in ascending id order (file
+ * order if sort_by_id == 0): n_atoms NUL-terminated strings at stride label_stride bytes. */
+MDS_IO_API int mds_dump_first_frame_labels(mds_dump_t* h, int column, int sort_by_id, char* buf,
+                                           int label_stride);
+/* out[frame][atom][c] = float32((double) token of column columns[c]) for configurations
+ * [frame0, frame0 + n_frames), atoms in ascending id order (file order if sort_by_id == 0). */
+MDS_IO_API int mds_dump_read_columns(mds_dump_t* h, int64_t frame0, int64_t n_frames,
+                                     const int32_t* columns, int32_t n_cols, int sort_by_id,
+                                     float* out);
+/* Same, with the atom of rank k (k-th smallest id, or k-th line if sort_by_id == 0) written to
+ * row dest[k] (a permutation of 0..n_atoms-1; NULL = identity) — lets the caller receive the
+ * species-contiguous order of the trajectory store without a second gather. */
+MDS_IO_API int mds_dump_read_columns_mapped(mds_dump_t* h, int64_t frame0, int64_t n_frames,
+                                            const int32_t* columns, int32_t n_cols, int sort_by_id,
+                                            const int32_t* dest, float* out);
+/* The string -> float32 conversion on its own (for parity tests): n NUL-terminated tokens at
+ * stride `stride` bytes -> out[n]. */
+MDS_IO_API int mds_parse_float32(const char* tokens, int64_t n, int32_t stride, float* out);
+
+MDS_IO_API const char* mds_io_last_error(void);
+MDS_IO_API int mds_io_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDS_IO_H */

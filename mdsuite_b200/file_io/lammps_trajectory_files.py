@@ -1,11 +1,14 @@
 """
-LAMMPS text dump reader (reference mdsuite/file_io/lammps_trajectory_files.py:69-298 and
-tabular_text_files.py:122-220).
+LAMMPS text dump reader — drop-in for the reference's ``LAMMPSTrajectoryFile``
+(mdsuite/file_io/lammps_trajectory_files.py:69-298, tabular_text_files.py:122-220) on top of the
+native reader (include/mds_io.h, mdsuite_b200/_native): the file is mmap'ed, its configurations are
+indexed and parsed by all host threads, and positions arrive as float32(float64(token)) exactly as
+the reference's NumPy conversion + float32 store would produce them.
 
 Same conventions as the reference: 9 header lines per configuration, box lengths from header
-lines 5-7, the ``id`` column sorts the atoms of every configuration, species come from the
+lines 6-8, the ``id`` column orders the atoms of every configuration, species come from the
 ``element`` column (else ``type``) of the FIRST configuration in order of first appearance, and
-``x y z`` become the ``Positions`` property.  Only the properties the RDF loads are extracted.
+``x y z`` become the ``Positions`` property.
 """
 from __future__ import annotations
 
@@ -18,63 +21,55 @@ from mdsuite_b200.database.simulation_database import (PropertyInfo, SpeciesInfo
                                                        TrajectoryChunkData, TrajectoryMetadata)
 from mdsuite_b200.file_io.file_read import FileProcessor
 
-N_HEADER_LINES = 9
 COLUMN_NAMES = {"Positions": ["x", "y", "z"], "Unwrapped_Positions": ["xu", "yu", "zu"],
                 "Velocities": ["vx", "vy", "vz"], "Forces": ["fx", "fy", "fz"]}
 
 
 class LAMMPSTrajectoryFile(FileProcessor):
     def __init__(self, file_path, trajectory_is_sorted_by_ids: bool = False,
-                 chunk_configurations: int = 64):
+                 chunk_bytes: int = 256 << 20, n_threads: int = 0):
         self.file_path = str(pathlib.Path(file_path))
         self.trajectory_is_sorted_by_ids = trajectory_is_sorted_by_ids
-        self.chunk_configurations = chunk_configurations
+        self.chunk_bytes = chunk_bytes
+        self.n_threads = n_threads
         self._mdata = None
         self._layout = None
+        self._dump = None
 
     def __str__(self):
         return self.file_path
 
-    # ---- header analysis ------------------------------------------------------------------
+    def _open(self):
+        if self._dump is None:
+            from mdsuite_b200 import _native
+            self._dump = _native.LammpsDump(self.file_path, n_threads=self.n_threads)
+        return self._dump
+
+    # ---- header analysis (reference lammps_trajectory_files.py:103-179) ---------------------
     def _analyse(self):
         if self._layout is not None:
             return self._layout
-        with open(self.file_path, "r") as fh:
-            header = [fh.readline() for _ in range(N_HEADER_LINES)]
-            n_particles = int(header[3].split()[0])
-            columns = header[8].split()[2:]
-            if "id" not in columns:
-                raise ValueError("LAMMPS dump needs an 'id' column")
-            if "element" in columns:
-                species_col = columns.index("element")
-            elif "type" in columns:
-                species_col = columns.index("type")
-            else:
-                raise ValueError("Insufficient species or type identification available.")
-            box_l = [float(line.split()[1]) - float(line.split()[0]) for line in header[5:8]]
-            first = np.array([fh.readline().split() for _ in range(n_particles)])
-            step0 = int(header[1])
-            second = [fh.readline() for _ in range(N_HEADER_LINES)]
-            sample_rate = int(second[1]) - step0 if second[1].strip() else None
-            fh.seek(0)
-            n_lines = sum(1 for _ in fh)
-        n_configs_f = n_lines / (n_particles + N_HEADER_LINES)
-        n_configs = int(round(n_configs_f))
-        if abs(n_configs_f - n_configs) > 1e-10:
-            raise ValueError("file length is not a whole number of configurations")
-        id_col = columns.index("id")
-        if not self.trajectory_is_sorted_by_ids:
-            first = first[np.argsort(first[:, id_col].astype(np.int64), kind="stable")]
+        dump = self._open()
+        info = dump.info
+        columns = info.columns
+        if info.id_column < 0:
+            raise ValueError("LAMMPS dump needs an 'id' column")
+        if info.species_column < 0:
+            raise ValueError("Insufficient species or type identification available.")
+        labels = dump.first_frame_labels(info.species_column,
+                                         sort_by_id=not self.trajectory_is_sorted_by_ids)
         species: Dict[str, List[int]] = {}
-        for i, name in enumerate(first[:, species_col]):
-            species.setdefault(str(name), []).append(i)
+        for i, name in enumerate(labels):
+            species.setdefault(name, []).append(i)
         props = {}
         for prop, names in COLUMN_NAMES.items():
             if all(n in columns for n in names):
                 props[prop] = [columns.index(n) for n in names]
-        self._layout = dict(n_particles=n_particles, n_configs=n_configs, columns=columns,
-                            id_col=id_col, species=species, props=props, box_l=box_l,
-                            sample_rate=sample_rate)
+        box_l = [hi - lo for lo, hi in zip(info.box_lo, info.box_hi)]
+        sample_rate = info.timestep1 - info.timestep0 if info.n_configurations > 1 else None
+        self._layout = dict(n_particles=info.n_atoms, n_configs=info.n_configurations,
+                            columns=columns, id_col=info.id_column, species=species, props=props,
+                            box_l=box_l, sample_rate=sample_rate)
         return self._layout
 
     def _get_metadata(self) -> TrajectoryMetadata:
@@ -85,27 +80,34 @@ class LAMMPSTrajectoryFile(FileProcessor):
         return TrajectoryMetadata(n_configurations=lay["n_configs"], species_list=species_list,
                                   box_l=lay["box_l"], sample_rate=lay["sample_rate"])
 
-    # ---- streaming --------------------------------------------------------------------------
+    # ---- streaming (reference tabular_text_files.py:122-220) ---------------------------------
     def get_configurations_generator(self) -> Iterator[TrajectoryChunkData]:
         lay = self._analyse()
+        dump = self._open()
         n, species_list = lay["n_particles"], self.metadata.species_list
-        n_cols = len(lay["columns"])
-        with open(self.file_path, "r") as fh:
-            done = 0
-            while done < lay["n_configs"]:
-                chunk_n = min(self.chunk_configurations, lay["n_configs"] - done)
-                chunk = TrajectoryChunkData(species_list, chunk_n)
-                for c in range(chunk_n):
-                    for _ in range(N_HEADER_LINES):
-                        fh.readline()
-                    tokens = np.array("".join(fh.readline() for _ in range(n)).split())
-                    table = tokens.reshape(n, n_cols)
-                    if not self.trajectory_is_sorted_by_ids:
-                        order = np.argsort(table[:, lay["id_col"]].astype(np.int64), kind="stable")
-                        table = table[order]
-                    for prop, cols in lay["props"].items():
-                        values = table[:, cols].astype(np.float64)
-                        for name, idx in lay["species"].items():
-                            chunk.add_data(values[idx][None], c, name, prop)
-                done += chunk_n
-                yield chunk
+        prop_items = list(lay["props"].items())
+        all_cols = [c for _, cols in prop_items for c in cols]
+        per_frame = max(1, n * len(all_cols) * 4)
+        chunk_frames = max(1, min(lay["n_configs"], self.chunk_bytes // per_frame))
+        # the native reader scatters the atom of id-rank k to row dest[k]: species-contiguous, so the
+        # per-species slices below are plain views
+        dest = np.empty(n, dtype=np.int32)
+        bounds, off = {}, 0
+        for name, idx in lay["species"].items():
+            dest[np.asarray(idx, dtype=np.int64)] = np.arange(off, off + len(idx), dtype=np.int32)
+            bounds[name] = (off, off + len(idx))
+            off += len(idx)
+        done = 0
+        while done < lay["n_configs"]:
+            k = min(chunk_frames, lay["n_configs"] - done)
+            table = dump.read_columns(done, k, all_cols, dest=dest,
+                                      sort_by_id=not self.trajectory_is_sorted_by_ids)
+            chunk = TrajectoryChunkData(species_list, k)
+            off = 0
+            for prop, cols in prop_items:
+                values = table[:, :, off:off + len(cols)]
+                off += len(cols)
+                for name, (lo, hi) in bounds.items():
+                    chunk.add_data(values[:, lo:hi], 0, name, prop)
+            done += k
+            yield chunk
