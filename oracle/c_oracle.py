@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY — ctypes loader for oracle/librdf_oracle.so (see rdf_oracle.c).
 
-Parity unpinned (see oracle/rdf_oracle.py header).  Never imported by the product.
+Parity: see the header of oracle/rdf_oracle.py (control flow pinned, leaf arithmetic restated).  Never imported by the product.
 """
 from __future__ import annotations
 

@@ -1,10 +1,11 @@
 /*
  * TEST INFRASTRUCTURE ONLY — plain-C restatement ("oracle") of the MDSuite RDF hot path.
  *
- *   PARITY UNPINNED: the reference's arithmetic lives in TensorFlow (not vendored, not
- *   importable here) and the reference has no golden vectors for this path.  This file
- *   restates the op sequence; see oracle/rdf_oracle.py for the op-by-op NumPy twin it is
- *   checked against (tests/test_oracle.py).
+ *   PARITY: control flow, species masks (quirk Q1) and accumulation are pinned against the
+ *   reference's own run_calculator executed over a NumPy stand-in for its TensorFlow leaf ops
+ *   (tests/golden/reference_golden.json, tests/test_reference_golden.py); the float32 leaf
+ *   arithmetic lives in TensorFlow (not vendored, not importable here) and is a restatement.
+ *   See oracle/rdf_oracle.py for the op-by-op NumPy twin (tests/test_oracle.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load the library built from this file.  The product never links it.

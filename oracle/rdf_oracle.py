@@ -1,12 +1,22 @@
 """
 TEST INFRASTRUCTURE ONLY — CPU restatement ("oracle") of the MDSuite RDF hot path.
 
-    PARITY UNPINNED: the reference (zincware/MDSuite 0.2.0) delegates its arithmetic to
-    TensorFlow, which is neither vendored under /root/reference nor importable in this
-    image, and the reference holds no golden vectors for this path (its only RDF test
-    downloads JSON from GitHub and compares at decimal=1).  This file restates the
-    reference's op sequence one NumPy op per TensorFlow op; the golden vectors under
-    tests/golden/ are SELF-GENERATED from it (tests/golden/make_golden.py).
+    PARITY PINNED FOR CONTROL FLOW AND NORMALISATION, UNPINNED FOR LEAF ARITHMETIC.
+    The reference (zincware/MDSuite 0.2.0) delegates its arithmetic to TensorFlow, which is
+    neither vendored under /root/reference nor importable in this image, and the reference
+    holds no golden vectors for this path (its only RDF test downloads JSON from GitHub and
+    compares at decimal=1).  What can be done here is done: tests/golden/make_reference_golden.py
+    executes the reference's own run_calculator (calculators/radial_distribution_function.py,
+    utils/linalg.py, utils/meta_functions.py, loaded from /root/reference unmodified) over a
+    NumPy stand-in for its ~20 TensorFlow leaf ops, and commits the histograms and the
+    normalised x / y as tests/golden/reference_golden.json.  This file, the C twin and the
+    product's host logic are checked against those (tests/test_reference_golden.py): defaults,
+    sampling, index tensors, the strict-'>' species masks (quirk Q1), accumulation, prefactor,
+    ideal-gas correction, x axis are the reference's.  The float32 arithmetic of the leaf ops
+    (subtract, divide, rint, multiply, norm, less, histogram_fixed_width) is TensorFlow's and
+    remains a restatement of SURVEY.md §8c — in the shim exactly as here.
+    tests/golden/rdf_golden.json (tests/golden/make_golden.py) is SELF-GENERATED from this file
+    and kept because its cases are shared with the reference-run fixtures.
 
 Only tests/, __graft_entry__.smoke() and the cpu_baseline / --impl reference legs of
 bench.py may import this module.  The product (mdsuite_b200) never does.

@@ -1,7 +1,7 @@
 """
 TEST INFRASTRUCTURE / CPU BASELINE ONLY — op-by-op torch-CPU restatement of the reference's RDF
 batch loop, used by bench.py as the "reference-equivalent CPU" arm (TensorFlow is not importable
-in this image).  Parity unpinned (see oracle/rdf_oracle.py).
+in this image).  Parity: see oracle/rdf_oracle.py (control flow pinned, leaf arithmetic restated).
 
 It keeps the reference's cost structure, not just its results: one materialised tensor per
 TensorFlow op, the (2, P) index tensor rebuilt for every atom-minibatch of every batch
