@@ -1,7 +1,11 @@
 """``experiment.run`` / ``project.run`` (reference mdsuite/experiment/run.py:58-243): one property
-per calculator; only the RDF is in this package's scope."""
+per calculator; in this package's scope are the RDF and the calculators that
+consume its output (§8f rank 3)."""
 from __future__ import annotations
 
+from mdsuite_b200.calculators.coordination_number_calculation import CoordinationNumbers
+from mdsuite_b200.calculators.kirkwood_buff_integrals import KirkwoodBuffIntegral
+from mdsuite_b200.calculators.potential_of_mean_force import PotentialOfMeanForce
 from mdsuite_b200.calculators.radial_distribution_function import RadialDistributionFunction
 
 
@@ -15,3 +19,18 @@ class RunComputation:
     def RadialDistributionFunction(self) -> RadialDistributionFunction:
         """reference run.py:228-230."""
         return RadialDistributionFunction(**self.kwargs)
+
+    @property
+    def CoordinationNumbers(self) -> CoordinationNumbers:
+        """reference run.py:168-170."""
+        return CoordinationNumbers(**self.kwargs)
+
+    @property
+    def KirkwoodBuffIntegral(self) -> KirkwoodBuffIntegral:
+        """reference run.py:216-218."""
+        return KirkwoodBuffIntegral(**self.kwargs)
+
+    @property
+    def PotentialOfMeanForce(self) -> PotentialOfMeanForce:
+        """reference run.py:224-226."""
+        return PotentialOfMeanForce(**self.kwargs)
