@@ -174,42 +174,112 @@ class Database:
 
 
 class HDF5Database:
-    """Reader for a reference ``database.hdf5`` (atom-major, gzip); needs h5py."""
+    """Read-only adapter over a reference ``database.hdf5`` (atom-major (n, cfg, 3), chunked,
+    gzip — mdsuite/database/simulation_database.py:449-499, :594-639) using this package's own
+    HDF5 reader (no h5py).  Serves the same calls as ``Database``; decoded chunks of the most
+    recent frame window are cached so that consecutive batches do not inflate a chunk twice."""
 
-    def __init__(self, path: str):
-        try:
-            import h5py  # noqa: F401
-        except ImportError as exc:
-            raise ImportError("reading an MDSuite database.hdf5 needs h5py, which is not installed; "
-                              "re-ingest the trajectory into the native frame store") from exc
+    def __init__(self, path: str, n_configurations: int = None, cache_bytes: int = 512 << 20):
+        from mdsuite_b200.database.hdf5_reader import H5File
         self.path = path
+        self.file = H5File(path)
+        self._datasets = {}
+        self._n_configurations = n_configurations
+        self._cache = {}  # path -> (f0, f1, array (n_atoms, f1 - f0, dims))
+        self._cache_bytes = cache_bytes
+
+    def close(self):
+        self.file.close()
+
+    def _ds(self, path: str):
+        if path not in self._datasets:
+            self._datasets[path] = self.file.dataset(path)
+        return self._datasets[path]
+
+    def datasets(self) -> list:
+        return sorted(self.file.walk())
 
     def check_existence(self, path: str) -> bool:
-        import h5py
-        with h5py.File(self.path, "r") as db:
-            return path in db
+        return path in self.file
 
     def get_data_size(self, path: str) -> tuple:
-        import h5py
-        with h5py.File(self.path, "r") as db:
-            ds = db[path]
-            return ds.shape[0], ds.shape[1], int(np.prod(ds.shape)) * ds.dtype.itemsize
+        ds = self._ds(path)
+        n_cfg = ds.shape[1] if self._n_configurations is None else min(ds.shape[1],
+                                                                       self._n_configurations)
+        return ds.shape[0], n_cfg, int(ds.shape[0] * n_cfg * np.prod(ds.shape[2:])) * ds.dtype.itemsize
+
+    def _window(self, path: str, f0: int, f1: int) -> np.ndarray:
+        """(n_atoms, f1 - f0, dims) for configurations [f0, f1), widened to whole frame-chunks and
+        kept for the next call."""
+        ds = self._ds(path)
+        hit = self._cache.get(path)
+        if hit is not None and hit[0] <= f0 and f1 <= hit[1]:
+            return hit[2][:, f0 - hit[0]:f1 - hit[0]]
+        cf = ds.chunks[1] if ds.chunks else ds.shape[1]
+        w0, w1 = f0 // cf * cf, min(ds.shape[1], -(-f1 // cf) * cf)
+        per_frame = ds.shape[0] * int(np.prod(ds.shape[2:])) * ds.dtype.itemsize
+        if (w1 - w0) * per_frame > self._cache_bytes:  # too wide to keep: read exactly what is asked
+            w0, w1 = f0, f1
+        block = ds.read_hyperslab((slice(0, ds.shape[0]), slice(w0, w1)) +
+                                  tuple(slice(0, n) for n in ds.shape[2:]))
+        self._cache[path] = (w0, w1, block)
+        return block[:, f0 - w0:f1 - w0]
 
     def load_frames(self, path: str, frames: Sequence[int], out: np.ndarray = None,
                     atom_selection=None) -> np.ndarray:
-        import h5py
         frames = np.asarray(frames, dtype=np.int64)
-        with h5py.File(self.path, "r") as db:
-            ds = db[path]
-            if len(frames) and np.all(np.diff(frames) == 1):
-                data = ds[:, frames[0]:frames[-1] + 1]
-            else:
-                data = ds[:, list(frames)]
-        data = np.asarray(data, dtype=np.float32)
-        if atom_selection is not None:
+        if len(frames) == 0:
+            data = np.zeros((0,) + tuple(np.delete(self._ds(path).shape, 1)), dtype=np.float32)
+        else:
+            lo, hi = int(frames.min()), int(frames.max()) + 1
+            block = self._window(path, lo, hi)
+            data = block if (len(frames) == hi - lo and np.all(np.diff(frames) == 1)) \
+                else block[:, frames - lo]
+        if atom_selection is not None and not (isinstance(atom_selection, slice)
+                                               and atom_selection == slice(None)):
             data = data[atom_selection]
-        data = data.transpose(1, 0, 2)
+        data = data.transpose(1, 0, 2)  # atom-major on disk -> frame-major for the GPU feed
         if out is None:
-            return np.ascontiguousarray(data)
-        np.copyto(out, data)
+            return np.ascontiguousarray(data, dtype=np.float32)
+        np.copyto(out, data, casting="same_kind")
         return out
+
+    def load_data(self, path_list: Sequence[str], select_slice=np.s_[:]) -> Dict[str, np.ndarray]:
+        """Reference-shaped read (simulation_database.py:594-639), atom-major result."""
+        if not isinstance(select_slice, tuple):
+            select_slice = (select_slice, np.s_[:])
+        atoms_sel, conf_sel = (list(select_slice) + [np.s_[:]])[:2]
+        out = {}
+        for path in path_list:
+            n_cfg = self.get_data_size(path)[1]
+            frames = np.arange(n_cfg)[conf_sel]
+            fm = self.load_frames(path, frames)
+            out[path] = np.ascontiguousarray(fm.transpose(1, 0, 2)[atoms_sel])
+        return out
+
+
+def import_hdf5(hdf5_path: str, database: "Database", n_configurations: int = None,
+                frames_per_block: int = 256, properties: Sequence[str] = ("Positions",)) -> dict:
+    """Re-chunk a reference ``database.hdf5`` (atom-major, gzip) into the frame-major store the
+    GPU feed streams from ("a frame-major re-chunking transform").
+    Returns {dataset path: (n_particles, n_configurations)}."""
+    src = HDF5Database(hdf5_path, n_configurations=n_configurations)
+    done = {}
+    try:
+        for path in src.datasets():
+            species, _, prop = path.rpartition("/")
+            if prop not in properties:
+                continue
+            n_atoms, n_cfg, _ = src.get_data_size(path)
+            dims = src._ds(path).shape[2]
+            info = SpeciesInfo(species, n_atoms, [PropertyInfo(prop, dims)])
+            database.add_dataset(path, n_atoms, dims)
+            for f0 in range(0, n_cfg, frames_per_block):
+                f1 = min(n_cfg, f0 + frames_per_block)
+                chunk = TrajectoryChunkData([info], f1 - f0)
+                chunk.add_data(src.load_frames(path, np.arange(f0, f1)), 0, species, prop)
+                database.add_data(chunk)
+            done[path] = (n_atoms, n_cfg)
+    finally:
+        src.close()
+    return done

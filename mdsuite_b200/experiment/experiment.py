@@ -56,7 +56,9 @@ class Experiment:
         project.database.add_experiment(name)
         hdf5 = os.path.join(self.experiment_path, "database.hdf5")
         if os.path.exists(hdf5) and not os.path.exists(os.path.join(self.database_path, "index.json")):
-            self.database = HDF5Database(hdf5)  # an existing MDSuite project (needs h5py)
+            # an existing MDSuite project: read its atom-major gzip store in place (own HDF5
+            # reader); datasets are over-allocated on resize, the SQL record has the true length
+            self.database = HDF5Database(hdf5, n_configurations=self._get("number_of_configurations"))
         else:
             self.database = Database(self.database_path)
         if time_step is not None:

@@ -1,0 +1,52 @@
+"""Throughput of the from-scratch HDF5 reader on a reference-shaped database (atom-major, chunked,
+gzip): frame-major batches as the RDF batcher requests them, and the import transform.
+Usage: python scripts/hdf5_bench.py [n_frames]     (prints one JSON line)"""
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from hdf5_writer import H5Writer  # noqa: E402  (no libhdf5 in the image: the test writer makes the file)
+from mdsuite_b200 import synthetic  # noqa: E402
+from mdsuite_b200.database.simulation_database import Database, HDF5Database, import_hdf5  # noqa: E402
+
+n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+sysm = synthetic.nacl_melt(12, 8, seed=2)
+pos = np.tile(sysm.positions, ((n_frames + 7) // 8, 1, 1))[:n_frames]
+am = np.ascontiguousarray(pos.transpose(1, 0, 2))
+n = sysm.counts[0]
+with tempfile.TemporaryDirectory() as tmp:
+    w = H5Writer()
+    # h5py's guess_chunk on (6912, F, 3) float32 lands near (432, F/8, 3); use that shape
+    cf = max(1, n_frames // 8)
+    w.create_dataset("Na/Positions", am[:n], chunks=(432, cf, 3), maxshape=(n, None, 3))
+    w.create_dataset("Cl/Positions", am[n:], chunks=(432, cf, 3), maxshape=(n, None, 3))
+    path = os.path.join(tmp, "database.hdf5")
+    w.save(path)
+    raw_mb = pos.nbytes / 1e6
+    out = {"atoms": sysm.n_atoms, "frames": n_frames, "raw_mb": raw_mb,
+           "file_mb": os.path.getsize(path) / 1e6, "cores": os.cpu_count()}
+    db = HDF5Database(path)
+    t0 = time.perf_counter()
+    batch = 32
+    for f0 in range(0, n_frames, batch):
+        idx = np.arange(f0, min(n_frames, f0 + batch))
+        a = db.load_frames("Na/Positions", idx)
+        b = db.load_frames("Cl/Positions", idx)
+    dt = time.perf_counter() - t0
+    ok = np.array_equal(a, pos[idx][:, :n]) and np.array_equal(b, pos[idx][:, n:])
+    out["batched_read"] = {"seconds": dt, "raw_mb_per_s": raw_mb / dt, "batch_frames": batch,
+                           "last_batch_matches": bool(ok)}
+    db.close()
+    store = Database(os.path.join(tmp, "store"))
+    t0 = time.perf_counter()
+    import_hdf5(path, store, frames_per_block=64)
+    dt = time.perf_counter() - t0
+    out["import_to_frame_store"] = {"seconds": dt, "raw_mb_per_s": raw_mb / dt}
+print(json.dumps(out))
