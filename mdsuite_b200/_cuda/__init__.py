@@ -18,7 +18,9 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmds_rdf.so")
+# MDS_RDF_LIB selects another build of the same ABI, e.g. the self-checking libmds_rdf_checked.so
+# (make -C csrc checked; see rdf_common.cuh MDS_CHECKED)
+LIB_PATH = os.environ.get("MDS_RDF_LIB") or os.path.join(_HERE, "libmds_rdf.so")
 
 ABI_VERSION = 2
 MDS_OK = 0

@@ -9,9 +9,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... (see csrc/Makefile)."""
-    cmd = ["make", "-C", CSRC]
+def build(force: bool = False, verbose: bool = False, checked: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... (see csrc/Makefile).
+    checked=True also builds libmds_rdf_checked.so (-DMDS_CHECKED)."""
+    cmd = ["make", "-C", CSRC, "all"] + (["checked"] if checked else [])
     if force:
         cmd.append("-B")
     if not verbose:

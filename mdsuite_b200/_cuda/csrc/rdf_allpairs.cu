@@ -43,7 +43,9 @@ __device__ __forceinline__ void pair_tile(const float4* __restrict__ jt, int cnt
                                           float inv_hi, uint32_t c_edge, uint32_t c_hist,
                                           uint32_t four,
                                           const float* __restrict__ edges_g,
-                                          unsigned long long* hist_g) {
+                                          unsigned long long* hist_g,
+                                          unsigned long long& issued) {
+  (void)issued;
   float hi = 0.f;  // last table entry a lane looked up (see bin_count_dense)
 #pragma unroll 1
   for (int jj = 0; jj < cnt; jj += 4, jt += 3) {
@@ -59,12 +61,14 @@ __device__ __forceinline__ void pair_tile(const float4* __restrict__ jt, int cnt
         if (HIST_SMEM && DENSE) {
           bin_count_dense<DIAG, MDS_COND>(s[c], s_cut, inv_step, inv_hi, c_edge, c_hist, four, jg + c,
                                       ig[r], hi);
+          MDS_CHK(issued += 1;)
         } else {
           bool in = s[c] < s_cut;  // false for NaN (padding rows / columns, NaN input)
           if (DIAG) in = in && (jg + c > ig[r]);
           if (in) {
             if (HIST_SMEM) {
               bin_count(s[c], inv_step, c_edge, c_hist, four);
+              MDS_CHK(issued += 1;)
             } else {
               atomicAdd(hist_g + bin_of_s(s[c], inv_step, edges_g), 1ull);
             }
@@ -79,7 +83,8 @@ __device__ __forceinline__ void pair_tile(const float4* __restrict__ jt, int cnt
 // slot of every pair).
 template <int THREADS>
 __device__ __forceinline__ void merge_hist(uint32_t* s_hist, const AllPairsParams& p, int tid,
-                                           bool clear) {
+                                           bool clear, unsigned long long* s_chk = nullptr) {
+  (void)s_chk;
   const int stride = p.nbins + 1;
   for (int pr = 0; pr < p.pair_cnt; ++pr) {
     unsigned long long* g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
@@ -88,10 +93,16 @@ __device__ __forceinline__ void merge_hist(uint32_t* s_hist, const AllPairsParam
       const uint32_t v = h[k];
       if (v) {
         atomicAdd(g + k, (unsigned long long)v);
-        if (clear) h[k] = 0u;
+        if (clear) {
+          h[k] = 0u;
+          MDS_CHK(atomicAdd(&s_chk[1], (unsigned long long)v);)
+        }
       }
     }
-    if (clear && tid == 0) h[p.nbins] = 0u;
+    if (clear && tid == 0) {
+      MDS_CHK(atomicAdd(&s_chk[1], (unsigned long long)h[p.nbins]);)
+      h[p.nbins] = 0u;
+    }
   }
 }
 
@@ -107,6 +118,11 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
   const int hist_stride = p.nbins + 1;  // slot nbins of every pair is the out-of-cutoff sink
   const int n_hist = p.pair_cnt * hist_stride;
   const int tid = threadIdx.x;
+  MDS_CHK(__shared__ unsigned long long s_chk[2]; unsigned long long issued = 0;
+          if (tid == 0) { s_chk[0] = 0; s_chk[1] = 0; })
+#ifndef MDS_CHECKED
+  unsigned long long issued = 0;  // only counted in checked builds
+#endif
 
   if (HIST_SMEM) {
     for (int k = tid; k < n_edges; k += THREADS) s_edges[k] = p.edges[k];
@@ -134,7 +150,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
   const uint32_t four = (uint32_t)s_item[4 + (tid & 1)];
   const float bx = p.box[0], by = p.box[1], bz = p.box[2];
   const float s_cut = p.s_cut, inv_step = p.inv_step, inv_hi = p.inv_step_hi;
-  const bool dense = HIST_SMEM && (p.dense != 0);
+  const bool dense = HIST_SMEM && ((p.dense & 1) != 0);
   const long long total = (long long)p.n_items * (long long)p.n_frames;
   uint32_t ph0 = 0, ph1 = 0;
   unsigned long long since_flush = 0;
@@ -166,7 +182,9 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
       }
     }
 
-    const uint32_t c_hist = hist0 + (uint32_t)((it.pair - p.pair_lo) * hist_stride) * 4u;
+    uint32_t c_hist = hist0 + (uint32_t)((it.pair - p.pair_lo) * hist_stride) * 4u;
+    // fault injection for the self-check's own test: aim the atomics at the column tiles
+    MDS_CHK(if (p.dense & 2) c_hist = smem_u32(jt) - kMagic4;)
     const int r_item = min(R, (it.i_cnt + THREADS - 1) / THREADS);  // row registers in use
     unsigned long long* hist_g = p.counts + (long long)it.pair * p.nbins;
     const int n_cols = it.j1 - it.j0;
@@ -198,7 +216,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
 #define MDS_TILE(RAV, FASTV, DIAGV, DENSEV)                                                    \
   pair_tile<R, RAV, FASTV, DIAGV, HIST_SMEM, DENSEV>(seg, scnt, sbase, xi, yi, zi, ig, bx, by, bz, \
                                                      s_cut, inv_step, inv_hi, c_edge, c_hist,   \
-                                                     four, p.edges, hist_g)
+                                                     four, p.edges, hist_g, issued)
 #define MDS_TILE_FD(RAV)                                                                       \
   do {                                                                                         \
     if (dense) { if (dg) MDS_TILE(RAV, true, true, true); else MDS_TILE(RAV, true, false, true); } \
@@ -237,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
     if (HIST_SMEM) {
       since_flush += (unsigned long long)it.i_cnt * (unsigned long long)n_cols;
       if (since_flush >= (1ull << 31)) {  // uniform across the CTA
-        merge_hist<THREADS>(s_hist, p, tid, true);
+        merge_hist<THREADS>(s_hist, p, tid, true MDS_CHK(, s_chk));
         since_flush = 0;
         __syncthreads();
       }
@@ -245,6 +263,8 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
   }
 
   if (HIST_SMEM) {
+    MDS_CHK(__syncthreads();
+            checked_conservation(s_chk, issued, s_hist, n_hist, tid, THREADS, "rdf_allpairs_kernel");)
     merge_hist<THREADS>(s_hist, p, tid, false);
   }
 }

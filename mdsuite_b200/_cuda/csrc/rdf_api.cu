@@ -253,6 +253,9 @@ mds::AllPairsParams allpairs_params(mds_rdf* h, int buf, int64_t n_frames, int p
   ap.inv_step = h->inv_step;
   ap.inv_step_hi = h->inv_step_hi;
   ap.dense = h->dense ? 1 : 0;
+#ifdef MDS_CHECKED
+  if (const char* env = getenv("MDS_CHECKED_INJECT_FAULT")) ap.dense |= atoi(env) ? 2 : 0;
+#endif
   for (int k = 0; k < 3; ++k) ap.box[k] = h->box[k];
   ap.frame_need_bits = 0;
   ap.gate = nullptr;

@@ -114,7 +114,9 @@ __device__ __forceinline__ void cell_chunk(const float* __restrict__ tl, int cnt
                                            float bx, float by, float bz, float s_cut,
                                            float inv_step, uint32_t c_edge, uint32_t c_hist,
                                            uint32_t four, const float* __restrict__ edges_g,
-                                           unsigned long long* hist_g) {
+                                           unsigned long long* hist_g,
+                                           unsigned long long& issued) {
+  (void)issued;
   float hi = 0.f;
 #pragma unroll 1
   for (int c0 = ph * 2; c0 < cnt; c0 += 2 * PH) {
@@ -132,6 +134,7 @@ __device__ __forceinline__ void cell_chunk(const float* __restrict__ tl, int cnt
         if (HIST_SMEM) {
           bin_count_dense<DIAG, false>(s[c], s_cut, inv_step, 0.f, c_edge, c_hist, four, q + c,
                                        il[r], hi);
+          MDS_CHK(issued += 1;)
         } else {
           bool in = s[c] < s_cut;  // false for NaN (padding rows / columns, NaN input)
           if (DIAG) in = in && (q + c > il[r]);
@@ -154,6 +157,7 @@ struct WarpStream {
   uint32_t c_edge, c_hist, four;
   const float* edges_g;
   unsigned long long* hist_g;
+  unsigned long long* issued;  // histogram atomics issued by this thread (checked builds)
 };
 
 // Columns [qs, qe) of the stream against the register rows of the warp: lanes gather 32 columns
@@ -201,7 +205,7 @@ __device__ __forceinline__ void cell_stream(const WarpStream& w, int qs, int qe,
     const float* tl = w.tile + st * (CH * 3);
     cell_chunk<R, FAST, DIAG, HIST_SMEM>(tl, cnt, q0, w.ph, xi, yi, zi, il, w.bx, w.by, w.bz,
                                          w.s_cut, w.inv_step, w.c_edge, w.c_hist, w.four,
-                                         w.edges_g, w.hist_g);
+                                         w.edges_g, w.hist_g, *w.issued);
     if (q0 + CH < qe) stage(w.tile + (st ^ 1) * (CH * 3), nxt);  // warp-uniform condition
     __syncwarp();
   }
@@ -209,16 +213,25 @@ __device__ __forceinline__ void cell_stream(const WarpStream& w, int qs, int qe,
 
 // Move what has accumulated in the CTA's shared histogram to the global counts while other warps
 // keep counting: atomicExch takes each bin's value and zeroes it in one step, so nothing is lost.
-__device__ __forceinline__ void flush_hist_warp(uint32_t* s_hist, const CellsParams& p, int lane) {
+__device__ __forceinline__ void flush_hist_warp(uint32_t* s_hist, const CellsParams& p, int lane,
+                                                unsigned long long* s_chk = nullptr) {
+  (void)s_chk;
   const int stride = p.nbins + 1;
   for (int pr = 0; pr < p.pair_cnt; ++pr) {
     unsigned long long* g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
     uint32_t* h = s_hist + pr * stride;
     for (int k = lane; k < p.nbins; k += 32) {
       const uint32_t v = atomicExch(h + k, 0u);
-      if (v) atomicAdd(g + k, (unsigned long long)v);
+      if (v) {
+        atomicAdd(g + k, (unsigned long long)v);
+        MDS_CHK(atomicAdd(&s_chk[1], (unsigned long long)v);)
+      }
     }
-    if (lane == 0) atomicExch(h + p.nbins, 0u);  // the sink may wrap; nobody reads it
+    if (lane == 0) {  // the sink may wrap; nobody reads it
+      const uint32_t v = atomicExch(h + p.nbins, 0u);
+      (void)v;
+      MDS_CHK(atomicAdd(&s_chk[1], (unsigned long long)v);)
+    }
   }
 }
 
@@ -234,6 +247,8 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsP
   const int hist_stride = p.nbins + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rg = lane % RG, ph = lane / RG;
+  unsigned long long issued = 0;  // only counted in checked builds
+  MDS_CHK(__shared__ unsigned long long s_chk[2]; if (tid == 0) { s_chk[0] = 0; s_chk[1] = 0; })
 
   if (HIST_SMEM) {
     for (int k = tid; k < n_edges; k += CELL_THREADS) s_edges[k] = p.edges[k];
@@ -280,6 +295,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsP
   ws.c_edge = c_edge;
   ws.four = four;
   ws.edges_g = p.edges;
+  ws.issued = &issued;
 
   unsigned long long nxt_raw = 0;
   if (lane == 0) nxt_raw = atomicAdd(p.work_counter, 1ull);
@@ -422,7 +438,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsP
               // the warp whose contribution crosses the threshold empties the histogram
               if (old < p.flush_threshold && old + unpublished >= p.flush_threshold) {
                 if (lane == 0) atomicSub(s_evals, p.flush_threshold);
-                flush_hist_warp(s_hist, p, lane);
+                flush_hist_warp(s_hist, p, lane MDS_CHK(, s_chk));
               }
               unpublished = 0;
             }
@@ -440,6 +456,8 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsP
   if (lane == 0 && evaluated) atomicAdd(p.evaluated, evaluated);
   if (HIST_SMEM) {
     __syncthreads();
+    MDS_CHK(checked_conservation(s_chk, issued, s_hist, p.pair_cnt * hist_stride, tid, CELL_THREADS,
+                                 "rdf_cells_kernel");)
     const int stride = p.nbins + 1;
     for (int pr = 0; pr < p.pair_cnt; ++pr) {
       unsigned long long* g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;

@@ -6,8 +6,40 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+
+// -DMDS_CHECKED builds a self-checking library (libmds_rdf_checked.so; compute-sanitizer is closed
+// on the GPU pool this was developed on).  Every CTA then proves a conservation law at exit: the
+// number of shared-memory histogram atomics its threads issued equals what sits in its histogram
+// slots (bins + sink slots) plus what it already flushed to the global counts.  An atomic that
+// landed anywhere outside the CTA's histogram region — a wild shared-memory address — breaks the
+// equality; the CTA prints the two numbers and traps, which fails the launch.
+#ifdef MDS_CHECKED
+#define MDS_CHK(...) __VA_ARGS__
+#else
+#define MDS_CHK(...)
+#endif
 
 namespace mds {
+
+#ifdef MDS_CHECKED
+// called by every thread of the CTA after all counting is done; s_chk[0] = issued, s_chk[1] = found
+__device__ __forceinline__ void checked_conservation(unsigned long long* s_chk,
+                                                     unsigned long long issued,
+                                                     const uint32_t* s_hist, int n_slots, int tid,
+                                                     int n_threads, const char* kernel) {
+  if (issued) atomicAdd(&s_chk[0], issued);
+  unsigned long long part = 0;
+  for (int k = tid; k < n_slots; k += n_threads) part += s_hist[k];
+  if (part) atomicAdd(&s_chk[1], part);
+  __syncthreads();
+  if (tid == 0 && s_chk[0] != s_chk[1]) {
+    printf("MDS_CHECKED %s block %d: %llu histogram atomics issued, %llu found\n", kernel,
+           (int)blockIdx.x, s_chk[0], s_chk[1]);
+    __trap();
+  }
+}
+#endif
 
 // One unit of work of the all-pairs kernel: rows [i0, i0+i_cnt) of species a against columns
 // [j0, j1) of species b (packed atom indices inside one frame).  When `diag` is set the item

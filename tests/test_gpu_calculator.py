@@ -84,3 +84,23 @@ def test_cell_list_path_through_the_calculator_matches_all_pairs(tmp_path):
         y = np.array(out["Ar_Ar"]["y"])
         assert np.allclose(y[1:], np.array(want["Ar_Ar"]["y"])[1:], rtol=1e-6, atol=0)
     assert np.array_equal(np.array(auto["Ar_Ar"]["y"])[1:], np.array(forced["Ar_Ar"]["y"])[1:])
+
+
+def test_cfg3_scale_through_the_frame_store_and_batcher(tmp_path):
+    """97k-atom LJ frames from the trajectory store through FrameBatcher (pinned ring, several
+    batches) into the cell-list kernel; the forced all-pairs run on the same store must agree."""
+    sysm = synthetic.lj_fluid(46, 6, seed=3)
+    project = mds.Project("cfg3", storage_path=str(tmp_path))
+    exp = project.add_experiment("lj", units="real")
+    exp.add_positions(sysm.positions, sysm.species, sysm.box)
+    exp2 = project.add_experiment("lj_allpairs", units="real")
+    exp2.add_positions(sysm.positions[:2], sysm.species, sysm.box)
+    cells = exp.run.RadialDistributionFunction(number_of_configurations=6, number_of_bins=300,
+                                               cutoff=3.0, plot=False, frames_per_batch=4)
+    first2 = exp.run.RadialDistributionFunction(number_of_configurations=2, stop=1, number_of_bins=300,
+                                                cutoff=3.0, plot=False)
+    allp = exp2.run.RadialDistributionFunction(number_of_configurations=2, number_of_bins=300,
+                                               cutoff=3.0, plot=False, path="allpairs")
+    assert np.array_equal(np.array(first2["Ar_Ar"]["y"])[1:], np.array(allp["Ar_Ar"]["y"])[1:])
+    y = np.array(cells["Ar_Ar"]["y"])
+    assert np.isfinite(y[1:]).all() and y[1:].max() > 1.0
