@@ -189,3 +189,30 @@ def test_memory_manager_batch_size_contract():
     assert mm.get_batch_size() == (100, 1, 0)  # clipped to the number of configurations
     with pytest.raises(ValueError):
         MemoryManager(database=FakeDB(), free_memory=1).get_batch_size()
+
+
+def test_molecules_true_reads_molecule_datasets(project, tmp_path):
+    """molecules=True (reference :245-249, :701-705): species are the molecule names whose
+    <molecule>/Positions datasets a MolecularMap run left in the store; same kernel, the molecule
+    table supplies particles_list and the prefactor counts."""
+    from mdsuite_b200.database.simulation_database import (PropertyInfo, SpeciesInfo,
+                                                           TrajectoryChunkData)
+    p, sysm, _ = project
+    exp = p.experiments.NaCl
+    n_mol = sysm.counts[0]
+    mol = 0.5 * (sysm.positions[:, :n_mol] + sysm.positions[:, n_mol:])  # one "NaCl" site per ion pair
+    info = SpeciesInfo("NaCl", n_mol, [PropertyInfo("Positions", 3)])
+    exp.database.add_dataset("NaCl/Positions", n_mol, 3)
+    chunk = TrajectoryChunkData([info], mol.shape[0])
+    chunk.add_data(mol.astype(np.float32), 0, "NaCl", "Positions")
+    exp.database.add_data(chunk)
+    p.database.set_species("NaCl", {"NaCl": {"n_particles": n_mol, "mass": None, "charge": None,
+                                              "properties": ["Positions"]}}, molecule=True)
+    comp = exp.run.RadialDistributionFunction(number_of_configurations=12, number_of_bins=30,
+                                              cutoff=6.0, plot=False, molecules=True)
+    assert comp.keys() == ["NaCl_NaCl"]
+    counts, _ = c_oracle.rdf_counts_c(mol.astype(np.float32), [n_mol], sysm.box, 6.0, 30,
+                                      layout=c_oracle.FRAME_MAJOR)
+    want = rdf_oracle.normalise(counts, ["NaCl"], [n_mol], sysm.box, 6.0, 12, length_unit=1e-10)
+    assert np.allclose(np.array(comp["NaCl_NaCl"]["y"])[1:], np.array(want["NaCl_NaCl"]["y"])[1:],
+                       rtol=1e-12)
