@@ -72,15 +72,16 @@ def make_workload(name: str, rank: int, frames: int):
         desc = (f"cfg5: 50k-atom ideal gas, {frames} configurations, cutoff 10, 1000 bins "
                 f"(cell-list path)")
     elif name == "cfg3":
-        sysm = synthetic.lj_fluid(46, frames, seed=3 + 1000 * rank)
+        sysm = synthetic.lj_fluid(47, frames, seed=3 + 1000 * rank, n_atoms=100_000)
         cutoff, nbins = 3.0, 300
-        desc = (f"cfg3: {sysm.n_atoms}-atom LJ fluid (46^3, rho*=0.8442), {frames} configurations "
-                f"per GPU, cutoff 3.0 sigma, 300 bins, cell-list path, parity mode")
+        desc = (f"cfg3: {sysm.n_atoms}-atom LJ fluid (rho*=0.8442, L=49.1 sigma), {frames} "
+                f"configurations per GPU, cutoff 3.0 sigma, 300 bins, cell-list path, parity mode")
     elif name == "cfg4":
-        sysm = synthetic.spc_water(69, frames, seed=4 + 1000 * rank)
+        sysm = synthetic.spc_water(70, frames, seed=4 + 1000 * rank, n_molecules=333_333)
         cutoff, nbins = 8.0, 800
-        desc = (f"cfg4: {sysm.n_atoms}-atom SPC water (69^3 molecules), {frames} configurations "
-                f"per GPU, cutoff 8 A, 800 bins, 3 species pairs, cell-list path, parity mode")
+        desc = (f"cfg4: {sysm.n_atoms}-atom SPC water (333,333 molecules, L=215.3 A), {frames} "
+                f"configurations per GPU, cutoff 8 A, 800 bins, 3 species pairs, cell-list path, "
+                f"parity mode")
     else:
         raise SystemExit(f"unknown workload {name}")
     return sysm, cutoff, nbins, desc
@@ -235,12 +236,12 @@ def run_reference(args):
 # this repo's arm
 # ----------------------------------------------------------------------------------------------
 def cell_list_probe(device: int, fp32_peak: float, frames: int = 160):
-    """cfg3-shaped (97k-atom LJ fluid, cutoff 3 sigma, 300 bins) frames resident in HBM through the
+    """cfg3-shaped (100k-atom LJ fluid, cutoff 3 sigma, 300 bins) frames resident in HBM through the
     cell-list kernel: candidate-pair rate against the same FP32 roofline, the all-pairs-equivalent
     rate, and a parity gate against the all-pairs kernel on the same frames."""
     import torch
     from mdsuite_b200 import _cuda, synthetic
-    sysm = synthetic.lj_fluid(46, 4, seed=3)
+    sysm = synthetic.lj_fluid(47, 4, seed=3, n_atoms=100_000)
     base = torch.from_numpy(sysm.positions).cuda(device)
     pos = base.repeat((frames + 3) // 4, 1, 1)[:frames].contiguous()
     best = None

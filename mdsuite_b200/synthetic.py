@@ -72,13 +72,23 @@ def nacl_melt(n_cells: int, n_frames: int, seed: int, lattice: float = 6.3,
     return SyntheticSystem(f"nacl_{base.shape[0]}", pos, {"Na": len(na), "Cl": len(cl)}, box)
 
 
-def lj_fluid(n_side: int, n_frames: int, seed: int, rho: float = 0.8442,
-             sigma: float = 0.1) -> SyntheticSystem:
-    """n_side^3 atoms on a jittered simple-cubic lattice at reduced density rho (cfg3)."""
-    rng = _rng(seed)
-    n = n_side ** 3
-    box = np.full(3, (n / rho) ** (1.0 / 3.0))
+def _lattice_sites(n_side: int, n_keep: int, rng) -> np.ndarray:
+    """(n_keep, 3) integer sites of an n_side^3 simple-cubic lattice (random vacancies if fewer)."""
     g = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    if n_keep < len(g):
+        g = g[np.sort(rng.permutation(len(g))[:n_keep])]
+    return g
+
+
+def lj_fluid(n_side: int, n_frames: int, seed: int, rho: float = 0.8442,
+             sigma: float = 0.1, n_atoms: int = None) -> SyntheticSystem:
+    """Atoms on a jittered simple-cubic lattice at reduced density rho (cfg3): n_side^3 of them, or
+    exactly ``n_atoms`` (<= n_side^3, the rest of the sites stay vacant; cfg3 proper is
+    lj_fluid(47, F, seed, n_atoms=100_000))."""
+    rng = _rng(seed)
+    n = n_side ** 3 if n_atoms is None else int(n_atoms)
+    box = np.full(3, (n / rho) ** (1.0 / 3.0))
+    g = _lattice_sites(n_side, n, rng)
     base = (g + 0.5) * (box[0] / n_side)
     pos = np.empty((n_frames, n, 3), dtype=np.float32)
     for f in range(n_frames):
@@ -86,13 +96,15 @@ def lj_fluid(n_side: int, n_frames: int, seed: int, rho: float = 0.8442,
     return SyntheticSystem(f"lj_{n}", pos, {"Ar": n}, box)
 
 
-def spc_water(n_side: int, n_frames: int, seed: int, rho_mol: float = 0.0334) -> SyntheticSystem:
-    """n_side^3 rigid SPC molecules (r_OH = 1.0 A, 109.47 deg), random orientations, on a jittered
-    lattice; species order O (n), H (2n) (cfg4: n_side=70 -> 343 000 molecules ~ 1.03 M atoms)."""
+def spc_water(n_side: int, n_frames: int, seed: int, rho_mol: float = 0.0334,
+              n_molecules: int = None) -> SyntheticSystem:
+    """Rigid SPC molecules (r_OH = 1.0 A, 109.47 deg), random orientations, on a jittered lattice;
+    species order O (n), H (2n): n_side^3 molecules, or exactly ``n_molecules`` (cfg4 proper is
+    spc_water(70, F, seed, n_molecules=333_333): 999 999 atoms, L = 215.3 A)."""
     rng = _rng(seed)
-    n = n_side ** 3
+    n = n_side ** 3 if n_molecules is None else int(n_molecules)
     box = np.full(3, (n / rho_mol) ** (1.0 / 3.0))
-    g = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    g = _lattice_sites(n_side, n, rng)
     base = (g + 0.5) * (box[0] / n_side)
     half = np.deg2rad(109.47) / 2
     h_local = np.array([[np.sin(half), 0.0, np.cos(half)], [-np.sin(half), 0.0, np.cos(half)]])

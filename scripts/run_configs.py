@@ -91,12 +91,12 @@ def main():
                                int(cutoff / 0.01), 1000, 16))
         results.append(measure("cfg2 NaCl 13,824 atoms, 1,000 cfgs, B=500, rc=10", s, 10.0, 500, 1000, 16))
     if "cfg3" in which:
-        s = synthetic.lj_fluid(46, 8, seed=3)
-        results.append(measure("cfg3 LJ 97,336 atoms (46^3), 1,000 of 10,000 cfgs, B=300, rc=3",
+        s = synthetic.lj_fluid(47, 8, seed=3, n_atoms=100_000)
+        results.append(measure("cfg3 LJ 100,000 atoms, 1,000 of 10,000 cfgs, B=300, rc=3",
                                s, 3.0, 300, 1000, 1))
     if "cfg4" in which:
-        s = synthetic.spc_water(69, 2, seed=4)
-        results.append(measure("cfg4 SPC water 985,527 atoms (69^3 x 3), 32 of 1,000 cfgs, B=800, rc=8",
+        s = synthetic.spc_water(70, 2, seed=4, n_molecules=333_333)
+        results.append(measure("cfg4 SPC water 999,999 atoms, 32 of 1,000 cfgs, B=800, rc=8",
                                s, 8.0, 800, 32, 0))
     if "cfg5" in which:
         s = synthetic.ideal_gas(50_000, 8, seed=5)
