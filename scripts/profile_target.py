@@ -13,7 +13,7 @@ if which == "allpairs":
     cutoff = s.box[0] / 2 - 0.1
     nbins, frames, path = int(cutoff / 0.01), 48, "allpairs"
 elif which == "cells":
-    s = synthetic.lj_fluid(46, 4, seed=3)
+    s = synthetic.lj_fluid(47, 4, seed=3, n_atoms=100_000)
     cutoff, nbins, frames, path = 3.0, 300, 64, "celllist"
 else:
     s = synthetic.spc_water(69, 1, seed=4)
