@@ -774,8 +774,15 @@ int mds_rdf_submit(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
   }
   CUDA_TRY(cudaEventRecord(h->ev_t0, h->s_compute));
   bool first_kernel = true;
-  for (int64_t f0 = 0; f0 < n_frames; f0 += h->batch_frames) {
-    const int64_t nf = std::min<int64_t>(h->batch_frames, n_frames - f0);
+  // Ramp: the first host->device copy of a submit cannot overlap any compute, so the first two
+  // batches are small (1/16 and 1/4 of a full one) and the pipeline fills in a fraction of a
+  // full batch's copy time.
+  int64_t ramp = 0;
+  for (int64_t f0 = 0; f0 < n_frames;) {
+    int64_t cap = h->batch_frames;
+    if (n_frames > h->batch_frames && ramp < 2) cap = std::max<int64_t>(1, cap / (ramp == 0 ? 16 : 4));
+    ++ramp;
+    const int64_t nf = std::min<int64_t>(cap, n_frames - f0);
     const int b = h->buf;
     // the staging buffer must have been consumed by the pack kernel of two batches ago
     CUDA_TRY(cudaStreamWaitEvent(h->s_copy, h->ev_raw_free[b], 0));
@@ -799,6 +806,7 @@ int mds_rdf_submit(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
     if (rc != MDS_OK) return rc;
     CUDA_TRY(cudaEventRecord(h->ev_raw_free[b], h->s_compute));
     h->buf ^= 1;
+    f0 += nf;
   }
   CUDA_TRY(cudaEventRecord(h->ev_k1, h->s_compute));
   CUDA_TRY(cudaEventRecord(h->ev_t1, h->s_compute));
