@@ -62,6 +62,24 @@ def measure(name, sysm, cutoff, nbins, frames, oracle_frames, path=None, parity=
             "us_per_frame_resident": statistics.median(step) * 1e3 / frames,
             "bins_over_int32": int((got >= np.uint64(2 ** 31)).sum()),
         })
+        if name.startswith("cfg5") and not parity:
+            # analytic check: uniform random points, every pair counted -> g(r) = 1; compare the
+            # counts with the exact shell volumes (minimum-image sphere inside the box: r <= L/2)
+            n, L = sysm.n_atoms, float(sysm.box[0])
+            k = np.arange(nbins)
+            dr = cutoff / nbins
+            shell = 4 * np.pi / 3 * (((k + 1) * dr) ** 3 - (k * dr) ** 3)
+            expect = frames * n * (n - 1) / 2 * shell / L ** 3
+            ok = (k + 1) * dr <= L / 2
+            # the timed trajectory repeats the distinct frames `reps` times: the fluctuation of a
+            # count is that of the distinct frames, scaled by reps
+            z = (got[0][ok].astype(np.float64) - expect[ok]) / np.sqrt(expect[ok] * reps)
+            big = expect[ok] > 50  # Gaussian regime
+            out["ideal_gas_gate"] = {"bins_checked": int(big.sum()), "distinct_frames": int(base.shape[0]),
+                                     "max_abs_z": float(np.abs(z[big]).max()) if big.any() else None,
+                                     "rms_z": float(np.sqrt(np.mean(z[big] ** 2))) if big.any() else None,
+                                     "g_mean": float(np.mean(got[0][ok][big] / expect[ok][big]))
+                                     if big.any() else None}
         # gates: bit-exact vs the oracle on a bounded sample of the same frames
         nf = min(oracle_frames, base.shape[0])
         if nf > 0:
