@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in Nsight Systems, no-ops otherwise
+
 #include "mds_rdf.h"
 #include "rdf_common.cuh"
 #include "rdf_launch.h"
@@ -149,6 +151,11 @@ struct mds_rdf {
 namespace {
 
 constexpr int WORK_RING = 4096;
+
+struct NvtxRange {  // tracing hook the reference lacks (timers at DEBUG level only)
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DeviceGuard {
   int prev = -1;
@@ -429,6 +436,8 @@ int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t fram
 
 int process_batch(mds_rdf* h, const float* d_xyz, int layout, int64_t frame0, int64_t n_frames,
                   int64_t n_frames_total, int buf) {
+  NvtxRange range(h->path == MDS_RDF_PATH_CELLLIST ? "mds_rdf batch (cell list)"
+                                                   : "mds_rdf batch (all pairs)");
   return h->path == MDS_RDF_PATH_CELLLIST
              ? process_batch_cells(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf)
              : process_batch_allpairs(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf);
@@ -735,6 +744,7 @@ int mds_rdf_submit_device(mds_rdf_t* h, const float* d_xyz, int64_t n_frames, in
   int rc = check_submit_args(h, d_xyz, n_frames, layout, "mds_rdf_submit_device");
   if (rc != MDS_OK) return rc;
   if (n_frames == 0) return MDS_OK;
+  NvtxRange range("mds_rdf_submit_device");
   DeviceGuard guard(h->device);
   CUDA_TRY(cudaEventRecord(h->ev_ext, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_ext, 0));
@@ -758,6 +768,7 @@ int mds_rdf_submit(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
   int rc = check_submit_args(h, xyz, n_frames, layout, "mds_rdf_submit");
   if (rc != MDS_OK) return rc;
   if (n_frames == 0) return MDS_OK;
+  NvtxRange range("mds_rdf_submit (host frames)");
   (void)host_is_pinned;  // cudaMemcpyAsync stages pageable memory itself
   DeviceGuard guard(h->device);
   const size_t frame_bytes = (size_t)h->n_atoms * 3 * sizeof(float);
