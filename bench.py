@@ -477,7 +477,7 @@ def run_ours(args):
         "config": {"workload": desc, "frames_per_gpu": n_frames, "atoms": n_atoms, "nbins": nbins,
                    "cutoff": cutoff, "species_pairs": n_pairs,
                    "l2": f"inputs larger than L2: {12 * n_atoms * n_frames / 1e6:.0f} MB raw xyz + "
-                         f"{16 * n_atoms * n_frames / 1e6:.0f} MB packed per step vs 126 MB L2",
+                         f"{12 * n_atoms * n_frames / 1e6:.0f} MB packed per step vs 126 MB L2",
                    "parallelism": f"frames sharded over {world} GPU(s), 1 NCCL allreduce/step"
                    if world > 1 else "1 GPU"},
         "roofline": roofline, "cell_list_path": cell_list, "cpu_baseline": cpu_baseline,

@@ -6,7 +6,7 @@ scale function (mdsuite/memory_management/memory_manager.py:179-219); for the RD
 function (calculators/radial_distribution_function.py:119-121) collapses that to ONE configuration
 per batch for anything above ~1 000 atoms, because the TensorFlow path materialises
 O(m*N) pair tensors.  The CUDA path materialises nothing per pair: a configuration costs 12 B/atom
-of staging plus 16 B/atom packed, so the scale function is linear and batches hold hundreds of
+of staging plus 12 B/atom packed (up to 44 B/atom on the cell-list path), so the scale function is linear and batches hold hundreds of
 frames.  ``get_batch_size`` keeps the reference's (batch_size, n_batches, remainder) contract.
 """
 from __future__ import annotations
@@ -18,8 +18,8 @@ import numpy as np
 from mdsuite_b200.utils.config import config
 
 # bytes held per configuration byte on disk: pinned host ring (2 x 1) + device staging (2 x 1) +
-# packed float4 frames (2 x 16/12)
-GPU_LINEAR_SCALE = 2 + 2 + 2 * 16 / 12
+# packed quad-block frames (2 x 1); the cell-list path adds sorted atoms and ranks (2 x 20/12)
+GPU_LINEAR_SCALE = 2 + 2 + 2 + 2 * 20 / 12
 
 
 def linear_scale_function(memory_usage: float, scale_factor: float = 1.0) -> float:
