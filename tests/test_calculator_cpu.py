@@ -183,7 +183,8 @@ def test_memory_manager_batch_size_contract():
     mm = MemoryManager(data_path=["Na/Positions", "Cl/Positions"], database=FakeDB(),
                        memory_fraction=0.5, free_memory=10 ** 6)
     batch, n_batches, remainder = mm.get_batch_size()
-    per_conf = 2 * 12000 * (2 + 2 + 2 * 16 / 12)
+    from mdsuite_b200.memory_management.memory_manager import GPU_LINEAR_SCALE
+    per_conf = 2 * 12000 * GPU_LINEAR_SCALE
     assert batch == int(0.5 * 10 ** 6 / per_conf) and (n_batches, remainder) == divmod(100, batch)
     mm = MemoryManager(data_path=["Na/Positions"], database=FakeDB(), free_memory=10 ** 12)
     assert mm.get_batch_size() == (100, 1, 0)  # clipped to the number of configurations
