@@ -1,0 +1,76 @@
+"""Two ranks, two GPUs, NCCL: the calculator shards the sampled configurations over the ranks,
+every rank's handle accumulates its block, ONE allreduce of the device accumulator combines them,
+and every rank ends with the full g(r) — equal to the oracle's.  Skipped on boxes with one GPU (the
+same logic runs on CPU under gloo in tests/test_distributed_cpu.py)."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import json, os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["MDS_ROOT"])
+import mdsuite_b200 as mds
+from mdsuite_b200 import synthetic
+
+rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+os.environ.pop("NCCL_DEBUG", None)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+out = os.environ["MDS_OUT"]
+for name, sysm, cutoff, nbins in (
+        ("nacl", synthetic.nacl_melt(4, 11, seed=21), 9.0, 90),          # all-pairs kernel, 11 frames
+        ("lj", synthetic.lj_fluid(16, 5, seed=22), 3.0, 300)):          # cell-list kernel, 5 frames
+    project = mds.Project(f"{name}_rank{rank}", storage_path=out)
+    exp = project.add_experiment("e")
+    exp.add_positions(sysm.positions, sysm.species, sysm.box)
+    calc = exp.run.RadialDistributionFunction
+    comp = calc(number_of_configurations=sysm.n_frames, number_of_bins=nbins, cutoff=cutoff, plot=False)
+    np.save(os.path.join(out, f"{name}_y{rank}.npy"),
+            np.array([comp[k]["y"] for k in comp.keys()], dtype=float))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_two_ranks_nccl_calculator(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MDS_ROOT=ROOT, MDS_OUT=str(tmp_path))
+    proc = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
+        env=env, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, (proc.stdout + proc.stderr)[-3000:]
+
+    from mdsuite_b200 import synthetic
+    from oracle import c_oracle, rdf_oracle
+    for name, sysm, cutoff, nbins in (("nacl", synthetic.nacl_melt(4, 11, seed=21), 9.0, 90),
+                                      ("lj", synthetic.lj_fluid(16, 5, seed=22), 3.0, 300)):
+        y0, y1 = np.load(tmp_path / f"{name}_y0.npy"), np.load(tmp_path / f"{name}_y1.npy")
+        assert np.array_equal(y0[:, 1:], y1[:, 1:])  # every rank holds the allreduced result
+        counts, _ = c_oracle.rdf_counts_c(sysm.positions, sysm.counts, sysm.box, cutoff, nbins,
+                                          layout=c_oracle.FRAME_MAJOR)
+        names = list(sysm.species)
+        want = rdf_oracle.normalise(counts, names, sysm.counts, sysm.box, cutoff, sysm.n_frames)
+        for row, key in zip(y0, want):
+            assert np.allclose(row[1:], np.array(want[key]["y"])[1:], rtol=1e-12, atol=0)
