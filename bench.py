@@ -421,7 +421,11 @@ def run_ours(args):
         except (OSError, ValueError, AttributeError):
             traffic = None
     roofline = {
-        "bound": "fp32", "kernel": kernel_name, "achieved": achieved / 1e12,
+        "bound": "fp32",
+        "bound_note": "FP32 issue rate and shared-memory atomics govern this path (SURVEY.md 8d): a "
+                      "distance histogram is not a contraction (no tensor-core work) and the frame "
+                      "stream uses <0.1% of HBM bandwidth (see hbm)",
+        "kernel": kernel_name, "achieved": achieved / 1e12,
         "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
         "traffic": traffic, "pair_evals_per_s": kernel_rate,
         "pair_evals_per_s_peak": fp32_peak / FLOP_PER_PAIR, "flop_per_pair": FLOP_PER_PAIR,
