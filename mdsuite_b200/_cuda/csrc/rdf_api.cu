@@ -649,9 +649,21 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   CREATE_TRY(cudaMalloc(&h->d_general, 2 * sizeof(unsigned long long)));
   CREATE_TRY(cudaMemset(h->d_general, 0, 2 * sizeof(unsigned long long)));
   if (cells) {
+    // (row species, column species) of every pair.  For a != b either orientation counts the same
+    // pairs (full 27-cell shell); rows fill lane slots in groups of 8 (passes of 32), so the
+    // species whose average cell occupancy packs better becomes the row species
+    // (SPC water, 8 A cutoff: O 19 per cell -> 24 slots, H 38 -> 40 slots: H rows, -17 % work).
+    auto lane_efficiency = [&](int s) {
+      const double n = (double)h->pcnt[s] / (double)h->grid.nc;
+      if (n <= 0.0) return 0.0;
+      const double full = std::floor(n / 32.0) * 32.0;
+      const double slots = full + std::ceil((n - full) / 8.0) * 8.0;
+      return n / std::max(slots, 8.0);
+    };
     std::vector<int2> ab;
     for (int a = 0; a < h->n_species; ++a)
-      for (int b = a; b < h->n_species; ++b) ab.push_back(make_int2(a, b));
+      for (int b = a; b < h->n_species; ++b)
+        ab.push_back(lane_efficiency(b) > lane_efficiency(a) ? make_int2(b, a) : make_int2(a, b));
     CREATE_TRY(cudaMalloc(&h->d_pair_ab, ab.size() * sizeof(int2)));
     CREATE_TRY(cudaMemcpy(h->d_pair_ab, ab.data(), ab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMalloc(&h->d_work64, sizeof(unsigned long long) * WORK_RING));
