@@ -338,6 +338,53 @@ class RDFHandle:
         return edges, np.float32(s_cut.value)
 
 
+# ---- handle reuse ------------------------------------------------------------------------------
+# Creating and destroying a handle costs ~50 ms (cudaMalloc / cudaFree of the frame buffers, the
+# threshold table, the work schedule) — more than the kernels of a few hundred frames.  The
+# calculator therefore parks its handle here when a run ends and the next run with the same
+# configuration takes it back (after a reset).  One parked handle per device.
+_PARKED = {}
+
+
+def _handle_key(counts, nbins, cutoff, box, parity, device, path):
+    return (tuple(int(c) for c in counts), int(nbins), float(np.float32(cutoff)),
+            tuple(float(v) for v in np.asarray(box, dtype=np.float32)), bool(parity), int(device),
+            path or "auto")
+
+
+def acquire_handle(counts, nbins, cutoff, box, parity=True, device=0, path=None) -> "RDFHandle":
+    """A reset handle for this configuration: the parked one if it matches, else a new one."""
+    key = _handle_key(counts, nbins, cutoff, box, parity, device, path)
+    parked = _PARKED.pop(int(device), None)
+    if parked is not None:
+        if parked[0] == key:
+            parked[1].reset()
+            return parked[1]
+        parked[1].close()
+    h = RDFHandle(counts, nbins, cutoff, box, parity=parity, device=device, path=path)
+    h._park_key = key
+    return h
+
+
+def park_handle(h: "RDFHandle"):
+    """Give a handle back for reuse (its streams are synchronised first)."""
+    key = getattr(h, "_park_key", None)
+    if key is None or not h._h.value:
+        h.close()
+        return
+    h.synchronize()
+    old = _PARKED.pop(h.device, None)
+    if old is not None:
+        old[1].close()
+    _PARKED[h.device] = (key, h)
+
+
+def drop_parked_handles():
+    for _key, h in list(_PARKED.values()):
+        h.close()
+    _PARKED.clear()
+
+
 def build_threshold_table(cutoff: float, nbins: int):
     """Host-only: (edges[0..nbins] float32, s_cut) for float32(cutoff) — needs no GPU."""
     edges = np.zeros(nbins + 1, dtype=np.float32)

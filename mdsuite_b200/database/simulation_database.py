@@ -66,6 +66,19 @@ class TrajectoryChunkData:
         sp[property_name][config_idx:config_idx + n] = array
 
 
+_COPY_THREADS = max(1, min(8, (os.cpu_count() or 1) // 2))
+_POOL = None
+
+
+def _copy_pool():
+    """Threads that move frames from the page cache into (pinned) staging buffers."""
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=_COPY_THREADS, thread_name_prefix="mds-frames")
+    return _POOL
+
+
 def _file_name(path: str) -> str:
     return path.replace("/", "__") + ".f32"
 
@@ -148,14 +161,36 @@ class Database:
         into ``out`` (e.g. a pinned staging buffer slice) when given."""
         mm = self._map(path)
         frames = np.asarray(frames, dtype=np.int64)
-        contiguous = len(frames) > 0 and np.all(np.diff(frames) == 1)
-        src = mm[frames[0]:frames[-1] + 1] if contiguous else mm[frames]
+        select = None
         if atom_selection is not None and not (isinstance(atom_selection, slice)
                                                and atom_selection == slice(None)):
-            src = src[:, atom_selection]
+            select = atom_selection
+        n_sel = mm.shape[1] if select is None else len(np.arange(mm.shape[1])[select])
         if out is None:
-            return np.array(src, dtype=np.float32)
-        np.copyto(out, src)
+            out = np.empty((len(frames), n_sel, mm.shape[2]), dtype=np.float32)
+        if len(frames) == 0:
+            return out
+        if frames.min() < 0 or frames.max() >= mm.shape[0]:
+            raise IndexError(f"{path}: configuration index outside [0, {mm.shape[0]})")
+        contiguous = bool(np.all(np.diff(frames) == 1))
+
+        def copy_block(lo: int, hi: int):  # one pass from the page cache into `out`, no temporaries
+            if select is None and contiguous:
+                np.copyto(out[lo:hi], mm[frames[lo]:frames[lo] + (hi - lo)])
+            elif select is None:
+                # mode="clip": with the default "raise" NumPy buffers `out` (a second copy)
+                np.take(mm, frames[lo:hi], axis=0, out=out[lo:hi], mode="clip")
+            else:
+                for k in range(lo, hi):
+                    out[k] = mm[frames[k]][select]
+
+        n_bytes = len(frames) * n_sel * mm.shape[2] * 4
+        n_jobs = min(_COPY_THREADS, len(frames), max(1, n_bytes // (4 << 20)))
+        if n_jobs <= 1:
+            copy_block(0, len(frames))
+        else:  # NumPy releases the GIL in these copies: the threads run on separate cores
+            bounds = np.linspace(0, len(frames), n_jobs + 1).astype(int)
+            list(_copy_pool().map(lambda ab: copy_block(ab[0], ab[1]), zip(bounds[:-1], bounds[1:])))
         return out
 
     def load_data(self, path_list: Sequence[str], select_slice=np.s_[:]) -> Dict[str, np.ndarray]:

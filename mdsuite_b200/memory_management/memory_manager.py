@@ -75,6 +75,28 @@ class MemoryManager:
         return batch_size, n_batches, remainder
 
 
+_RING_CACHE = {}  # (shape, pinned) -> list of idle rings
+
+
+def _acquire_ring(shape, pin: bool):
+    """Two staging buffers of ``shape``.  Page-locking costs ~0.2 ms/MB, so rings are returned to
+    a small per-process cache when a batcher is closed and reused by the next calculator call."""
+    import torch
+    key = (tuple(shape), bool(pin))
+    idle = _RING_CACHE.get(key)
+    if idle:
+        return key, idle.pop()
+    return key, [torch.empty(shape, dtype=torch.float32, pin_memory=pin) for _ in range(2)]
+
+
+def _release_ring(key, ring):
+    for other in [k for k in _RING_CACHE if k != key]:  # keep one shape: bounded pinned memory
+        del _RING_CACHE[other]
+    idle = _RING_CACHE.setdefault(key, [])
+    if len(idle) < 8:
+        idle.append(ring)
+
+
 class FrameBatcher:
     """Streams configurations from the trajectory store into a ring of two pinned host buffers and
     submits them to a ``RDFHandle``; the library copies them H2D on its side stream while the
@@ -92,11 +114,16 @@ class FrameBatcher:
         self.frames_per_batch = max(1, int(frames_per_batch))
         self.atom_selections = atom_selections or [None] * len(self.paths)
         n_atoms = sum(self.n_particles)
-        self._ring = [torch.empty((self.frames_per_batch, n_atoms, 3), dtype=torch.float32,
-                                  pin_memory=pin) for _ in range(2)]
+        self._ring_key, self._ring = _acquire_ring((self.frames_per_batch, n_atoms, 3), pin)
         self.pinned = pin
         self.frames_submitted = 0
         self.bytes_staged = 0
+
+    def close(self):
+        """Hand the staging buffers back (call after the handle has been synchronised)."""
+        if self._ring is not None:
+            _release_ring(self._ring_key, self._ring)
+            self._ring = None
 
     def run(self, sample_configurations: Sequence[int]) -> int:
         """Submit the given configuration indices (in order); returns the number of frames."""
