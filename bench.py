@@ -235,6 +235,30 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------------
+def user_api_probe(sysm, cutoff, nbins, pairs_per_step):
+    """The workload through the call a user makes: frames ingested into a project's trajectory
+    store, then ``experiment.run.RadialDistributionFunction(...)`` (FrameBatcher -> C ABI ->
+    normalisation); wall time of the best of three calls after a first one."""
+    import tempfile
+    import mdsuite_b200 as mds
+    with tempfile.TemporaryDirectory() as tmp:
+        project = mds.Project("bench", storage_path=tmp)
+        exp = project.add_experiment("workload", units="real")
+        exp.add_positions(sysm.positions, sysm.species, sysm.box)
+        times = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            exp.run.RadialDistributionFunction(number_of_configurations=sysm.n_frames, cutoff=cutoff,
+                                               number_of_bins=nbins, plot=False, save=False)
+            times.append(time.perf_counter() - t0)
+    best = min(times[1:])
+    return {"call": "experiment.run.RadialDistributionFunction(number_of_configurations=%d, ...)"
+                    % sysm.n_frames, "seconds": best, "first_call_seconds": times[0],
+            "value": pairs_per_step / best, "unit": UNIT,
+            "note": "frames read from the frame-major store through the pinned ring; includes "
+                    "normalisation; results not saved"}
+
+
 def cell_list_probe(device: int, fp32_peak: float, frames: int = 160):
     """cfg3-shaped (100k-atom LJ fluid, cutoff 3 sigma, 300 bins) frames resident in HBM through the
     cell-list kernel: candidate-pair rate against the same FP32 roofline, the all-pairs-equivalent
@@ -449,6 +473,14 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             cell_list = {"error": str(exc)}
 
+    # ---- the same step through the user-level call (rank 0, N = 1 only) ---------------------
+    user_api = None
+    if world == 1 and not args.no_user_api:
+        try:
+            user_api = user_api_probe(sysm, cutoff, nbins, pairs_per_step)
+        except Exception as exc:  # noqa: BLE001
+            user_api = {"error": str(exc)}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------
     cpu_baseline = None
     parity = None
@@ -484,7 +516,8 @@ def run_ours(args):
                          f"{12 * n_atoms * n_frames / 1e6:.0f} MB packed per step vs 126 MB L2",
                    "parallelism": f"frames sharded over {world} GPU(s), 1 NCCL allreduce/step"
                    if world > 1 else "1 GPU"},
-        "roofline": roofline, "cell_list_path": cell_list, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "cell_list_path": cell_list, "user_api": user_api,
+        "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "h2d_bytes_per_step": int(12 * n_atoms * n_frames),
                 "d2h_bytes_per_step": int(8 * n_pairs * nbins)},
@@ -535,6 +568,8 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=12,
                     help="configurations timed by the op-by-op CPU baseline (x8 for the C port)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-user-api", action="store_true",
+                    help="skip the Project -> Experiment -> run.RadialDistributionFunction timing")
     ap.add_argument("--no-cell-probe", action="store_true",
                     help="skip the short cfg3-shaped cell-list measurement added at N=1")
     args = ap.parse_args()
