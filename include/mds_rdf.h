@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MDS_RDF_ABI_VERSION 2
+#define MDS_RDF_ABI_VERSION 3
 
 #if defined(MDS_BUILD) && defined(__GNUC__)
 #define MDS_API __attribute__((visibility("default")))
@@ -85,8 +85,11 @@ typedef struct mds_rdf_stats {
   uint32_t struct_size;
   int32_t path;                /* MDS_RDF_PATH_ALLPAIRS or MDS_RDF_PATH_CELLLIST actually used */
   int64_t frames;              /* frames accumulated since create/reset */
-  double pairs_evaluated;      /* (i, j, frame) triples distance-tested (candidates on the cell path) */
-  double pairs_allpairs_equiv; /* frames * sum over species pairs of the reference's pair count */
+  double pairs_evaluated;      /* (i, j, frame) triples distance-tested by this handle, counted on the
+                                  device: reference pairs on the all-pairs path, candidate pairs of
+                                  adjacent cells on the cell path (this shard's share if sharded) */
+  double pairs_allpairs_equiv; /* frames * sum over species pairs of the reference's pair count
+                                  (divided by the shard count if sharded) */
   double pairs_binned;         /* triples with d < cutoff (= sum of all histogram bins) */
   int64_t frames_general_minimage; /* frames that needed the div/rint minimum image (not wrapped) */
   int64_t kernel_launches;     /* kernels of this library launched since create/reset */
@@ -102,7 +105,7 @@ typedef struct mds_rdf_stats {
   int32_t frames_far;          /* cell path: frames with a coordinate beyond 8 box lengths, which
                                   were handed to the all-pairs kernel */
   int32_t cells[3];            /* cell path: cells per dimension (0 on the all-pairs path) */
-  int32_t reserved;
+  int32_t item_shards;         /* shard count set with mds_rdf_set_item_shard (1: none) */
 } mds_rdf_stats;
 
 typedef struct mds_rdf mds_rdf_t;
@@ -147,6 +150,13 @@ MDS_API int mds_rdf_wait(mds_rdf_t* h, void* stream);
 /* Block the host until every host->device copy issued by mds_rdf_submit so far has completed,
  * i.e. until the submitted host buffers may be overwritten (the kernels may still be running). */
 MDS_API int mds_rdf_wait_host_copies(mds_rdf_t* h);
+
+/* Item sharding — strong scaling WITHIN frames, for runs with fewer configurations than GPUs
+ * (SURVEY.md §8e "fallback for F < G"): every rank submits the same frames, the handle of rank
+ * `index` of `count` processes every count-th unit of the (work item, frame) enumeration, and the
+ * allreduce over the ranks' counts gives the full histogram.  Affects submits made afterwards;
+ * (0, 1) restores the default.  Statistics report this shard's share. */
+MDS_API int mds_rdf_set_item_shard(mds_rdf_t* h, int32_t index, int32_t count);
 
 MDS_API int mds_rdf_synchronize(mds_rdf_t* h);
 MDS_API int mds_rdf_reset(mds_rdf_t* h); /* zero the accumulated counts and statistics */

@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # (make -C csrc checked; see rdf_common.cuh MDS_CHECKED)
 LIB_PATH = os.environ.get("MDS_RDF_LIB") or os.path.join(_HERE, "libmds_rdf.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MDS_OK = 0
 PARITY_SKIP_FIRST = 0x1
 PATH_ALLPAIRS = 0x2
@@ -33,7 +33,7 @@ LAYOUT_ATOM_MAJOR = 1  # (n_atoms, n_frames, 3) — the reference's positions_te
 EXPORTED_SYMBOLS = (
     "mds_rdf_create", "mds_rdf_destroy", "mds_rdf_submit", "mds_rdf_submit_device",
     "mds_rdf_counts", "mds_rdf_device_counts", "mds_rdf_join", "mds_rdf_wait", "mds_rdf_wait_host_copies", "mds_rdf_synchronize",
-    "mds_rdf_reset",
+    "mds_rdf_reset", "mds_rdf_set_item_shard",
     "mds_rdf_stats_get", "mds_rdf_threshold_table", "mds_rdf_build_threshold_table",
     "mds_bench_shared_atomics",
     "mds_last_error", "mds_abi_version",
@@ -79,7 +79,7 @@ class _Stats(ctypes.Structure):
         ("dense", ctypes.c_int32),
         ("frames_far", ctypes.c_int32),
         ("cells", ctypes.c_int32 * 3),
-        ("reserved", ctypes.c_int32),
+        ("item_shards", ctypes.c_int32),
     ]
 
 
@@ -103,6 +103,7 @@ class RDFStats:
     dense: int
     frames_far: int = 0
     cells: tuple = (0, 0, 0)
+    item_shards: int = 1
 
     @property
     def path_name(self) -> str:
@@ -135,6 +136,7 @@ def load() -> ctypes.CDLL:
     lib.mds_rdf_wait_host_copies.argtypes = [vp]
     lib.mds_rdf_synchronize.argtypes = [vp]
     lib.mds_rdf_reset.argtypes = [vp]
+    lib.mds_rdf_set_item_shard.argtypes = [vp, ctypes.c_int32, ctypes.c_int32]
     lib.mds_rdf_stats_get.argtypes = [vp, ctypes.POINTER(_Stats)]
     lib.mds_rdf_threshold_table.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_float)]
     lib.mds_rdf_build_threshold_table.argtypes = [ctypes.c_float, i32, vp,
@@ -318,6 +320,13 @@ class RDFHandle:
     def reset(self):
         _check(self._lib.mds_rdf_reset(self._h), "mds_rdf_reset")
 
+    def set_item_shard(self, index: int, count: int):
+        """Strong scaling within frames: this handle takes every ``count``-th (work item, frame)
+        unit, starting at ``index``, of the frames submitted from now on; the sum over the
+        ``count`` handles' histograms is the full result.  (0, 1) switches it off."""
+        _check(self._lib.mds_rdf_set_item_shard(self._h, int(index), int(count)),
+               "mds_rdf_set_item_shard")
+
     def stats(self) -> RDFStats:
         st = _Stats()
         st.struct_size = ctypes.sizeof(_Stats)
@@ -327,7 +336,7 @@ class RDFHandle:
                         st.pairs_binned, st.frames_general_minimage, st.kernel_launches,
                         st.kernel_ms, st.submit_ms, st.n_pairs, st.nbins, st.sm_count, st.variant,
                         st.pair_kernel_ms, st.pair_kernel_launches, st.dense, st.frames_far,
-                        tuple(st.cells))
+                        tuple(st.cells), st.item_shards)
 
     def threshold_table(self):
         """(edges[0..nbins] float32, s_cut): the squared-distance thresholds the kernels use."""

@@ -154,17 +154,19 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
   const long long total = (long long)p.n_items * (long long)p.n_frames;
   uint32_t ph0 = 0, ph1 = 0;
   unsigned long long since_flush = 0;
+  unsigned long long my_pairs = 0;  // thread 0: reference pairs of the units this CTA processed
 
   for (;;) {
     if (tid == 0) *s_item = (int)atomicAdd(p.work_counter, 1u);
     __syncthreads();
-    const long long idx = (unsigned int)*s_item;
+    const long long idx = (long long)(unsigned int)*s_item * p.shard_count + p.shard_index;
     __syncthreads();  // everyone has read the slot before thread 0 overwrites it
     if (idx >= total) break;
     // big items first: consecutive indices walk the frames of one item
     const PairItem it = p.items[idx / p.n_frames];
     const int frame = (int)(idx % p.n_frames);
     if (p.frame_need_bits && !(p.frame_flags[frame] & p.frame_need_bits)) continue;  // CTA-uniform
+    if (tid == 0) my_pairs += ((unsigned long long)it.pairs_hi << 32) | it.pairs_lo;
     const float* __restrict__ fpos = p.pos + (long long)frame * p.frame_stride * 3;
     const bool fast = ((p.frame_flags[frame] & 3u) != 3u);  // see rdf_pack.cu
 
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(THREADS, MINB) rdf_allpairs_kernel(const AllPa
     }
   }
 
+  if (tid == 0 && my_pairs && p.evaluated) atomicAdd(p.evaluated, my_pairs);
   if (HIST_SMEM) {
     MDS_CHK(__syncthreads();
             checked_conservation(s_chk, issued, s_hist, n_hist, tid, THREADS, "rdf_allpairs_kernel");)
@@ -293,6 +296,7 @@ static cudaError_t launch_variant(const AllPairsParams& p, int sm_count, cudaStr
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
   long long total = (long long)p.n_items * p.n_frames;
+  total = (total - p.shard_index + p.shard_count - 1) / p.shard_count;  // this shard's units
   long long grid = (long long)per_sm * sm_count;  // persistent: a multiple of the SM count
   if (grid > total) grid = total;
   if (grid < 1) grid = 1;

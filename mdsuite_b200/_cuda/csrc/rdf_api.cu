@@ -112,6 +112,7 @@ struct mds_rdf {
   mds::CellGrid grid = {0, 0, 0, 0, {0, 0, 0}};
   int64_t off_stride = 0;         // uint32 entries per frame of the cell-offset table
   uint32_t flush_threshold = 1u << 30;
+  uint32_t shard_index = 0, shard_count = 1;  // item sharding (mds_rdf_set_item_shard)
   // device state
   int32_t* d_src_index = nullptr;
   int32_t* d_species = nullptr;
@@ -210,11 +211,31 @@ void build_items(mds_rdf* h, int tile_rows, int64_t frames_hint) {
       chunk = std::max(2048, ((chunk / 2 + 511) / 512) * 512);
     if (chunk > 8192) chunk = 8192;
   }
+  // species of every pair index, to find where the real (unpadded) columns of an item end
+  std::vector<int> pair_b;
+  for (int a = 0; a < h->n_species; ++a)
+    for (int b = a; b < h->n_species; ++b) pair_b.push_back(b);
   for (auto& it : items) {
     for (int j = it.j0; j < it.j1; j += chunk) {
       mds::PairItem c = it;
       c.j0 = j;
       c.j1 = std::min(it.j1, j + chunk);
+      // reference pairs of this item: real rows x real columns, col > row on same-species items
+      const int b = pair_b[(size_t)c.pair];
+      const long long c1 = std::min<long long>(c.j1, (long long)h->poff[b] + h->pcnt[b]);
+      unsigned long long pairs = 0;
+      if (c1 > c.j0) {
+        if (!c.diag) {
+          pairs = (unsigned long long)c.i_cnt * (unsigned long long)(c1 - c.j0);
+        } else {
+          for (long long r = c.i0; r < (long long)c.i0 + c.i_cnt; ++r) {
+            const long long lo = std::max<long long>(c.j0, r + 1);
+            if (c1 > lo) pairs += (unsigned long long)(c1 - lo);
+          }
+        }
+      }
+      c.pairs_lo = (uint32_t)(pairs & 0xffffffffull);
+      c.pairs_hi = (uint32_t)(pairs >> 32);
       h->items.push_back(c);
     }
   }
@@ -266,6 +287,9 @@ mds::AllPairsParams allpairs_params(mds_rdf* h, int buf, int64_t n_frames, int p
   for (int k = 0; k < 3; ++k) ap.box[k] = h->box[k];
   ap.frame_need_bits = 0;
   ap.gate = nullptr;
+  ap.evaluated = h->d_evaluated;
+  ap.shard_index = h->shard_index;
+  ap.shard_count = h->shard_count;
   ap.items = nullptr;
   ap.n_items = 0;
   ap.work_counter = nullptr;
@@ -406,6 +430,8 @@ int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t fram
     cp.inv_step = h->inv_step;
     for (int k = 0; k < 3; ++k) cp.box[k] = h->box[k];
     cp.flush_threshold = h->flush_threshold;
+    cp.shard_index = h->shard_index;
+    cp.shard_count = h->shard_count;
     const int slot = next_work_slot(h);
     if (slot < 0) return fail(MDS_ERR_CUDA, "work-counter reset failed");
     cp.work_counter = h->d_work64 + slot;
@@ -616,6 +642,16 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   }
   h->batch_frames = bf;
   build_items(h, mds::allpairs_variant_tile(h->variant), bf);
+  {
+    double sum = 0;
+    for (const auto& it : h->items) sum += (double)(((unsigned long long)it.pairs_hi << 32) | it.pairs_lo);
+    if (sum != h->pairs_per_frame) {
+      const int rc = fail(MDS_ERR_INVALID, "internal: work items cover %.0f pairs, expected %.0f", sum,
+                          h->pairs_per_frame);
+      delete h;
+      return rc;
+    }
+  }
   // group items by pair group so a launch sees a contiguous range (stable: keeps cost order)
   std::stable_sort(h->items.begin(), h->items.end(), [h](const mds::PairItem& x, const mds::PairItem& y) {
     return x.pair / h->pair_group < y.pair / h->pair_group;
@@ -646,6 +682,8 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   const size_t n_counts = (size_t)h->n_pairs * (size_t)h->nbins;
   CREATE_TRY(cudaMalloc(&h->d_counts, n_counts * sizeof(unsigned long long)));
   CREATE_TRY(cudaMemset(h->d_counts, 0, n_counts * sizeof(unsigned long long)));
+  CREATE_TRY(cudaMalloc(&h->d_evaluated, sizeof(unsigned long long)));
+  CREATE_TRY(cudaMemset(h->d_evaluated, 0, sizeof(unsigned long long)));
   CREATE_TRY(cudaMalloc(&h->d_general, 2 * sizeof(unsigned long long)));
   CREATE_TRY(cudaMemset(h->d_general, 0, 2 * sizeof(unsigned long long)));
   if (cells) {
@@ -668,8 +706,6 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
     CREATE_TRY(cudaMemcpy(h->d_pair_ab, ab.data(), ab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMalloc(&h->d_work64, sizeof(unsigned long long) * WORK_RING));
     CREATE_TRY(cudaMemset(h->d_work64, 0, sizeof(unsigned long long) * WORK_RING));
-    CREATE_TRY(cudaMalloc(&h->d_evaluated, sizeof(unsigned long long)));
-    CREATE_TRY(cudaMemset(h->d_evaluated, 0, sizeof(unsigned long long)));
     CREATE_TRY(cudaMalloc(&h->d_batch_far, 2 * sizeof(unsigned long long)));
     CREATE_TRY(cudaMemset(h->d_batch_far, 0, 2 * sizeof(unsigned long long)));
     for (int b = 0; b < 2; ++b) {
@@ -899,6 +935,15 @@ int mds_rdf_reset(mds_rdf_t* h) {
   return MDS_OK;
 }
 
+int mds_rdf_set_item_shard(mds_rdf_t* h, int32_t index, int32_t count) {
+  if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_set_item_shard: handle is NULL");
+  if (count < 1 || index < 0 || index >= count)
+    return fail(MDS_ERR_INVALID, "mds_rdf_set_item_shard: shard %d of %d", index, count);
+  h->shard_index = (uint32_t)index;
+  h->shard_count = (uint32_t)count;
+  return MDS_OK;
+}
+
 int mds_rdf_stats_get(mds_rdf_t* h, mds_rdf_stats* out) {
   if (!h || !out) return fail(MDS_ERR_INVALID, "mds_rdf_stats_get: NULL argument");
   if (out->struct_size != sizeof(mds_rdf_stats))
@@ -918,14 +963,15 @@ int mds_rdf_stats_get(mds_rdf_t* h, mds_rdf_stats* out) {
   out->path = h->path;
   out->frames = h->frames_done;
   out->pairs_allpairs_equiv = h->pairs_per_frame * (double)h->frames_done;
-  if (h->path == MDS_RDF_PATH_CELLLIST) {
+  {
+    // counted on the device: reference pairs of every (item, frame) unit the all-pairs kernel
+    // processed (all of them, or this handle's item shard, or the far frames handed over by the
+    // cell path) + the candidate pairs the cell kernel tested
     unsigned long long ev = 0;
     CUDA_TRY(cudaMemcpy(&ev, h->d_evaluated, sizeof(ev), cudaMemcpyDeviceToHost));
-    // candidates tested by the cell kernel + every pair of the frames the all-pairs kernel took
-    out->pairs_evaluated = (double)ev + h->pairs_per_frame * (double)general[1];
-  } else {
-    out->pairs_evaluated = out->pairs_allpairs_equiv;
+    out->pairs_evaluated = (double)ev;
   }
+  out->pairs_allpairs_equiv /= (double)h->shard_count;
   out->pairs_binned = binned;
   out->frames_general_minimage = (int64_t)general[0];
   out->kernel_launches = h->launches;
@@ -952,7 +998,7 @@ int mds_rdf_stats_get(mds_rdf_t* h, mds_rdf_stats* out) {
   out->cells[0] = h->grid.nx;
   out->cells[1] = h->grid.ny;
   out->cells[2] = h->grid.nz;
-  out->reserved = 0;
+  out->item_shards = (int32_t)h->shard_count;
   return MDS_OK;
 }
 

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsP
 
   unsigned long long nxt_raw = 0;
   if (lane == 0) nxt_raw = atomicAdd(p.work_counter, 1ull);
-  unsigned long long idx = __shfl_sync(0xffffffffu, nxt_raw, 0);
+  unsigned long long idx = __shfl_sync(0xffffffffu, nxt_raw, 0) * p.shard_count + p.shard_index;
 
   while (idx < total_items) {
     if (lane == 0) nxt_raw = atomicAdd(p.work_counter, 1ull);  // in flight during this item
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsP
                               (unsigned long long)n * (unsigned long long)(total - n)
                         : (unsigned long long)n * (unsigned long long)total;
     } while (0);
-    idx = __shfl_sync(0xffffffffu, nxt_raw, 0);
+    idx = __shfl_sync(0xffffffffu, nxt_raw, 0) * p.shard_count + p.shard_index;
   }
 
   if (lane == 0 && evaluated) atomicAdd(p.evaluated, evaluated);
@@ -509,8 +509,9 @@ cudaError_t launch_cells(const CellsParams& p, int sm_count, cudaStream_t stream
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CELL_THREADS, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-  const unsigned long long items =
+  unsigned long long items =
       (unsigned long long)p.n_frames * (unsigned long long)p.pair_cnt * (unsigned long long)p.nc;
+  items = (items + p.shard_count - 1) / p.shard_count;
   unsigned long long grid = (unsigned long long)per_sm * sm_count;  // persistent
   const unsigned long long need = (items + CELL_WARPS - 1) / CELL_WARPS;
   if (grid > need) grid = need;

@@ -51,7 +51,7 @@ struct PairItem {
   int32_t j0;
   int32_t j1;
   int32_t diag;
-  int32_t pad0, pad1;
+  uint32_t pairs_lo, pairs_hi;  // reference pairs of this item in one frame (64-bit, for statistics)
 };
 static_assert(sizeof(PairItem) == 32, "PairItem must stay 32 bytes");
 
@@ -83,6 +83,10 @@ struct AllPairsParams {
   float box[3];
   uint32_t frame_need_bits;   // nonzero: only frames whose flags have one of these bits
   const unsigned long long* gate;  // non-null: the whole launch is a no-op when *gate == 0
+  unsigned long long* evaluated;   // += reference pairs of the (item, frame) units processed
+  // Item sharding (strong scaling within frames, for fewer frames than GPUs): this launch takes
+  // the units u with u % shard_count == shard_index of the (item, frame) enumeration.
+  uint32_t shard_index, shard_count;
 };
 
 // frame classification of the pack kernels

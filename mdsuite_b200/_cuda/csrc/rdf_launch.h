@@ -71,6 +71,7 @@ struct CellsParams {
   float s_cut, inv_step;
   float box[3];
   uint32_t flush_threshold;   // candidate pairs per CTA between histogram flushes (<= 2^30)
+  uint32_t shard_index, shard_count;  // item sharding: units u with u % shard_count == shard_index
 };
 size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem);
 // pp must have cell_off / rank / grid set: pack + count, scan, scatter into `sorted`

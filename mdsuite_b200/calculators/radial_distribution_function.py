@@ -266,7 +266,11 @@ class RadialDistributionFunction(Calculator):
             devices = list(self.devices)
         else:
             devices = [torch.cuda.current_device() if torch.cuda.is_available() else 0]
-        my_frames = shard_configurations(frames, world, rank)
+        # Frames are the shard unit.  With fewer frames than ranks that would leave GPUs idle, so
+        # every rank then takes ALL frames and a 1/world share of the work items inside them
+        # (mds_rdf_set_item_shard); the allreduce adds the shares up either way.
+        item_shards = dist is not None and len(frames) < world and injected is None
+        my_frames = frames if item_shards else shard_configurations(frames, world, rank)
         shards = np.array_split(my_frames, len(devices))
         box = np.asarray(self.experiment.box_array, dtype=np.float64)
         handles, batchers = [], []
@@ -276,6 +280,8 @@ class RadialDistributionFunction(Calculator):
                 h = factory(particles, self.args.number_of_bins, self.args.cutoff, box,
                             parity=self.parity, device=dev, path=self.kernel_path)
                 handles.append(h)
+                if injected is None:
+                    h.set_item_shard(rank if item_shards else 0, world if item_shards else 1)
                 fpb = self.frames_per_batch
                 if fpb is None:
                     mm = MemoryManager(data_path=paths, database=self.experiment.database, device=dev,

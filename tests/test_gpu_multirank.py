@@ -30,7 +30,8 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 out = os.environ["MDS_OUT"]
 for name, sysm, cutoff, nbins in (
         ("nacl", synthetic.nacl_melt(4, 11, seed=21), 9.0, 90),          # all-pairs kernel, 11 frames
-        ("lj", synthetic.lj_fluid(16, 5, seed=22), 3.0, 300)):          # cell-list kernel, 5 frames
+        ("lj", synthetic.lj_fluid(16, 5, seed=22), 3.0, 300),           # cell-list kernel, 5 frames
+        ("one", synthetic.nacl_melt(5, 1, seed=23), 9.0, 90)):          # 1 frame < 2 ranks: item shards
     project = mds.Project(f"{name}_rank{rank}", storage_path=out)
     exp = project.add_experiment("e")
     exp.add_positions(sysm.positions, sysm.species, sysm.box)
@@ -65,7 +66,8 @@ def test_two_ranks_nccl_calculator(tmp_path):
     from mdsuite_b200 import synthetic
     from oracle import c_oracle, rdf_oracle
     for name, sysm, cutoff, nbins in (("nacl", synthetic.nacl_melt(4, 11, seed=21), 9.0, 90),
-                                      ("lj", synthetic.lj_fluid(16, 5, seed=22), 3.0, 300)):
+                                      ("lj", synthetic.lj_fluid(16, 5, seed=22), 3.0, 300),
+                                      ("one", synthetic.nacl_melt(5, 1, seed=23), 9.0, 90)):
         y0, y1 = np.load(tmp_path / f"{name}_y0.npy"), np.load(tmp_path / f"{name}_y1.npy")
         assert np.array_equal(y0[:, 1:], y1[:, 1:])  # every rank holds the allreduced result
         counts, _ = c_oracle.rdf_counts_c(sysm.positions, sysm.counts, sysm.box, cutoff, nbins,

@@ -276,3 +276,35 @@ def test_committed_golden_vectors(case):
     got, _ = gpu_counts(pos, case["counts"], box, case["cutoff"], case["nbins"], parity=False,
                         layout=_cuda.LAYOUT_ATOM_MAJOR)
     assert_same(got, np.array(case["counts_corrected"], dtype=np.uint64))
+
+
+@pytest.mark.parametrize("path", ["allpairs", "celllist"])
+def test_item_shards_add_up_to_the_full_histogram(path):
+    """mds_rdf_set_item_shard: strong scaling inside frames (fewer frames than GPUs).  The shards
+    of one frame, summed, equal the unsharded histogram and the oracle's; so do their pair counts."""
+    sysm = synthetic.lj_fluid(14, 2, seed=41) if path == "celllist" else synthetic.nacl_melt(6, 2, seed=41)
+    cutoff, nbins = (2.9, 145) if path == "celllist" else (9.0, 300)
+    want, ev = oracle_counts(sysm.positions, sysm.counts, sysm.box, cutoff, nbins)
+    for count in (1, 3, 8):
+        total = np.zeros_like(want)
+        evaluated = equiv = 0.0
+        with _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, path=path) as h:
+            for index in range(count):
+                h.reset()
+                h.set_item_shard(index, count)
+                h.submit(sysm.positions)
+                part = h.counts()
+                st = h.stats()
+                assert st.item_shards == count
+                if count > 1:
+                    assert 0 < part.sum() < want.sum()
+                total += part
+                evaluated += st.pairs_evaluated
+                equiv += st.pairs_allpairs_equiv
+        assert_same(total, want)
+        assert abs(equiv - ev) < 1e-6 * ev
+        if path == "allpairs":
+            assert evaluated == ev
+    with _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, path=path) as h:
+        with pytest.raises(_cuda.MdsCudaError, match="shard 3 of 3"):
+            h.set_item_shard(3, 3)
