@@ -207,6 +207,8 @@ def run_reference(args):
         return 0
     per_step = max(1, min(8, int(60.0 / (4.5 * (args.steps + args.warmup)))))
     sysm, cutoff, nbins, desc = make_workload(args.workload, 0, per_step)
+    # same workload as the GPU arm; a step of this arm is a bounded sample of it (see "sample")
+    desc = desc.replace(f" {per_step} configurations", f" {args.frames} configurations", 1)
     for _ in range(args.warmup):
         cpu_reference_rate(sysm, cutoff, nbins, per_step)
     t0 = time.perf_counter()
@@ -222,7 +224,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": desc},
+        "data": "synthetic",
+        "config": {"workload": desc, "frames_per_gpu": args.frames, "atoms": sysm.n_atoms,
+                   "nbins": nbins, "cutoff": cutoff,
+                   "species_pairs": len(sysm.counts) * (len(sysm.counts) + 1) // 2,
+                   "sample": f"each step times {per_step} configuration(s) of the workload; the "
+                             f"rate is per pair evaluation, so it does not depend on the count"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
