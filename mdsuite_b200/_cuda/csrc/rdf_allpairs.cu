@@ -314,13 +314,14 @@ cudaError_t launch_allpairs(const AllPairsParams& p, int variant, int sm_count,
     case 3: return launch_variant<512, 2, 2>(p, sm_count, stream, grid_out);
     case 4: return launch_variant<512, 4, 2>(p, sm_count, stream, grid_out);
     case 5: return launch_variant<256, 4, 2>(p, sm_count, stream, grid_out);
+    case 6: return launch_variant<256, 4, 4>(p, sm_count, stream, grid_out);
     default: return cudaErrorInvalidValue;
   }
 }
 
 int allpairs_variant_tile(int variant) {
-  static const int tiles[] = {256, 512, 1024, 1024, 2048, 1024};
-  return (variant >= 0 && variant < 6) ? tiles[variant] : -1;
+  static const int tiles[] = {256, 512, 1024, 1024, 2048, 1024, 1024};
+  return (variant >= 0 && variant < 7) ? tiles[variant] : -1;
 }
 
 }  // namespace mds

@@ -619,6 +619,10 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   h->hist_in_smem = true;
   h->pair_group = h->n_pairs;
   while (h->pair_group > 1 && smem_need(h->pair_group) > target) --h->pair_group;
+  if (const char* env = getenv("MDS_RDF_PAIR_GROUP")) {  // tuning aid
+    const int v = atoi(env);
+    if (v >= 1 && v <= h->n_pairs && smem_need(v) <= smem_cap) h->pair_group = v;
+  }
   if (smem_need(h->pair_group) > target) {
     // a single pair does not fit the 2-CTA budget: allow the full opt-in size, then give up on smem
     if (smem_need(1) > smem_cap) {

@@ -15,7 +15,7 @@ size_t allpairs_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem);
 cudaError_t launch_allpairs(const AllPairsParams& p, int variant, int sm_count,
                             cudaStream_t stream, int* grid_out);
 int allpairs_variant_tile(int variant);  // rows per work item of a variant, -1 if unknown
-constexpr int ALLPAIRS_N_VARIANTS = 6;
+constexpr int ALLPAIRS_N_VARIANTS = 7;
 
 // ---- rdf_pack.cu ----
 struct CellGrid {

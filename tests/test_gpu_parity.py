@@ -219,7 +219,7 @@ def test_reset_and_accumulate():
     assert (lib_edges == edges).all() and s_cut == sc
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("dense", [0, 1])
 def test_every_kernel_variant(variant, dense, monkeypatch):
     monkeypatch.setenv("MDS_RDF_VARIANT", str(variant))
