@@ -21,15 +21,37 @@ from mdsuite_b200.database.simulation_database import (PropertyInfo, SpeciesInfo
                                                        TrajectoryChunkData, TrajectoryMetadata)
 from mdsuite_b200.file_io.file_read import FileProcessor
 
-COLUMN_NAMES = {"Positions": ["x", "y", "z"], "Unwrapped_Positions": ["xu", "yu", "zu"],
-                "Velocities": ["vx", "vy", "vz"], "Forces": ["fx", "fy", "fz"]}
+# dump column names of every per-atom property the reference recognises
+# (mdsuite/file_io/lammps_trajectory_files.py:39-64; names from database/mdsuite_properties.py)
+COLUMN_NAMES = {
+    "Positions": ["x", "y", "z"],
+    "Scaled_Positions": ["xs", "ys", "zs"],
+    "Unwrapped_Positions": ["xu", "yu", "zu"],
+    "Scaled_Unwrapped_Positions": ["xsu", "ysu", "zsu"],
+    "Velocities": ["vx", "vy", "vz"],
+    "Forces": ["fx", "fy", "fz"],
+    "Box_Images": ["ix", "iy", "iz"],
+    "Dipole_Orientation_Magnitude": ["mux", "muy", "muz"],
+    "Angular_Velocity_Spherical": ["omegax", "omegay", "omegaz"],
+    "Angular_Velocity_Non_Spherical": ["angmomx", "angmomy", "angmomz"],
+    "Torque": ["tqx", "tqy", "tqz"],
+    "Charge": ["q"],
+    "Kinetic_Energy": ["c_KE"],
+    "Potential_Energy": ["c_PE"],
+    "Stress": ["c_Stress[1]", "c_Stress[2]", "c_Stress[3]", "c_Stress[4]", "c_Stress[5]",
+               "c_Stress[6]"],
+}
 
 
 class LAMMPSTrajectoryFile(FileProcessor):
     def __init__(self, file_path, trajectory_is_sorted_by_ids: bool = False,
-                 chunk_bytes: int = 256 << 20, n_threads: int = 0):
+                 custom_data_map: dict = None, chunk_bytes: int = 256 << 20, n_threads: int = 0):
+        """``custom_data_map`` maps further property names to dump columns, e.g.
+        {"Reduced_Momentum": ["rp_x", "rp_y", "rp_z"]} (reference :80-90)."""
         self.file_path = str(pathlib.Path(file_path))
         self.trajectory_is_sorted_by_ids = trajectory_is_sorted_by_ids
+        self.column_names = dict(COLUMN_NAMES)
+        self.column_names.update(custom_data_map or {})
         self.chunk_bytes = chunk_bytes
         self.n_threads = n_threads
         self._mdata = None
@@ -62,7 +84,7 @@ class LAMMPSTrajectoryFile(FileProcessor):
         for i, name in enumerate(labels):
             species.setdefault(name, []).append(i)
         props = {}
-        for prop, names in COLUMN_NAMES.items():
+        for prop, names in self.column_names.items():
             if all(n in columns for n in names):
                 props[prop] = [columns.index(n) for n in names]
         box_l = [hi - lo for lo, hi in zip(info.box_lo, info.box_hi)]

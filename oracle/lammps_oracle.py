@@ -25,8 +25,18 @@ from mdsuite_b200.database.simulation_database import (PropertyInfo, SpeciesInfo
 from mdsuite_b200.file_io.file_read import FileProcessor
 
 N_HEADER_LINES = 9
-COLUMN_NAMES = {"Positions": ["x", "y", "z"], "Unwrapped_Positions": ["xu", "yu", "zu"],
-                "Velocities": ["vx", "vy", "vz"], "Forces": ["fx", "fy", "fz"]}
+# reference mdsuite/file_io/lammps_trajectory_files.py:39-64
+COLUMN_NAMES = {
+    "Positions": ["x", "y", "z"], "Scaled_Positions": ["xs", "ys", "zs"],
+    "Unwrapped_Positions": ["xu", "yu", "zu"], "Scaled_Unwrapped_Positions": ["xsu", "ysu", "zsu"],
+    "Velocities": ["vx", "vy", "vz"], "Forces": ["fx", "fy", "fz"], "Box_Images": ["ix", "iy", "iz"],
+    "Dipole_Orientation_Magnitude": ["mux", "muy", "muz"],
+    "Angular_Velocity_Spherical": ["omegax", "omegay", "omegaz"],
+    "Angular_Velocity_Non_Spherical": ["angmomx", "angmomy", "angmomz"],
+    "Torque": ["tqx", "tqy", "tqz"], "Charge": ["q"], "Kinetic_Energy": ["c_KE"],
+    "Potential_Energy": ["c_PE"],
+    "Stress": ["c_Stress[%d]" % k for k in range(1, 7)],
+}
 
 
 class LAMMPSTrajectoryFileOracle(FileProcessor):

@@ -178,3 +178,26 @@ def test_cfg1_dump_roundtrip_through_the_native_reader(tmp_path):
     got = np.concatenate([np.concatenate([c.data["Na"]["Positions"], c.data["Cl"]["Positions"]], 1)
                           for c in chunks])
     assert np.array_equal(got.view(np.uint32), sysm.positions.view(np.uint32))
+
+
+def test_every_reference_property_and_custom_columns(tmp_path):
+    """The reference's column-name table (positions in four flavours, velocities, forces, charge,
+    per-atom energies, stress ...) plus a custom_data_map entry."""
+    path = tmp_path / "props.lammpstraj"
+    cols = ["id", "type", "x", "y", "z", "xu", "yu", "zu", "q", "c_KE", "c_Stress[1]", "c_Stress[2]",
+            "c_Stress[3]", "c_Stress[4]", "c_Stress[5]", "c_Stress[6]", "rp_x", "rp_y", "rp_z"]
+    rows = []
+    for i in (2, 1, 3):
+        rows.append(" ".join([str(i), "1"] + ["%d.%d" % (i, k) for k in range(len(cols) - 2)]))
+    frame = ("ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n3\nITEM: BOX BOUNDS pp pp pp\n0 5\n0 5\n0 5\n"
+             "ITEM: ATOMS " + " ".join(cols) + "\n" + "\n".join(rows) + "\n")
+    path.write_text(frame)
+    proc = LAMMPSTrajectoryFile(str(path), custom_data_map={"Reduced_Momentum": ["rp_x", "rp_y", "rp_z"]})
+    props = {p.name: p.n_dims for p in proc.metadata.species_list[0].properties}
+    assert props == {"Positions": 3, "Unwrapped_Positions": 3, "Charge": 1, "Kinetic_Energy": 1,
+                     "Stress": 6, "Reduced_Momentum": 3}
+    chunk = next(iter(proc.get_configurations_generator()))
+    data = chunk.data["1"]
+    assert data["Charge"][0, :, 0].tolist() == [np.float32(1.6), np.float32(2.6), np.float32(3.6)]
+    assert data["Stress"].shape == (1, 3, 6)
+    assert data["Reduced_Momentum"][0, 2].tolist() == [np.float32(3.14), np.float32(3.15), np.float32(3.16)]
