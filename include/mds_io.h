@@ -1,5 +1,6 @@
 /*
- * mds_io.h — C ABI of the native trajectory ingestion (host code, no CUDA).
+ * mds_io.h — C ABI of the native trajectory ingestion (host code, no CUDA): LAMMPS text dumps and
+ * extended XYZ files.
  *
  * Replaces the pure-Python text parsing of the reference on the way INTO the trajectory store
  * (SURVEY.md §8f rank 2):
@@ -9,6 +10,8 @@
  *                                                        split n_particles lines, sort by the id
  *                                                        column (utils/meta_functions.py:519-527),
  *                                                        slice property columns
+ *   mdsuite/file_io/extxyz_files.py:93-121               extended XYZ: atom count + key=value line
+ *                                                        per configuration, atoms in file order
  * The reference turns every token into float64 (NumPy's correctly rounded string conversion) and
  * stores float32 (h5py dataset dtype, database/simulation_database.py:491-497); this library
  * returns float32((double) token) — the same two roundings.
@@ -24,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MDS_IO_ABI_VERSION 1
+#define MDS_IO_ABI_VERSION 2
 
 #if defined(MDS_BUILD) && defined(__GNUC__)
 #define MDS_IO_API __attribute__((visibility("default")))
@@ -57,10 +60,21 @@ typedef struct mds_dump_info {
 /* mmap the dump, read the first header and index the configurations with n_threads threads
  * (<= 0: hardware concurrency). */
 MDS_IO_API int mds_dump_open(mds_dump_t** out, const char* path, int n_threads);
+/* Same for an extended XYZ file (2 header lines per configuration: the atom count and the
+ * key=value line).  The handle serves every mds_dump_* call below; in its info n_columns is the
+ * token count of the first atom line (columns are named "c0", "c1", ...), id_column and
+ * species_column are -1 and the timestep / box fields are 0: Lattice, Properties and time live on
+ * the key=value line, which the caller reads with mds_dump_header_line(h, frame, 1, ...). */
+MDS_IO_API int mds_xyz_open(mds_dump_t** out, const char* path, int n_threads);
 MDS_IO_API void mds_dump_close(mds_dump_t* h);
 MDS_IO_API int mds_dump_info_get(mds_dump_t* h, mds_dump_info* out);
 /* name of per-atom column idx into buf (NUL terminated, truncated to buf_len) */
 MDS_IO_API int mds_dump_column_name(mds_dump_t* h, int idx, char* buf, int buf_len);
+/* Header line `line` (0-based; 9 per configuration in a LAMMPS dump, 2 in an extended XYZ file) of
+ * configuration `frame`, without its line end, NUL terminated and truncated to buf_len - 1 bytes.
+ * Returns the full length of the line (>= 0), or a negative status. */
+MDS_IO_API int64_t mds_dump_header_line(mds_dump_t* h, int64_t frame, int line, char* buf,
+                                        int64_t buf_len);
 /* Labels of column `column` for the first configuration, atoms in ascending id order (file
  * order if sort_by_id == 0): n_atoms NUL-terminated strings at stride label_stride bytes. */
 MDS_IO_API int mds_dump_first_frame_labels(mds_dump_t* h, int column, int sort_by_id, char* buf,

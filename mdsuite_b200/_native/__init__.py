@@ -17,10 +17,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmds_io.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTED_SYMBOLS = (
-    "mds_dump_open", "mds_dump_close", "mds_dump_info_get", "mds_dump_column_name",
+    "mds_dump_open", "mds_xyz_open", "mds_dump_header_line", "mds_dump_close", "mds_dump_info_get", "mds_dump_column_name",
     "mds_dump_first_frame_labels", "mds_dump_read_columns", "mds_dump_read_columns_mapped",
     "mds_parse_float32",
     "mds_io_last_error", "mds_io_abi_version",
@@ -71,6 +71,9 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(LIB_PATH)
     vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
     lib.mds_dump_open.argtypes = [ctypes.POINTER(vp), ctypes.c_char_p, ctypes.c_int]
+    lib.mds_xyz_open.argtypes = [ctypes.POINTER(vp), ctypes.c_char_p, ctypes.c_int]
+    lib.mds_dump_header_line.argtypes = [vp, i64, ctypes.c_int, ctypes.c_char_p, i64]
+    lib.mds_dump_header_line.restype = i64
     lib.mds_dump_close.argtypes = [vp]
     lib.mds_dump_close.restype = None
     lib.mds_dump_info_get.argtypes = [vp, ctypes.POINTER(_DumpInfo)]
@@ -111,12 +114,13 @@ class LammpsDump:
     """An mmap'ed LAMMPS text dump with an index of its configurations."""
 
     LABEL_STRIDE = 32
+    _OPEN = "mds_dump_open"
 
     def __init__(self, path: str, n_threads: int = 0):
         self._lib = load()
         self._h = ctypes.c_void_p()
-        _check(self._lib.mds_dump_open(ctypes.byref(self._h), os.fsencode(path), int(n_threads)),
-               "mds_dump_open")
+        _check(getattr(self._lib, self._OPEN)(ctypes.byref(self._h), os.fsencode(path),
+                                              int(n_threads)), self._OPEN)
         raw = _DumpInfo()
         raw.struct_size = ctypes.sizeof(_DumpInfo)
         _check(self._lib.mds_dump_info_get(self._h, ctypes.byref(raw)), "mds_dump_info_get")
@@ -145,6 +149,18 @@ class LammpsDump:
 
     def __exit__(self, *exc):
         self.close()
+
+    def header_line(self, frame: int, line: int) -> str:
+        """Header line ``line`` (0-based) of configuration ``frame``, without the line end."""
+        size = 4096
+        while True:
+            buf = ctypes.create_string_buffer(size)
+            n = self._lib.mds_dump_header_line(self._h, int(frame), int(line), buf, size)
+            if n < 0:
+                _check(int(n), "mds_dump_header_line")
+            if n < size:
+                return buf.value.decode()
+            size = int(n) + 1
 
     def first_frame_labels(self, column: int, sort_by_id: bool = True) -> List[str]:
         n = self.info.n_atoms
@@ -178,6 +194,13 @@ class LammpsDump:
                                                       dest_ptr, out.ctypes.data),
                "mds_dump_read_columns")
         return out
+
+
+class XyzDump(LammpsDump):
+    """An mmap'ed extended XYZ file; same calls as LammpsDump, atoms always in file order
+    (``sort_by_id=False``), the key=value line of a configuration is ``header_line(frame, 1)``."""
+
+    _OPEN = "mds_xyz_open"
 
 
 def parse_float32(tokens: Sequence[str]) -> np.ndarray:

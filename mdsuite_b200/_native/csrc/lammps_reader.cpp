@@ -1,10 +1,14 @@
-// Native LAMMPS text-dump reader behind include/mds_io.h: mmap, multi-threaded configuration
-// index (newline scan), multi-threaded tokenise + exact decimal -> float32((double) token).
+// Native tabular-text trajectory reader behind include/mds_io.h (LAMMPS text dumps and extended
+// XYZ files): mmap, multi-threaded configuration index (newline scan), multi-threaded tokenise +
+// exact decimal -> float32((double) token).
 //
 // Follows the reference's reader semantics (mdsuite/file_io/lammps_trajectory_files.py:103-146,
 // mdsuite/file_io/tabular_text_files.py:160-220): 9 header lines per configuration, n_atoms data
 // lines split on whitespace, atoms ordered by the numeric value of the `id` column
 // (utils/meta_functions.py:519-527), every kept token converted string -> float64 -> float32.
+// Extended XYZ (mdsuite/file_io/extxyz_files.py:93-121): 2 header lines per configuration (atom
+// count, key=value line), atoms kept in file order; the key=value line is handed to the caller
+// (mds_dump_header_line), who owns the Lattice / Properties / time conventions.
 #include <algorithm>
 #include <atomic>
 #include <cerrno>
@@ -41,7 +45,8 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-constexpr int N_HEADER = 9;
+constexpr int N_HEADER_LAMMPS = 9;
+constexpr int N_HEADER_XYZ = 2;
 
 inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\f' || c == '\v'; }
 
@@ -188,6 +193,7 @@ struct mds_dump {
   const char* data = nullptr;
   size_t size = 0;
   int n_threads = 1;
+  int n_header = N_HEADER_LAMMPS;  // header lines in front of the atom lines of every configuration
   mds_dump_info info;
   std::vector<std::string> columns;
   std::vector<size_t> frame_off;  // byte offset of every configuration, + file size at the end
@@ -218,8 +224,8 @@ std::string line_at(const char* p, const char* end) {
 int read_header(mds_dump* h) {
   const char* p = h->data;
   const char* end = h->data + h->size;
-  std::string lines[N_HEADER];
-  for (int i = 0; i < N_HEADER; ++i) {
+  std::string lines[N_HEADER_LAMMPS];
+  for (int i = 0; i < N_HEADER_LAMMPS; ++i) {
     if (p >= end) return fail(MDS_IO_ERR_FORMAT, "file ends inside the first header");
     lines[i] = line_at(p, end);
     p = next_line(p, end);
@@ -259,12 +265,45 @@ int read_header(mds_dump* h) {
   return MDS_IO_OK;
 }
 
+// extended XYZ: line 1 is the atom count, line 2 the key=value comment; the number of columns is
+// the token count of the first atom line (they carry no names in the file)
+int read_header_xyz(mds_dump* h) {
+  const char* p = h->data;
+  const char* end = h->data + h->size;
+  const std::string first = line_at(p, end);
+  {
+    const char* tb[2];
+    const char* te[2];
+    const int n = split_line(first.data(), first.data() + first.size(), tb, te, 2);
+    char* endp = nullptr;
+    const long long v = n == 1 ? strtoll(first.c_str(), &endp, 10) : -1;
+    if (n != 1 || v < 0 || (endp && *endp && !is_space(*endp)))
+      return fail(MDS_IO_ERR_FORMAT, "first line of an extended XYZ file must be the atom count, got '%s'",
+                  first.substr(0, 60).c_str());
+    h->info.n_atoms = v;
+  }
+  p = next_line(p, end);
+  if (p >= end) return fail(MDS_IO_ERR_FORMAT, "file ends inside the first header");
+  p = next_line(p, end);
+  h->info.n_columns = 0;
+  if (h->info.n_atoms > 0) {
+    if (p >= end) return fail(MDS_IO_ERR_FORMAT, "file ends before the first atom line");
+    const std::string l = line_at(p, end);
+    h->info.n_columns = split_line(l.data(), l.data() + l.size(), nullptr, nullptr, 0);
+    if (h->info.n_columns < 1) return fail(MDS_IO_ERR_FORMAT, "the first atom line is empty");
+  }
+  for (int i = 0; i < h->info.n_columns; ++i) h->columns.emplace_back("c" + std::to_string(i));
+  h->info.id_column = -1;
+  h->info.species_column = -1;
+  return MDS_IO_OK;
+}
+
 // configuration offsets: count newlines per slab in parallel, then place every
-// (n_atoms + 9)-th line start
+// (n_atoms + n_header)-th line start
 int index_frames(mds_dump* h) {
   const size_t size = h->size;
   const char* data = h->data;
-  const int64_t lpf = h->info.n_atoms + N_HEADER;
+  const int64_t lpf = h->info.n_atoms + h->n_header;
   const int slabs = std::max(1, std::min<int>(h->n_threads * 4, (int)(size / (1 << 20)) + 1));
   std::vector<size_t> lo((size_t)slabs + 1);
   for (int s = 0; s <= slabs; ++s) lo[(size_t)s] = size * (size_t)s / (size_t)slabs;
@@ -324,7 +363,7 @@ int parse_frame(const mds_dump* h, int64_t frame, const int32_t* columns, int n_
   const int64_t n = h->info.n_atoms;
   const char* p = h->data + h->frame_off[(size_t)frame];
   const char* end = h->data + h->frame_off[(size_t)frame + 1];
-  for (int i = 0; i < N_HEADER; ++i) p = next_line(p, end);
+  for (int i = 0; i < h->n_header; ++i) p = next_line(p, end);
   const int n_file_cols = h->info.n_columns;
   const int idc = h->info.id_column;
   const bool staged = sort_by_id || dest != nullptr;  // rows do not land in file order
@@ -425,13 +464,14 @@ extern "C" {
 const char* mds_io_last_error(void) { return g_err.c_str(); }
 int mds_io_abi_version(void) { return MDS_IO_ABI_VERSION; }
 
-int mds_dump_open(mds_dump_t** out, const char* path, int n_threads) {
+static int open_common(mds_dump_t** out, const char* path, int n_threads, bool xyz) {
   if (!out || !path) return fail(MDS_IO_ERR_INVALID, "mds_dump_open: NULL argument");
   *out = nullptr;
   mds_dump* h = new (std::nothrow) mds_dump();
   if (!h) return fail(MDS_IO_ERR_NOMEM, "mds_dump_open: out of memory");
   memset(&h->info, 0, sizeof(h->info));
   h->info.struct_size = sizeof(mds_dump_info);
+  h->n_header = xyz ? N_HEADER_XYZ : N_HEADER_LAMMPS;
   h->n_threads = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   h->fd = open(path, O_RDONLY);
   if (h->fd < 0) {
@@ -457,9 +497,9 @@ int mds_dump_open(mds_dump_t** out, const char* path, int n_threads) {
   }
   madvise(m, h->size, MADV_SEQUENTIAL);
   h->data = (const char*)m;
-  int rc = read_header(h);
+  int rc = xyz ? read_header_xyz(h) : read_header(h);
   if (rc == MDS_IO_OK) rc = index_frames(h);
-  if (rc == MDS_IO_OK) {
+  if (rc == MDS_IO_OK && !xyz) {
     h->info.timestep1 = h->info.timestep0;
     if (h->info.n_configurations > 1) {
       const char* p = h->data + h->frame_off[1];
@@ -474,6 +514,34 @@ int mds_dump_open(mds_dump_t** out, const char* path, int n_threads) {
   }
   *out = h;
   return MDS_IO_OK;
+}
+
+int mds_dump_open(mds_dump_t** out, const char* path, int n_threads) {
+  return open_common(out, path, n_threads, false);
+}
+
+int mds_xyz_open(mds_dump_t** out, const char* path, int n_threads) {
+  return open_common(out, path, n_threads, true);
+}
+
+int64_t mds_dump_header_line(mds_dump_t* h, int64_t frame, int line, char* buf, int64_t buf_len) {
+  if (!h || !buf || buf_len < 1) return fail(MDS_IO_ERR_INVALID, "mds_dump_header_line: bad argument");
+  if (frame < 0 || frame >= h->info.n_configurations)
+    return fail(MDS_IO_ERR_INVALID, "mds_dump_header_line: configuration %lld of %lld",
+                (long long)frame, (long long)h->info.n_configurations);
+  if (line < 0 || line >= h->n_header)
+    return fail(MDS_IO_ERR_INVALID, "mds_dump_header_line: line %d of %d", line, h->n_header);
+  const char* p = h->data + h->frame_off[(size_t)frame];
+  const char* end = h->data + h->frame_off[(size_t)frame + 1];
+  for (int i = 0; i < line; ++i) p = next_line(p, end);
+  const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+  const char* e = nl ? nl : end;
+  if (e > p && e[-1] == '\r') --e;
+  const int64_t len = (int64_t)(e - p);
+  const int64_t n = std::min<int64_t>(len, buf_len - 1);
+  memcpy(buf, p, (size_t)n);
+  buf[n] = 0;
+  return len;
 }
 
 void mds_dump_close(mds_dump_t* h) {
@@ -512,7 +580,7 @@ int mds_dump_first_frame_labels(mds_dump_t* h, int column, int sort_by_id, char*
   const int64_t n = h->info.n_atoms;
   const char* p = h->data + h->frame_off[0];
   const char* end = h->data + h->frame_off[1];
-  for (int i = 0; i < N_HEADER; ++i) p = next_line(p, end);
+  for (int i = 0; i < h->n_header; ++i) p = next_line(p, end);
   const int nc = h->info.n_columns;
   std::vector<const char*> tb((size_t)nc), te((size_t)nc);
   std::vector<RowRef> order((size_t)n);

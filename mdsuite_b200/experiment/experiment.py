@@ -22,6 +22,7 @@ from mdsuite_b200.database.simulation_database import (Database, HDF5Database, P
 from mdsuite_b200.experiment.run import RunComputation
 from mdsuite_b200.file_io.file_read import FileProcessor
 from mdsuite_b200.file_io.lammps_trajectory_files import LAMMPSTrajectoryFile
+from mdsuite_b200.file_io.extxyz_files import EXTXYZFile
 from mdsuite_b200.file_io.script_input import ScriptInput
 from mdsuite_b200.utils.units import Units, resolve_units
 
@@ -36,8 +37,10 @@ def _get_processor(simulation_data) -> FileProcessor:
         suffix = pathlib.Path(simulation_data).suffix
         if suffix in (".lammpstraj", ".lammpstrj", ".dump"):
             return LAMMPSTrajectoryFile(simulation_data)
+        if suffix == ".extxyz":
+            return EXTXYZFile(simulation_data)
         raise ValueError(f"datafile ending '{suffix}' not recognized; pass a FileProcessor "
-                         f"(LAMMPS dumps use .lammpstraj)")
+                         f"(LAMMPS dumps use .lammpstraj, extended XYZ files .extxyz)")
     raise ValueError(f"simulation_data of type {type(simulation_data)} not supported")
 
 

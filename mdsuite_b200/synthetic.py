@@ -150,3 +150,25 @@ def write_lammps_dump(system: SyntheticSystem, path: str, timestep_stride: int =
             p = system.positions[f]
             fh.write("".join("%d %s %.9g %.9g %.9g\n" % (i + 1, names[i], p[i, 0], p[i, 1], p[i, 2])
                              for i in range(system.n_atoms)))
+
+
+def write_extxyz(system: SyntheticSystem, path: str, time_stride: float = 1.0,
+                 interleave: bool = True) -> None:
+    """Extended XYZ file with ``species pos`` columns — what the reference's EXTXYZFile reads
+    (file_io/extxyz_files.py:93-181).  ``interleave`` mixes the species along the file (the reader
+    has to gather them); positions are written with 9 significant digits (float32 round trip)."""
+    names = []
+    for name, count in system.species.items():
+        names += [name] * count
+    order = np.arange(system.n_atoms)
+    if interleave:
+        order = np.random.Generator(np.random.Philox(17)).permutation(system.n_atoms)
+    lattice = "%.9g 0.0 0.0 0.0 %.9g 0.0 0.0 0.0 %.9g" % tuple(system.box)
+    with open(path, "w") as fh:
+        for f in range(system.n_frames):
+            fh.write("%d\n" % system.n_atoms)
+            fh.write('Lattice="%s" Properties=species:S:1:pos:R:3 time=%.9g pbc="T T T"\n'
+                     % (lattice, f * time_stride))
+            p = system.positions[f]
+            fh.write("".join("%s %.9g %.9g %.9g\n" % (names[i], p[i, 0], p[i, 1], p[i, 2])
+                             for i in order))

@@ -4,9 +4,10 @@ TEST INFRASTRUCTURE ONLY — pure-Python restatement of the reference's LAMMPS t
 the checker for the native reader behind include/mds_io.h (mdsuite_b200/_native).  Never imported
 by the product.
 
-PARITY UNPINNED beyond the format itself: the reference's reader cannot be imported here (its
-package needs tensorflow/h5py), and its tests read downloaded files; the golden check for this
-path is tests/golden/lammps_golden.* (a dump written by hand in the documented LAMMPS format).
+Pinned: tests/test_reader_golden.py holds this restatement to the output of the reference's own
+LAMMPSTrajectoryFile (tests/golden/reader_golden.json, made by tests/golden/make_reader_golden.py,
+which executes the reference's reader modules unmodified); tests/golden/lammps_golden.json is an
+additional hand-computed vector.
 
 Same conventions as the reference: 9 header lines per configuration, box lengths from header
 lines 5-7, the ``id`` column sorts the atoms of every configuration, species come from the
