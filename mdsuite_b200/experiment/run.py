@@ -1,8 +1,9 @@
 """``experiment.run`` / ``project.run`` (reference mdsuite/experiment/run.py:58-243): one property
-per calculator; in this package's scope are the RDF and the calculators that
-consume its output (§8f rank 3)."""
+per calculator; in this package's scope are the RDF, the calculators that consume
+its output (§8f rank 3) and the angular distribution function (§8f rank 4)."""
 from __future__ import annotations
 
+from mdsuite_b200.calculators.angular_distribution_function import AngularDistributionFunction
 from mdsuite_b200.calculators.coordination_number_calculation import CoordinationNumbers
 from mdsuite_b200.calculators.kirkwood_buff_integrals import KirkwoodBuffIntegral
 from mdsuite_b200.calculators.potential_of_mean_force import PotentialOfMeanForce
@@ -19,6 +20,11 @@ class RunComputation:
     def RadialDistributionFunction(self) -> RadialDistributionFunction:
         """reference run.py:228-230."""
         return RadialDistributionFunction(**self.kwargs)
+
+    @property
+    def AngularDistributionFunction(self) -> AngularDistributionFunction:
+        """reference run.py:164-166."""
+        return AngularDistributionFunction(**self.kwargs)
 
     @property
     def CoordinationNumbers(self) -> CoordinationNumbers:

@@ -1,0 +1,165 @@
+"""GPU parity of the ADF path, through the C ABI (include/mds_adf.h): per-configuration weight sums
+against the NumPy oracle.  With norm_power = 0 the sums are counts and must be IDENTICAL (same
+neighbours under the float16 cutoff, same bin for every triple); with weights the kernel adds
+float32 terms in another order than NumPy: tolerance 2e-6 of the row maximum, written below."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import adf_oracle
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+WEIGHT_TOL = 2e-6
+
+
+def _adf():
+    from mdsuite_b200._cuda import adf as cuda_adf
+    return cuda_adf
+
+
+def uniform(seed, counts, frames, box, unwrapped=False):
+    rng = np.random.Generator(np.random.Philox(seed))
+    box = np.asarray(box, dtype=np.float64)
+    pos = rng.random((frames, sum(counts), 3)) * box
+    if unwrapped:
+        pos += rng.integers(-3, 4, size=pos.shape) * box
+    return pos.astype(np.float32)
+
+
+def oracle_raw(pos, counts, box, cutoff, nbins, power):
+    return np.stack([adf_oracle.raw_histograms(f, counts, box, cutoff, nbins, power) for f in pos])
+
+
+def check(pos, counts, box, cutoff, nbins, power, **kw):
+    with _adf().ADFHandle(counts, nbins, cutoff, box, norm_power=power, **kw) as h:
+        got = h.compute(pos)
+        st = h.stats()
+    want = oracle_raw(pos, counts, box, cutoff, nbins, power)
+    assert got.shape == want.shape
+    if power == 0:
+        assert np.array_equal(got, want), f"{int(np.sum(got != want))} bins differ"
+        assert st.triples == want.sum()
+    else:
+        scale = np.maximum(want.max(axis=-1, keepdims=True), 1e-300)
+        assert np.max(np.abs(got - want) / scale) <= WEIGHT_TOL
+    return got, st
+
+
+CASES = [
+    dict(id="two_species", counts=[40, 30], box=[9.0, 9.0, 9.0], cutoff=3.5, nbins=50, frames=3),
+    dict(id="three_species_noncubic", counts=[25, 31, 17], box=[7.0, 9.5, 8.25], cutoff=3.0,
+         nbins=36, frames=2),
+    dict(id="single_species_cutoff_not_float16", counts=[97], box=[8.0, 8.0, 8.0], cutoff=3.2,
+         nbins=100, frames=4),
+    dict(id="unwrapped", counts=[33, 20], box=[8.0, 8.0, 8.0], cutoff=3.2, nbins=64, frames=3,
+         unwrapped=True),
+    dict(id="ragged_species", counts=[1, 0, 50, 2], box=[7.0, 7.0, 7.0], cutoff=2.9, nbins=40,
+         frames=2),
+    dict(id="cutoff_beyond_half_box", counts=[20, 12], box=[5.0, 5.0, 5.0], cutoff=4.0, nbins=30,
+         frames=2),
+    dict(id="many_bins", counts=[60], box=[9.0, 9.0, 9.0], cutoff=3.4, nbins=3000, frames=2),
+    dict(id="one_bin", counts=[30, 30], box=[9.0, 9.0, 9.0], cutoff=3.4, nbins=1, frames=1),
+    dict(id="more_atoms_than_an_item", counts=[150, 143], box=[14.0, 14.0, 14.0], cutoff=3.3,
+         nbins=90, frames=2),
+]
+
+
+@pytest.mark.parametrize("power", [0, 4])
+@pytest.mark.parametrize("case", CASES, ids=[c["id"] for c in CASES])
+def test_weight_sums_equal_the_oracle(case, power):
+    pos = uniform(11 + len(case["id"]), case["counts"], case["frames"], case["box"],
+                  case.get("unwrapped", False))
+    check(pos, case["counts"], case["box"], case["cutoff"], case["nbins"], power)
+
+
+@pytest.mark.parametrize("power", [1, 2, 7])
+def test_other_powers(power):
+    pos = uniform(5, [30, 20], 2, [8.0, 8.0, 8.0])
+    check(pos, [30, 20], [8.0, 8.0, 8.0], 3.3, 45, power)
+
+
+def test_reference_run_cases_through_the_calculator_arithmetic():
+    """The positions of the reference-run fixtures: counts identical to the restatement that the
+    fixtures pin."""
+    with open(os.path.join(HERE, "golden", "adf_golden.json")) as fh:
+        cases = json.load(fh)["cases"]
+    for case in cases:
+        rng = np.random.Generator(np.random.Philox(case["seed"]))
+        box = np.asarray(case["box"], dtype=np.float64)
+        pos = rng.random((case["frames"], sum(case["counts"]), 3)) * box
+        if case.get("unwrapped"):
+            pos += rng.integers(-2, 3, size=pos.shape) * box
+        check(pos.astype(np.float32), case["counts"], case["box"], case["cutoff"], case["nbins"], 0)
+
+
+def test_coincident_nan_and_far_atoms():
+    """Two atoms on the same point (norm 0: float16 zero, not neighbours), a NaN atom and an atom at
+    1e30 take part in no triple; everything else is untouched."""
+    counts, box = [30, 24], [8.0, 8.0, 8.0]
+    pos = uniform(21, counts, 2, box)
+    pos[0, 5] = pos[0, 4]
+    pos[0, 40] = np.nan
+    pos[1, 7] = [1e30, 0.0, 0.0]
+    pos[1, 8] = [np.inf, 1.0, 2.0]
+    with np.errstate(all="ignore"):
+        check(pos, counts, box, 3.2, 48, 0)
+
+
+def test_frames_are_independent_and_batched():
+    counts, box = [48], [8.0, 8.0, 8.0]
+    pos = uniform(31, counts, 9, box)
+    got, _ = check(pos, counts, box, 3.1, 32, 0, max_frames_in_flight=4)
+    with _adf().ADFHandle(counts, 32, 3.1, box, norm_power=0) as h:
+        single = np.stack([h.compute(pos[k:k + 1])[0] for k in range(len(pos))])
+        assert h.stats().frames == len(pos)
+    assert np.array_equal(single, got)
+
+
+def test_device_entry_point_equals_host_entry_point():
+    import torch
+    counts, box = [35, 29], [8.0, 8.0, 8.0]
+    pos = uniform(41, counts, 3, box)
+    with _adf().ADFHandle(counts, 40, 3.3, box, norm_power=4) as h:
+        host = h.compute(pos)
+        dev = h.compute_device(torch.from_numpy(pos).cuda())
+        torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), host) or \
+        np.max(np.abs(dev.cpu().numpy() - host)) <= WEIGHT_TOL * host.max()
+
+
+def test_too_many_neighbours_is_an_error_not_a_wrong_answer():
+    cuda_adf, cuda = _adf(), __import__("mdsuite_b200._cuda", fromlist=["x"])
+    counts, box = [700], [6.0, 6.0, 6.0]
+    pos = uniform(51, counts, 1, box)
+    with cuda_adf.ADFHandle(counts, 20, 5.9, box, norm_power=0) as h:
+        with pytest.raises(cuda.MdsCudaError, match="neighbours"):
+            h.compute(pos)
+
+
+def test_dense_liquid_at_scale_properties():
+    """4 096 atoms: totals against the triple count from an independent neighbour count, symmetry
+    of the same-species rows (every unordered pair is two triples: even counts)."""
+    counts, box = [2048, 2048], [36.0, 36.0, 36.0]
+    pos = uniform(61, counts, 2, box)
+    with _adf().ADFHandle(counts, 180, 4.0, box, norm_power=0) as h:
+        got = h.compute(pos)
+        st = h.stats()
+    s_lo, s_hi = _adf().neighbour_window(4.0)
+    species = np.repeat([0, 1], counts)
+    for f in range(2):
+        r = adf_oracle.min_image_vectors(pos[f], box)
+        sq = r * r
+        s = (sq[..., 0] + sq[..., 1]) + sq[..., 2]
+        nb = (s >= s_lo) & (s < s_hi)
+        n0 = (nb & (species[None, :] == 0)).sum(1)
+        n1 = (nb & (species[None, :] == 1)).sum(1)
+        c0, c1 = species == 0, species == 1
+        want = [np.sum(n0[c0] * (n0[c0] - 1)), np.sum(n0[c0] * n1[c0]),
+                np.sum(n1[c0] * (n1[c0] - 1)), np.sum(n1[c1] * (n1[c1] - 1))]
+        assert got[f].sum(axis=1).tolist() == [float(w) for w in want]
+    assert np.all(got[:, [0, 2, 3]] % 2 == 0)
+    assert st.triples == got.sum() and st.max_neighbours < 64
