@@ -46,7 +46,7 @@ extern "C" {
 #define MDS_ADF_ERR_NOMEM (-3)
 #define MDS_ADF_ERR_UNSUPPORTED (-4)
 
-#define MDS_ADF_MAX_NEIGHBOURS 512 /* neighbours of one atom that can take part in a triple */
+#define MDS_ADF_MAX_NEIGHBOURS 1024 /* neighbours of one atom that can take part in a triple */
 #define MDS_ADF_RANGE_HI 3.15      /* upper edge of the angle axis, "a chemist's pi" (:215) */
 
 typedef struct mds_adf_config {
@@ -66,12 +66,18 @@ typedef struct mds_adf_stats {
   int32_t n_combinations;   /* S (S + 1) (S + 2) / 6 */
   int64_t frames;           /* configurations processed since create */
   double triples;           /* ordered (i, j, k) triples binned since create */
-  double pair_tests;        /* (i, j) distance tests of the neighbour search since create */
+  double pair_tests;        /* (i, j) distance tests of the neighbour search since create, counted
+                               on the device */
   int64_t kernel_launches;
   float kernel_ms;          /* device time of the kernels of the LAST compute call (CUDA events) */
   float compute_ms;         /* device time of the whole LAST compute call incl. copies */
   int32_t max_neighbours;   /* largest neighbour list seen since create */
   int32_t sm_count;
+  int32_t cells[3];         /* cells per dimension of the neighbour search (0: every atom is tested
+                               against every atom — small boxes, few atoms) */
+  int32_t reserved;
+  int64_t frames_far;       /* cell search: configurations with a coordinate beyond 8 box lengths,
+                               which were searched atom against atom instead */
 } mds_adf_stats;
 
 typedef struct mds_adf mds_adf_t;

@@ -17,7 +17,7 @@ from mdsuite_b200 import _cuda
 from mdsuite_b200._cuda import MdsCudaError
 
 ABI_VERSION = 1
-MAX_NEIGHBOURS = 512
+MAX_NEIGHBOURS = 1024
 RANGE_HI = 3.15
 
 EXPORTED_SYMBOLS = (
@@ -53,6 +53,9 @@ class _Stats(ctypes.Structure):
         ("compute_ms", ctypes.c_float),
         ("max_neighbours", ctypes.c_int32),
         ("sm_count", ctypes.c_int32),
+        ("cells", ctypes.c_int32 * 3),
+        ("reserved", ctypes.c_int32),
+        ("frames_far", ctypes.c_int64),
     ]
 
 
@@ -67,6 +70,8 @@ class ADFStats:
     compute_ms: float
     max_neighbours: int
     sm_count: int
+    cells: tuple = (0, 0, 0)
+    frames_far: int = 0
 
 
 _declared = False
@@ -194,4 +199,5 @@ class ADFHandle:
         _check(self._lib.mds_adf_stats_get(self._h, ctypes.byref(raw)), "mds_adf_stats_get")
         return ADFStats(int(raw.n_combinations), int(raw.frames), float(raw.triples),
                         float(raw.pair_tests), int(raw.kernel_launches), float(raw.kernel_ms),
-                        float(raw.compute_ms), int(raw.max_neighbours), int(raw.sm_count))
+                        float(raw.compute_ms), int(raw.max_neighbours), int(raw.sm_count),
+                        tuple(int(c) for c in raw.cells), int(raw.frames_far))

@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "mds_adf.h"
+#include "rdf_common.cuh"
 
 namespace {
 
@@ -54,7 +55,8 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int ADF_WARPS = 8;
 constexpr int ADF_THREADS = ADF_WARPS * 32;
-constexpr int MAX_NB = MDS_ADF_MAX_NEIGHBOURS;
+constexpr int MAX_NB_LIMIT = MDS_ADF_MAX_NEIGHBOURS;
+constexpr int N_SPANS = 18;  // 9 cell rows x up to 2 pieces where the x window wraps
 constexpr int CENTRES_PER_ITEM = 128;
 constexpr int MAX_SPECIES = 8;
 
@@ -142,8 +144,20 @@ int neighbour_window_norm(float cutoff, float* n_lo, float* n_hi) {
 
 // ---- device -----------------------------------------------------------------------------------
 
+struct AdfGrid {
+  int nx, ny, nz, nc;  // cells per dimension (each >= 3), nc = nx * ny * nz
+  float box[3];
+};
+
 struct AdfParams {
   const float* pos;         // [F][N][3]
+  const float4* sorted;     // [F][N] (x, y, z, species bits), atoms ordered by cell (cell path)
+  const uint32_t* cell_off; // [F][nc + 1] first sorted slot of every cell (cell path)
+  const uint32_t* frame_flags;  // [F] != 0: a coordinate beyond 8 box lengths (cell path declines)
+  unsigned long long* pair_tests;
+  AdfGrid grid;
+  int only_flagged;         // all-atoms form: process the flagged configurations only
+  int max_nb;               // capacity of a warp's neighbour list
   const uint8_t* species;   // [N]
   const float* cos_edges;   // [nbins + 1]
   double* out;              // [F][combos][nbins]
@@ -167,13 +181,94 @@ __device__ __forceinline__ float min_image(float d, float box) {
   return __fsub_rn(d, __fmul_rn(rintf(q), box));
 }
 
-__global__ void __launch_bounds__(ADF_THREADS, 2) adf_kernel(const AdfParams p) {
+// Test atom j (position pj, species sp_j) against centre i and append it to the warp's neighbour
+// list: unit vector, norm, species.  Warp-collective (ballot); `valid` masks lanes without an atom.
+__device__ __forceinline__ void consider(bool valid, float xi, float yi, float zi, float xj, float yj,
+                                         float zj, int sp_i, int sp_j, const AdfParams& p,
+                                         float4* my_vec, uint8_t* my_sp, int& m, int lane) {
+  bool is_nb = false;
+  float dx = 0.f, dy = 0.f, dz = 0.f, s = 0.f;
+  if (valid) {
+    dx = min_image(__fsub_rn(xi, xj), p.box[0]);
+    dy = min_image(__fsub_rn(yi, yj), p.box[1]);
+    dz = min_image(__fsub_rn(zi, zj), p.box[2]);
+    s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    is_nb = (s >= p.s_lo) && (s < p.s_hi) && (sp_j >= sp_i);
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, is_nb);
+  if (is_nb) {
+    const int slot = m + __popc(ballot & ((1u << lane) - 1u));
+    if (slot < p.max_nb) {
+      const float n = __fsqrt_rn(s);
+      my_vec[slot] = make_float4(__fdiv_rn(dx, n), __fdiv_rn(dy, n), __fdiv_rn(dz, n), n);
+      my_sp[slot] = (uint8_t)sp_j;
+    }
+  }
+  m += __popc(ballot);
+}
+
+// acos(c) to ~7e-5 rad (Abramowitz & Stegun 4.4.45) — only the GUESS of the bin; the table decides
+__device__ __forceinline__ float acos_guess(float c) {
+  const float ax = fabsf(c);
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f - ax));
+  const float poly = ((-0.0187293f * ax + 0.0742610f) * ax - 0.2121144f) * ax + 1.5707288f;
+  const float t = r * poly;
+  return c < 0.0f ? 3.14159265f - t : t;
+}
+
+// Every unordered pair (a, b), a < b, of the neighbour list, flattened over the lanes: row a holds
+// b = a + 1 .. m - 1; a lane walks positions lane, lane + 32, ... of the concatenated rows.
+__device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t* my_sp, int m,
+                                            int sp_i, const AdfParams& p, float* hist,
+                                            const float* edges, const int8_t* s_combo, int lane,
+                                            unsigned long long& my_triples) {
+  int a = 0, q = lane, len = m - 1;  // q: position inside row a, len: length of row a
+  while (len > 0 && q >= len) { q -= len; ++a; --len; }
+  while (len > 0) {
+    const int b = a + 1 + q;
+    const float4 va = my_vec[a];
+    const float4 vb = my_vec[b];
+    const int sa = my_sp[a], sb = my_sp[b];
+    float c = __fadd_rn(__fadd_rn(__fmul_rn(va.x, vb.x), __fmul_rn(va.y, vb.y)),
+                        __fmul_rn(va.z, vb.z));
+    c = fminf(fmaxf(c, -1.0f), 1.0f);
+    int g = (int)(acos_guess(c) * p.bin_scale);
+    g = max(0, min(g, p.nbins - 1));
+    while (g < p.nbins - 1 && c <= edges[g + 1]) ++g;
+    while (g > 0 && c > edges[g]) --g;
+    const int lo = min(sa, sb), hi = max(sa, sb);
+    const int combo = s_combo[(sp_i * MAX_SPECIES + lo) * MAX_SPECIES + hi];
+    float w = (sa == sb) ? 2.0f : 1.0f;
+    my_triples += (sa == sb) ? 2ull : 1ull;
+    if (p.norm_power > 0) {
+      const float pr = __fmul_rn(va.w, vb.w);
+      float pw = pr;
+      for (int e = 1; e < p.norm_power; ++e) pw = __fmul_rn(pw, pr);
+      w = __fmul_rn(w, __frcp_rn(pw));
+    }
+    atomicAdd(&hist[combo * p.nbins + g], w);
+    q += 32;
+    while (len > 0 && q >= len) { q -= len; ++a; --len; }
+  }
+}
+
+// CELLS = false: every atom of the configuration is tested against the centre (any input; the
+//   frames flagged in p.frame_flags only, if p.only_flagged).
+// CELLS = true: the configuration was counting-sorted into cells of width >= 1.002 x the largest
+//   norm that can pass the float16 test (x fastest), and only the 27 cells around the centre are
+//   searched; frames with a coordinate beyond 8 box lengths are flagged and left to the other form
+//   (the cell-assignment error bound of DESIGN.md §9 needs |x| <= 8 L).
+template <bool CELLS>
+__global__ void __launch_bounds__(ADF_THREADS, 3) adf_kernel(const AdfParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* nb_vec = reinterpret_cast<float4*>(smem_raw);                    // [WARPS][MAX_NB]
-  uint8_t* nb_sp = reinterpret_cast<uint8_t*>(nb_vec + ADF_WARPS * MAX_NB);  // [WARPS][MAX_NB]
-  float* hist = reinterpret_cast<float*>(nb_sp + ADF_WARPS * MAX_NB);       // [combos][nbins]
-  float* edges = hist + p.n_combos * p.nbins;                               // [nbins + 1]
+  float4* nb_vec = reinterpret_cast<float4*>(smem_raw);                       // [WARPS][max_nb]
+  uint8_t* nb_sp = reinterpret_cast<uint8_t*>(nb_vec + ADF_WARPS * p.max_nb);  // [WARPS][max_nb]
+  float* hist = reinterpret_cast<float*>(nb_sp + ADF_WARPS * p.max_nb);        // [combos][nbins]
+  float* edges = hist + p.n_combos * p.nbins;                                  // [nbins + 1]
   __shared__ unsigned long long s_item;
+  __shared__ int s_span_end[ADF_WARPS][N_SPANS + 1];  // running end of every span in the flattened list
+  __shared__ int s_span_adj[ADF_WARPS][N_SPANS];      // sorted slot = flattened index + adj
   __shared__ int8_t s_combo[MAX_SPECIES * MAX_SPECIES * MAX_SPECIES];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -182,10 +277,10 @@ __global__ void __launch_bounds__(ADF_THREADS, 2) adf_kernel(const AdfParams p) 
   for (int k = tid; k <= p.nbins; k += ADF_THREADS) edges[k] = p.cos_edges[k];
   for (int k = tid; k < MAX_SPECIES * MAX_SPECIES * MAX_SPECIES; k += ADF_THREADS)
     s_combo[k] = p.combo_of[k];
-  float4* my_vec = nb_vec + warp * MAX_NB;
-  uint8_t* my_sp = nb_sp + warp * MAX_NB;
+  float4* my_vec = nb_vec + warp * p.max_nb;
+  uint8_t* my_sp = nb_sp + warp * p.max_nb;
   const unsigned long long n_items = (unsigned long long)p.n_frames * p.items_per_frame;
-  unsigned long long my_triples = 0;
+  unsigned long long my_triples = 0, my_tests = 0;
   int my_max_nb = 0;
 
   for (;;) {
@@ -195,72 +290,96 @@ __global__ void __launch_bounds__(ADF_THREADS, 2) adf_kernel(const AdfParams p) 
     const unsigned long long item = s_item;
     if (item >= n_items) break;
     const int frame = (int)(item / p.items_per_frame);
+    const bool flagged = p.frame_flags != nullptr && p.frame_flags[frame] != 0u;
+    if (CELLS ? flagged : (p.only_flagged && !flagged)) continue;
     const int c0 = (int)(item % p.items_per_frame) * CENTRES_PER_ITEM;
     const int c1 = min(p.n_atoms, c0 + CENTRES_PER_ITEM);
-    const float* fpos = p.pos + (size_t)frame * p.n_atoms * 3;
 
     for (int i = c0 + warp; i < c1; i += ADF_WARPS) {
-      const float xi = __ldg(fpos + 3 * i), yi = __ldg(fpos + 3 * i + 1), zi = __ldg(fpos + 3 * i + 2);
-      const int sp_i = p.species[i];
-      // ---- neighbour search: every atom of the configuration against centre i ----
-      int m = 0;
-      for (int j0 = 0; j0 < p.n_atoms; j0 += 32) {
-        const int j = j0 + lane;
-        bool is_nb = false;
-        float dx = 0.f, dy = 0.f, dz = 0.f, s = 0.f;
-        int sp_j = 0;
-        if (j < p.n_atoms) {
-          dx = min_image(__fsub_rn(xi, __ldg(fpos + 3 * j)), p.box[0]);
-          dy = min_image(__fsub_rn(yi, __ldg(fpos + 3 * j + 1)), p.box[1]);
-          dz = min_image(__fsub_rn(zi, __ldg(fpos + 3 * j + 2)), p.box[2]);
-          s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-          sp_j = p.species[j];
-          is_nb = (s >= p.s_lo) && (s < p.s_hi) && (sp_j >= sp_i);
-        }
-        const unsigned ballot = __ballot_sync(0xffffffffu, is_nb);
-        if (is_nb) {
-          const int slot = m + __popc(ballot & ((1u << lane) - 1u));
-          if (slot < MAX_NB) {
-            const float n = __fsqrt_rn(s);
-            my_vec[slot] = make_float4(__fdiv_rn(dx, n), __fdiv_rn(dy, n), __fdiv_rn(dz, n), n);
-            my_sp[slot] = (uint8_t)sp_j;
+      int m = 0, sp_i;
+      if (CELLS) {
+        const float4* sorted = p.sorted + (size_t)frame * p.n_atoms;
+        const uint32_t* off = p.cell_off + (size_t)frame * (p.grid.nc + 1);
+        const float4 ci = __ldg(sorted + i);
+        sp_i = __float_as_int(ci.w);
+        const int cx = mds::cell_coord(ci.x, p.grid.box[0], p.grid.nx);
+        const int cy = mds::cell_coord(ci.y, p.grid.box[1], p.grid.ny);
+        const int cz = mds::cell_coord(ci.z, p.grid.box[2], p.grid.nz);
+        // The x window [cx - 1, cx + 1] of a cell row is one contiguous span of the sorted array, or
+        // two where it wraps around the box: 18 spans at most.  Lane s < 18 fetches the bounds of
+        // span s (one round trip for all of them); the spans are then walked as ONE flattened
+        // list, 32 candidates per step, so that the loads of a centre are independent.
+        int len = 0, begin = 0;
+        if (lane < N_SPANS) {
+          const int r = lane >> 1, part = lane & 1;
+          int z = cz + r / 3 - 1, y = cy + r % 3 - 1;
+          z += (z < 0) ? p.grid.nz : 0;
+          z -= (z >= p.grid.nz) ? p.grid.nz : 0;
+          y += (y < 0) ? p.grid.ny : 0;
+          y -= (y >= p.grid.ny) ? p.grid.ny : 0;
+          int x0, x1;
+          if (part == 0) { x0 = max(cx - 1, 0); x1 = min(cx + 1, p.grid.nx - 1); }
+          else if (cx == 0) { x0 = x1 = p.grid.nx - 1; }
+          else if (cx == p.grid.nx - 1) { x0 = x1 = 0; }
+          else { x0 = 0; x1 = -1; }
+          if (x1 >= x0) {
+            const int row = (z * p.grid.ny + y) * p.grid.nx;
+            begin = (int)__ldg(off + row + x0);
+            len = (int)__ldg(off + row + x1 + 1) - begin;
           }
         }
-        m += __popc(ballot);
+        int incl = len;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane < N_SPANS) {
+          s_span_end[warp][lane] = incl;
+          s_span_adj[warp][lane] = begin - (incl - len);
+        }
+        if (lane == 0) s_span_end[warp][N_SPANS] = 0x7fffffff;
+        __syncwarp();
+        my_tests += (unsigned long long)total;
+        int span = 0;
+        for (int t0 = 0; t0 < total; t0 += 32) {
+          const int t = t0 + lane;
+          const bool valid = t < total;
+          float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) {
+            while (t >= s_span_end[warp][span]) ++span;
+            pj = __ldg(sorted + t + s_span_adj[warp][span]);
+          }
+          consider(valid, ci.x, ci.y, ci.z, pj.x, pj.y, pj.z, sp_i, __float_as_int(pj.w), p,
+                   my_vec, my_sp, m, lane);
+        }
+        __syncwarp();
+      } else {
+        const float* fpos = p.pos + (size_t)frame * p.n_atoms * 3;
+        const float xi = __ldg(fpos + 3 * i), yi = __ldg(fpos + 3 * i + 1), zi = __ldg(fpos + 3 * i + 2);
+        sp_i = p.species[i];
+        my_tests += (unsigned long long)p.n_atoms;
+        for (int j0 = 0; j0 < p.n_atoms; j0 += 32) {
+          const int j = j0 + lane;
+          const bool valid = j < p.n_atoms;
+          float xj = 0.f, yj = 0.f, zj = 0.f;
+          int sp_j = 0;
+          if (valid) {
+            xj = __ldg(fpos + 3 * j);
+            yj = __ldg(fpos + 3 * j + 1);
+            zj = __ldg(fpos + 3 * j + 2);
+            sp_j = p.species[j];
+          }
+          consider(valid, xi, yi, zi, xj, yj, zj, sp_i, sp_j, p, my_vec, my_sp, m, lane);
+        }
       }
-      if (m > MAX_NB) {
+      if (m > p.max_nb) {
         if (lane == 0) atomicExch(p.status, 1);
-        m = MAX_NB;
+        m = p.max_nb;
       }
       my_max_nb = max(my_max_nb, m);
       __syncwarp();
-      // ---- triples: every unordered pair (j, k) of the neighbour list ----
-      for (int a = 0; a + 1 < m; ++a) {
-        const float4 va = my_vec[a];
-        const int sa = my_sp[a];
-        for (int b = a + 1 + lane; b < m; b += 32) {
-          const float4 vb = my_vec[b];
-          const int sb = my_sp[b];
-          float c = __fadd_rn(__fadd_rn(__fmul_rn(va.x, vb.x), __fmul_rn(va.y, vb.y)),
-                              __fmul_rn(va.z, vb.z));
-          c = fminf(fmaxf(c, -1.0f), 1.0f);
-          int g = (int)(acosf(c) * p.bin_scale);
-          g = max(0, min(g, p.nbins - 1));
-          while (g < p.nbins - 1 && c <= edges[g + 1]) ++g;
-          while (g > 0 && c > edges[g]) --g;
-          const int lo = min(sa, sb), hi = max(sa, sb);
-          const int combo = s_combo[(sp_i * MAX_SPECIES + lo) * MAX_SPECIES + hi];
-          float w = (sa == sb) ? 2.0f : 1.0f;
-          my_triples += (sa == sb) ? 2ull : 1ull;
-          if (p.norm_power > 0) {
-            const float pr = __fmul_rn(va.w, vb.w);
-            float pw = pr;
-            for (int e = 1; e < p.norm_power; ++e) pw = __fmul_rn(pw, pr);
-            w = __fmul_rn(w, __fdiv_rn(1.0f, pw));
-          }
-          atomicAdd(&hist[combo * p.nbins + g], w);
-        }
-      }
+      bin_triples(my_vec, my_sp, m, sp_i, p, hist, edges, s_combo, lane, my_triples);
       __syncwarp();
     }
     // ---- flush this item's sums into the configuration's histogram ----
@@ -280,7 +399,69 @@ __global__ void __launch_bounds__(ADF_THREADS, 2) adf_kernel(const AdfParams p) 
   }
   if (lane == 0) {
     if (my_triples) atomicAdd(p.triples, my_triples);
+    if (my_tests) atomicAdd(p.pair_tests, my_tests);
     atomicMax(p.status + 1, my_max_nb);
+  }
+}
+
+// ---- cell build: count + rank, scan, scatter (one configuration = one segment) ----------------
+
+__global__ void adf_cell_count_kernel(const float* __restrict__ pos, int n_atoms, int n_frames,
+                                      AdfGrid g, uint32_t* __restrict__ cell_cnt,
+                                      uint32_t* __restrict__ cell_id, uint32_t* __restrict__ rank,
+                                      uint32_t* __restrict__ frame_flags) {
+  const size_t total = (size_t)n_atoms * n_frames;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(idx / n_atoms);
+    const float x = pos[3 * idx], y = pos[3 * idx + 1], z = pos[3 * idx + 2];
+    if (fabsf(x) > 8.0f * g.box[0] || fabsf(y) > 8.0f * g.box[1] || fabsf(z) > 8.0f * g.box[2])
+      frame_flags[f] = 1u;
+    const int c = mds::cell_of(x, y, z, g);
+    cell_id[idx] = (uint32_t)c;
+    rank[idx] = atomicAdd(cell_cnt + (size_t)f * (g.nc + 1) + c, 1u);
+  }
+}
+
+// one CTA per configuration: counts[0 .. nc] -> exclusive offsets, offsets[nc] = n_atoms
+__global__ void __launch_bounds__(256) adf_cell_scan_kernel(uint32_t* __restrict__ cell_cnt, int nc) {
+  __shared__ uint32_t s_part[256];
+  uint32_t* c = cell_cnt + (size_t)blockIdx.x * (nc + 1);
+  const int n = nc + 1;
+  const int per = (n + 255) / 256;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  uint32_t sum = 0;
+  for (int k = lo; k < hi; ++k) sum += c[k];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {
+    const uint32_t v = threadIdx.x >= (unsigned)o ? s_part[threadIdx.x - o] : 0u;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = s_part[threadIdx.x] - sum;
+  for (int k = lo; k < hi; ++k) {
+    const uint32_t v = c[k];
+    c[k] = run;
+    run += v;
+  }
+}
+
+__global__ void adf_cell_scatter_kernel(const float* __restrict__ pos,
+                                        const uint8_t* __restrict__ species, int n_atoms,
+                                        int n_frames, int nc, const uint32_t* __restrict__ cell_off,
+                                        const uint32_t* __restrict__ cell_id,
+                                        const uint32_t* __restrict__ rank,
+                                        float4* __restrict__ sorted) {
+  const size_t total = (size_t)n_atoms * n_frames;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t f = idx / n_atoms;
+    const int a = (int)(idx - f * n_atoms);
+    const uint32_t slot = cell_off[f * (nc + 1) + cell_id[idx]] + rank[idx];
+    sorted[f * n_atoms + slot] = make_float4(pos[3 * idx], pos[3 * idx + 1], pos[3 * idx + 2],
+                                             __int_as_float((int)species[a]));
   }
 }
 
@@ -303,6 +484,10 @@ struct mds_adf {
   AdfParams base;
   size_t smem_bytes = 0;
   int grid = 0;
+  bool use_cells = false;
+  AdfGrid cells;
+  int max_nb = 0;          // capacity of a warp's neighbour list in the current configuration
+  size_t smem_limit = 0;
   // device
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
@@ -310,8 +495,15 @@ struct mds_adf {
   double* d_out = nullptr;
   uint8_t* d_species = nullptr;
   float* d_edges = nullptr;
-  unsigned long long* d_counters = nullptr;  // [0] work counter, [1] triples
+  unsigned long long* d_counters = nullptr;  // [0] work counter, [1] triples, [2] pair tests
   int* d_status = nullptr;
+  float4* d_sorted = nullptr;     // cell path: [batch][N]
+  uint32_t* d_cell_off = nullptr; // [batch][nc + 1]
+  uint32_t* d_cell_id = nullptr;  // [batch][N]
+  uint32_t* d_rank = nullptr;     // [batch][N]
+  uint32_t* d_flags = nullptr;    // [batch]
+  std::vector<uint32_t> h_flags;
+  int64_t frames_far = 0;
   // statistics
   int64_t frames = 0, launches = 0;
   double triples = 0, pair_tests = 0;
@@ -321,37 +513,121 @@ struct mds_adf {
 
 namespace {
 
-int run_batch(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) {
+size_t smem_for(const mds_adf* h, int max_nb) {
+  return (size_t)ADF_WARPS * (size_t)max_nb * (sizeof(float4) + 1) +
+         sizeof(float) * ((size_t)h->n_combos * h->nbins + h->nbins + 1);
+}
+
+// shared-memory layout, launch attributes and grid for a neighbour-list capacity
+int configure(mds_adf* h, int max_nb) {
+  const size_t bytes = smem_for(h, max_nb);
+  if (bytes > h->smem_limit)
+    return fail(MDS_ADF_ERR_UNSUPPORTED,
+                "%d combinations x %d bins with %d neighbours per atom need %zu bytes of shared "
+                "memory (limit %zu)", h->n_combos, h->nbins, max_nb, bytes, h->smem_limit);
+  // the attribute belongs to the function, not to the handle: always allow the device maximum
+  if (cudaFuncSetAttribute(adf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)h->smem_limit) != cudaSuccess ||
+      cudaFuncSetAttribute(adf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)h->smem_limit) != cudaSuccess)
+    return fail(MDS_ADF_ERR_CUDA, "cudaFuncSetAttribute failed: %s",
+                cudaGetErrorString(cudaGetLastError()));
+  int per_sm = 0, per_sm_b = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adf_kernel<true>, ADF_THREADS, bytes) !=
+          cudaSuccess || per_sm < 1 ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, adf_kernel<false>, ADF_THREADS,
+                                                    bytes) != cudaSuccess || per_sm_b < 1)
+    return fail(MDS_ADF_ERR_CUDA, "the ADF kernel does not fit on an SM");
+  h->max_nb = max_nb;
+  h->smem_bytes = bytes;
+  h->grid = std::min(per_sm, per_sm_b) * h->sm_count;
+  h->base.max_nb = max_nb;
+  return MDS_ADF_OK;
+}
+
+constexpr int ADF_OVERFLOW = 1;  // run_batch_once: a neighbour list did not fit
+
+int run_batch_once(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) {
   const size_t out_bytes = (size_t)n_frames * h->n_combos * h->nbins * sizeof(double);
   ADF_CUDA_TRY(cudaMemsetAsync(d_out, 0, out_bytes, h->stream));
-  ADF_CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, 2 * sizeof(unsigned long long), h->stream));
+  ADF_CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, 3 * sizeof(unsigned long long), h->stream));
   AdfParams p = h->base;
   p.pos = d_xyz;
   p.out = d_out;
   p.n_frames = n_frames;
   const unsigned long long items = (unsigned long long)n_frames * p.items_per_frame;
-  const int grid = (int)std::min<unsigned long long>((unsigned long long)h->grid, items);
-  adf_kernel<<<std::max(grid, 1), ADF_THREADS, h->smem_bytes, h->stream>>>(p);
-  ADF_CUDA_TRY(cudaGetLastError());
-  h->launches += 1;
-  unsigned long long counters[2];
+  const int grid = std::max(1, (int)std::min<unsigned long long>((unsigned long long)h->grid, items));
+  if (h->use_cells) {
+    const size_t total = (size_t)n_frames * (size_t)h->n_atoms;
+    const int nc = h->cells.nc;
+    ADF_CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, sizeof(uint32_t) * (size_t)n_frames, h->stream));
+    ADF_CUDA_TRY(cudaMemsetAsync(h->d_cell_off, 0, sizeof(uint32_t) * (size_t)n_frames * (nc + 1),
+                                 h->stream));
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 16);
+    adf_cell_count_kernel<<<blocks, 256, 0, h->stream>>>(d_xyz, (int)h->n_atoms, n_frames, h->cells,
+                                                         h->d_cell_off, h->d_cell_id, h->d_rank,
+                                                         h->d_flags);
+    adf_cell_scan_kernel<<<n_frames, 256, 0, h->stream>>>(h->d_cell_off, nc);
+    adf_cell_scatter_kernel<<<blocks, 256, 0, h->stream>>>(d_xyz, h->d_species, (int)h->n_atoms,
+                                                           n_frames, nc, h->d_cell_off,
+                                                           h->d_cell_id, h->d_rank, h->d_sorted);
+    p.sorted = h->d_sorted;
+    p.cell_off = h->d_cell_off;
+    p.frame_flags = h->d_flags;
+    p.grid = h->cells;
+    adf_kernel<true><<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
+    ADF_CUDA_TRY(cudaGetLastError());
+    h->launches += 4;
+    h->h_flags.resize((size_t)n_frames);
+    ADF_CUDA_TRY(cudaMemcpyAsync(h->h_flags.data(), h->d_flags, sizeof(uint32_t) * (size_t)n_frames,
+                                 cudaMemcpyDeviceToHost, h->stream));
+    ADF_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int64_t far = 0;
+    for (int f = 0; f < n_frames; ++f) far += h->h_flags[(size_t)f] != 0u;
+    if (far) {  // configurations with a coordinate beyond 8 box lengths: all-atoms search
+      h->frames_far += far;
+      ADF_CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long), h->stream));
+      p.only_flagged = 1;
+      adf_kernel<false><<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
+      ADF_CUDA_TRY(cudaGetLastError());
+      h->launches += 1;
+    }
+  } else {
+    adf_kernel<false><<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
+    ADF_CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+  }
+  unsigned long long counters[3];
   int status[2];
   ADF_CUDA_TRY(cudaMemcpyAsync(counters, h->d_counters, sizeof(counters), cudaMemcpyDeviceToHost,
                                h->stream));
   ADF_CUDA_TRY(cudaMemcpyAsync(status, h->d_status, sizeof(status), cudaMemcpyDeviceToHost,
                                h->stream));
   ADF_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (status[0]) {
+    ADF_CUDA_TRY(cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream));
+    return ADF_OVERFLOW;
+  }
   h->triples += (double)counters[1];
-  h->pair_tests += (double)n_frames * (double)h->n_atoms * (double)h->n_atoms;
+  h->pair_tests += (double)counters[2];
   h->max_neighbours = std::max(h->max_neighbours, status[1]);
   h->frames += n_frames;
-  if (status[0]) {
-    cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream);
-    return fail(MDS_ADF_ERR_UNSUPPORTED,
-                "an atom has more than %d neighbours within the cutoff %g; reduce the cutoff",
-                MAX_NB, (double)h->cutoff);
-  }
   return MDS_ADF_OK;
+}
+
+// A neighbour list that does not fit makes the batch invalid: double the capacity (fewer CTAs per
+// SM from then on) and run the batch again, up to MDS_ADF_MAX_NEIGHBOURS.
+int run_batch(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) {
+  for (;;) {
+    const int rc = run_batch_once(h, d_xyz, n_frames, d_out);
+    if (rc != ADF_OVERFLOW) return rc;
+    if (h->max_nb >= MAX_NB_LIMIT)
+      return fail(MDS_ADF_ERR_UNSUPPORTED,
+                  "an atom has more than %d neighbours within the cutoff %g; reduce the cutoff",
+                  MAX_NB_LIMIT, (double)h->cutoff);
+    const int rc2 = configure(h, h->max_nb * 2);
+    if (rc2 != MDS_ADF_OK) return rc2;
+  }
 }
 
 }  // namespace
@@ -434,26 +710,57 @@ int mds_adf_create(mds_adf_t** out, const mds_adf_config* cfg) {
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess)
     return cleanup(fail(MDS_ADF_ERR_CUDA, "cudaGetDeviceProperties failed"));
   h->sm_count = prop.multiProcessorCount;
-  h->smem_bytes = (size_t)ADF_WARPS * MAX_NB * (sizeof(float4) + 1) +
-                  sizeof(float) * ((size_t)h->n_combos * h->nbins + h->nbins + 1);
-  if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
-    return cleanup(fail(MDS_ADF_ERR_UNSUPPORTED,
-                        "%d combinations x %d bins need %zu bytes of shared memory (limit %zu)",
-                        h->n_combos, h->nbins, h->smem_bytes, (size_t)prop.sharedMemPerBlockOptin));
-  if (cudaFuncSetAttribute(adf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)h->smem_bytes) != cudaSuccess)
-    return cleanup(fail(MDS_ADF_ERR_CUDA, "cudaFuncSetAttribute failed: %s",
-                        cudaGetErrorString(cudaGetLastError())));
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adf_kernel, ADF_THREADS,
-                                                    h->smem_bytes) != cudaSuccess || per_sm < 1)
-    return cleanup(fail(MDS_ADF_ERR_CUDA, "the ADF kernel does not fit on an SM"));
-  h->grid = per_sm * h->sm_count;
+  {
+    // dynamic shared memory available to the kernels: the opt-in maximum minus their static part
+    cudaFuncAttributes fa, fb;
+    if (cudaFuncGetAttributes(&fa, adf_kernel<true>) != cudaSuccess ||
+        cudaFuncGetAttributes(&fb, adf_kernel<false>) != cudaSuccess)
+      return cleanup(fail(MDS_ADF_ERR_CUDA, "cudaFuncGetAttributes failed: %s",
+                          cudaGetErrorString(cudaGetLastError())));
+    h->smem_limit = (size_t)prop.sharedMemPerBlockOptin - std::max(fa.sharedSizeBytes, fb.sharedSizeBytes);
+  }
+  {
+    // capacity of the neighbour lists: 2.5 x the mean number of atoms inside the cutoff sphere
+    // (+ 32), as a power of two in [64, MDS_ADF_MAX_NEIGHBOURS]; doubled on demand (run_batch)
+    const double volume = (double)h->box[0] * h->box[1] * h->box[2];
+    const double expected = (double)n_atoms / volume * 4.18879 * std::pow((double)s_hi, 1.5);
+    int cap = 64;
+    while (cap < MAX_NB_LIMIT && (double)cap < 2.5 * expected + 32.0) cap *= 2;
+    const char* env = getenv("MDS_ADF_NEIGHBOUR_CAPACITY");
+    if (env && atoi(env) >= 32 && atoi(env) <= MAX_NB_LIMIT) cap = atoi(env);
+    while (cap > 64 && smem_for(h, cap) > h->smem_limit) cap /= 2;
+    rc = configure(h, cap);
+    if (rc != MDS_ADF_OK) return cleanup(rc);
+  }
+
+  // Cell grid: width >= 1.002 x the largest norm that passes the float16 test, at most 128 cells
+  // per dimension, at least 3 (otherwise the 27-cell stencil would visit a cell twice); used from
+  // 27 cells and 256 atoms on, and switched off with MDS_ADF_PATH=allatoms (=cells insists).
+  {
+    const double reach = 1.002 * std::sqrt((double)s_hi);
+    int n[3];
+    for (int k = 0; k < 3; ++k) n[k] = (int)std::min(128.0, std::floor((double)h->box[k] / reach));
+    h->use_cells = n[0] >= 3 && n[1] >= 3 && n[2] >= 3 && n_atoms >= 256;
+    const char* env = getenv("MDS_ADF_PATH");
+    if (env && !strcmp(env, "allatoms")) h->use_cells = false;
+    if (env && !strcmp(env, "cells")) {
+      if (n[0] < 3 || n[1] < 3 || n[2] < 3)
+        return cleanup(fail(MDS_ADF_ERR_UNSUPPORTED, "the cell path needs box >= 3.006 x cutoff"));
+      h->use_cells = true;
+    }
+    h->cells.nx = n[0]; h->cells.ny = n[1]; h->cells.nz = n[2];
+    h->cells.nc = h->use_cells ? n[0] * n[1] * n[2] : 0;
+    memcpy(h->cells.box, h->box, sizeof(h->box));
+  }
 
   const size_t frame_bytes = (size_t)n_atoms * 3 * sizeof(float);
   const size_t out_frame_bytes = (size_t)h->n_combos * h->nbins * sizeof(double);
-  int64_t bf = cfg->max_frames_in_flight > 0 ? cfg->max_frames_in_flight
-                                             : (int64_t)((256u << 20) / (frame_bytes + out_frame_bytes));
+  const size_t cell_frame_bytes =
+      h->use_cells ? (size_t)n_atoms * (sizeof(float4) + 8) + sizeof(uint32_t) * ((size_t)h->cells.nc + 2)
+                   : 0;
+  int64_t bf = cfg->max_frames_in_flight > 0
+                   ? cfg->max_frames_in_flight
+                   : (int64_t)((512u << 20) / (frame_bytes + out_frame_bytes + cell_frame_bytes));
   bf = std::max<int64_t>(1, std::min<int64_t>(bf, 4096));
   h->batch_frames = (int)bf;
 
@@ -473,7 +780,14 @@ int mds_adf_create(mds_adf_t** out, const mds_adf_config* cfg) {
   ADF_TRY_CREATE(cudaMalloc(&h->d_out, out_frame_bytes * (size_t)bf));
   ADF_TRY_CREATE(cudaMalloc(&h->d_species, (size_t)n_atoms));
   ADF_TRY_CREATE(cudaMalloc(&h->d_edges, sizeof(float) * ((size_t)h->nbins + 1)));
-  ADF_TRY_CREATE(cudaMalloc(&h->d_counters, 2 * sizeof(unsigned long long)));
+  ADF_TRY_CREATE(cudaMalloc(&h->d_counters, 3 * sizeof(unsigned long long)));
+  if (h->use_cells) {
+    ADF_TRY_CREATE(cudaMalloc(&h->d_sorted, sizeof(float4) * (size_t)n_atoms * (size_t)bf));
+    ADF_TRY_CREATE(cudaMalloc(&h->d_cell_id, sizeof(uint32_t) * (size_t)n_atoms * (size_t)bf));
+    ADF_TRY_CREATE(cudaMalloc(&h->d_rank, sizeof(uint32_t) * (size_t)n_atoms * (size_t)bf));
+    ADF_TRY_CREATE(cudaMalloc(&h->d_cell_off, sizeof(uint32_t) * ((size_t)h->cells.nc + 1) * (size_t)bf));
+    ADF_TRY_CREATE(cudaMalloc(&h->d_flags, sizeof(uint32_t) * (size_t)bf));
+  }
   ADF_TRY_CREATE(cudaMalloc(&h->d_status, 2 * sizeof(int)));
   ADF_TRY_CREATE(cudaMemset(h->d_status, 0, 2 * sizeof(int)));
   {
@@ -493,6 +807,7 @@ int mds_adf_create(mds_adf_t** out, const mds_adf_config* cfg) {
   p.cos_edges = h->d_edges;
   p.work_counter = h->d_counters;
   p.triples = h->d_counters + 1;
+  p.pair_tests = h->d_counters + 2;
   p.status = h->d_status;
   p.n_atoms = (int)n_atoms;
   p.items_per_frame = (int)((n_atoms + CENTRES_PER_ITEM - 1) / CENTRES_PER_ITEM);
@@ -524,6 +839,11 @@ void mds_adf_destroy(mds_adf_t* h) {
   cudaFree(h->d_edges);
   cudaFree(h->d_counters);
   cudaFree(h->d_status);
+  cudaFree(h->d_sorted);
+  cudaFree(h->d_cell_id);
+  cudaFree(h->d_rank);
+  cudaFree(h->d_cell_off);
+  cudaFree(h->d_flags);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_k0) cudaEventDestroy(h->ev_k0);
@@ -572,8 +892,11 @@ int mds_adf_compute_device(mds_adf_t* h, const float* d_xyz, int64_t n_frames, d
   ADF_CUDA_TRY(cudaEventRecord(h->ev0, (cudaStream_t)stream));
   ADF_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev0, 0));
   ADF_CUDA_TRY(cudaEventRecord(h->ev_k0, h->stream));
-  if (n_frames > 0) {
-    const int rc = run_batch(h, d_xyz, (int)n_frames, d_out);
+  const size_t frame_floats = (size_t)h->n_atoms * 3;
+  const size_t out_frame = (size_t)h->n_combos * h->nbins;
+  for (int64_t f0 = 0; f0 < n_frames; f0 += h->batch_frames) {
+    const int nf = (int)std::min<int64_t>(h->batch_frames, n_frames - f0);
+    const int rc = run_batch(h, d_xyz + (size_t)f0 * frame_floats, nf, d_out + (size_t)f0 * out_frame);
     if (rc != MDS_ADF_OK) return rc;
   }
   ADF_CUDA_TRY(cudaEventRecord(h->ev_k1, h->stream));
@@ -597,6 +920,10 @@ int mds_adf_stats_get(mds_adf_t* h, mds_adf_stats* out) {
   out->compute_ms = h->compute_ms;
   out->max_neighbours = h->max_neighbours;
   out->sm_count = h->sm_count;
+  out->cells[0] = h->use_cells ? h->cells.nx : 0;
+  out->cells[1] = h->use_cells ? h->cells.ny : 0;
+  out->cells[2] = h->use_cells ? h->cells.nz : 0;
+  out->frames_far = h->frames_far;
   return MDS_ADF_OK;
 }
 

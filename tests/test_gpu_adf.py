@@ -133,11 +133,24 @@ def test_device_entry_point_equals_host_entry_point():
 
 def test_too_many_neighbours_is_an_error_not_a_wrong_answer():
     cuda_adf, cuda = _adf(), __import__("mdsuite_b200._cuda", fromlist=["x"])
-    counts, box = [700], [6.0, 6.0, 6.0]
+    counts, box = [1300], [6.0, 6.0, 6.0]
     pos = uniform(51, counts, 1, box)
     with cuda_adf.ADFHandle(counts, 20, 5.9, box, norm_power=0) as h:
         with pytest.raises(cuda.MdsCudaError, match="neighbours"):
             h.compute(pos)
+
+
+def test_neighbour_capacity_grows_on_demand(monkeypatch):
+    """Started with room for 32 neighbours per atom, the library doubles the capacity and repeats
+    the batch until the lists fit; the result is the same as with ample room."""
+    counts, box = [90, 70], [8.0, 8.0, 8.0]
+    pos = uniform(53, counts, 3, box)
+    monkeypatch.setenv("MDS_ADF_NEIGHBOUR_CAPACITY", "32")
+    got, st = check(pos, counts, box, 3.9, 48, 0)
+    assert st.max_neighbours > 64 and st.frames == 3
+    monkeypatch.setenv("MDS_ADF_NEIGHBOUR_CAPACITY", "512")
+    with _adf().ADFHandle(counts, 48, 3.9, box, norm_power=0) as h:
+        assert np.array_equal(h.compute(pos), got)
 
 
 def test_dense_liquid_at_scale_properties():
@@ -163,3 +176,89 @@ def test_dense_liquid_at_scale_properties():
         assert got[f].sum(axis=1).tolist() == [float(w) for w in want]
     assert np.all(got[:, [0, 2, 3]] % 2 == 0)
     assert st.triples == got.sum() and st.max_neighbours < 64
+
+
+# ---- cell-list neighbour search ---------------------------------------------------------------
+
+def _compute_with_path(monkeypatch, path, pos, counts, box, cutoff, nbins, power):
+    if path is None:
+        monkeypatch.delenv("MDS_ADF_PATH", raising=False)
+    else:
+        monkeypatch.setenv("MDS_ADF_PATH", path)
+    with _adf().ADFHandle(counts, nbins, cutoff, box, norm_power=power) as h:
+        out = h.compute(pos)
+        return out, h.stats()
+
+
+CELL_CASES = [
+    dict(id="cubic_two_species", counts=[300, 280], box=[16.0, 16.0, 16.0], cutoff=3.3, nbins=90),
+    dict(id="noncubic_three_species", counts=[200, 150, 90], box=[11.0, 17.5, 13.0], cutoff=3.1,
+         nbins=64),
+    dict(id="exactly_three_cells", counts=[400], box=[10.0, 10.0, 10.0], cutoff=3.3, nbins=50),
+    dict(id="unwrapped_within_8_boxes", counts=[260, 100], box=[14.0, 14.0, 14.0], cutoff=3.0,
+         nbins=72, unwrapped=True),
+]
+
+
+@pytest.mark.parametrize("case", CELL_CASES, ids=[c["id"] for c in CELL_CASES])
+def test_cell_search_equals_all_atoms_search_and_oracle(monkeypatch, case):
+    pos = uniform(71 + len(case["id"]), case["counts"], 2, case["box"], case.get("unwrapped", False))
+    # atoms exactly on cell and box boundaries
+    pos[0, 0] = [0.0, 0.0, 0.0]
+    pos[0, 1] = [case["box"][0], case["box"][1], case["box"][2]]
+    pos[0, 2] = [case["box"][0] / 3, case["box"][1] / 3, case["box"][2] / 3]
+    pos[0, 3] = np.nextafter(np.float32(case["box"][0]), np.float32(0))
+    args = (pos, case["counts"], case["box"], case["cutoff"], case["nbins"])
+    cells, st_c = _compute_with_path(monkeypatch, "cells", *args, 0)
+    allatoms, st_a = _compute_with_path(monkeypatch, "allatoms", *args, 0)
+    auto, st_auto = _compute_with_path(monkeypatch, None, *args, 0)
+    assert min(st_c.cells) >= 3 and st_a.cells == (0, 0, 0) and st_auto.cells == st_c.cells
+    # with exactly three cells per dimension the 27-cell stencil is the whole box
+    assert st_c.pair_tests <= st_a.pair_tests == 2 * sum(case["counts"]) ** 2
+    want = oracle_raw(*args, 0)
+    assert np.array_equal(allatoms, want)
+    assert np.array_equal(cells, want)
+    assert np.array_equal(auto, want)
+    weighted, _ = _compute_with_path(monkeypatch, "cells", *args, 4)
+    with np.errstate(all="ignore"):
+        want_w = oracle_raw(*args, 4)
+        # the atom one float below the box edge is ~1e-6 from the atom at the origin: its weights
+        # overflow to inf on both sides
+        assert np.array_equal(np.isinf(weighted), np.isinf(want_w))
+        finite = np.where(np.isinf(want_w), 0.0, want_w)
+        scale = np.maximum(finite.max(axis=-1, keepdims=True), 1e-300)
+        diff = np.where(np.isinf(want_w), 0.0, np.abs(weighted - want_w))
+    assert np.max(diff / scale) <= WEIGHT_TOL
+
+
+def test_cell_search_hands_far_configurations_to_the_all_atoms_search(monkeypatch):
+    counts, box = [300, 212], [15.0, 15.0, 15.0]
+    pos = uniform(81, counts, 4, box)
+    pos[1, 17, 0] += 9 * 15.0       # beyond 8 box lengths: same atom under the minimum image
+    pos[3, 400] = [np.inf, 1.0, 2.0]
+    with np.errstate(all="ignore"):
+        want = oracle_raw(pos, counts, box, 3.2, 60, 0)
+    got, st = _compute_with_path(monkeypatch, "cells", pos, counts, box, 3.2, 60, 0)
+    assert st.frames_far == 2
+    assert np.array_equal(got, want)
+
+
+def test_cell_path_is_refused_for_small_boxes(monkeypatch):
+    cuda = __import__("mdsuite_b200._cuda", fromlist=["x"])
+    monkeypatch.setenv("MDS_ADF_PATH", "cells")
+    with pytest.raises(cuda.MdsCudaError, match="3.006"):
+        _adf().ADFHandle([300], 10, 3.4, [10.0, 10.0, 10.0])
+
+
+def test_clustered_atoms_in_one_cell(monkeypatch):
+    """300 atoms in one cell corner and a dilute background: long neighbour lists next to empty
+    cells."""
+    rng = np.random.Generator(np.random.Philox(91))
+    box = [20.0, 20.0, 20.0]
+    cluster = rng.random((1, 120, 3)) * 3.0 + 1.0
+    rest = rng.random((1, 300, 3)) * 20.0
+    pos = np.concatenate([cluster, rest], axis=1).astype(np.float32)
+    counts = [200, 220]
+    want = oracle_raw(pos, counts, box, 3.0, 40, 0)
+    got, st = _compute_with_path(monkeypatch, "cells", pos, counts, box, 3.0, 40, 0)
+    assert np.array_equal(got, want) and st.max_neighbours > 100
