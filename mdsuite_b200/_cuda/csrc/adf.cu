@@ -220,7 +220,7 @@ __device__ __forceinline__ float acos_guess(float c) {
 // Every unordered pair (a, b), a < b, of the neighbour list, flattened over the lanes: row a holds
 // b = a + 1 .. m - 1; a lane walks positions lane, lane + 32, ... of the concatenated rows.
 __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t* my_sp, int m,
-                                            int sp_i, const AdfParams& p, float* hist,
+                                            int sp_i, const AdfParams& p, double* hist,
                                             const float* edges, const int8_t* s_combo, int lane,
                                             unsigned long long& my_triples) {
   int a = 0, q = lane, len = m - 1;  // q: position inside row a, len: length of row a
@@ -247,7 +247,8 @@ __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t*
       for (int e = 1; e < p.norm_power; ++e) pw = __fmul_rn(pw, pr);
       w = __fmul_rn(w, __frcp_rn(pw));
     }
-    atomicAdd(&hist[combo * p.nbins + g], w);
+    // float64 sums: a float32 bin that holds one large weight would swallow every later small one
+    atomicAdd(&hist[combo * p.nbins + g], (double)w);
     q += 32;
     while (len > 0 && q >= len) { q -= len; ++a; --len; }
   }
@@ -264,8 +265,8 @@ __global__ void __launch_bounds__(ADF_THREADS, 3) adf_kernel(const AdfParams p) 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* nb_vec = reinterpret_cast<float4*>(smem_raw);                       // [WARPS][max_nb]
   uint8_t* nb_sp = reinterpret_cast<uint8_t*>(nb_vec + ADF_WARPS * p.max_nb);  // [WARPS][max_nb]
-  float* hist = reinterpret_cast<float*>(nb_sp + ADF_WARPS * p.max_nb);        // [combos][nbins]
-  float* edges = hist + p.n_combos * p.nbins;                                  // [nbins + 1]
+  double* hist = reinterpret_cast<double*>(nb_sp + ADF_WARPS * p.max_nb);      // [combos][nbins]
+  float* edges = reinterpret_cast<float*>(hist + p.n_combos * p.nbins);        // [nbins + 1]
   __shared__ unsigned long long s_item;
   __shared__ int s_span_end[ADF_WARPS][N_SPANS + 1];  // running end of every span in the flattened list
   __shared__ int s_span_adj[ADF_WARPS][N_SPANS];      // sorted slot = flattened index + adj
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(ADF_THREADS, 3) adf_kernel(const AdfParams p) 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hist_len = p.n_combos * p.nbins;
-  for (int k = tid; k < hist_len; k += ADF_THREADS) hist[k] = 0.0f;
+  for (int k = tid; k < hist_len; k += ADF_THREADS) hist[k] = 0.0;
   for (int k = tid; k <= p.nbins; k += ADF_THREADS) edges[k] = p.cos_edges[k];
   for (int k = tid; k < MAX_SPECIES * MAX_SPECIES * MAX_SPECIES; k += ADF_THREADS)
     s_combo[k] = p.combo_of[k];
@@ -386,10 +387,10 @@ __global__ void __launch_bounds__(ADF_THREADS, 3) adf_kernel(const AdfParams p) 
     __syncthreads();
     double* fout = p.out + (size_t)frame * hist_len;
     for (int k = tid; k < hist_len; k += ADF_THREADS) {
-      const float v = hist[k];
-      if (v != 0.0f) {
-        atomicAdd(fout + k, (double)v);
-        hist[k] = 0.0f;
+      const double v = hist[k];
+      if (v != 0.0) {
+        atomicAdd(fout + k, v);
+        hist[k] = 0.0;
       }
     }
   }
@@ -515,7 +516,7 @@ namespace {
 
 size_t smem_for(const mds_adf* h, int max_nb) {
   return (size_t)ADF_WARPS * (size_t)max_nb * (sizeof(float4) + 1) +
-         sizeof(float) * ((size_t)h->n_combos * h->nbins + h->nbins + 1);
+         sizeof(double) * (size_t)h->n_combos * h->nbins + sizeof(float) * ((size_t)h->nbins + 1);
 }
 
 // shared-memory layout, launch attributes and grid for a neighbour-list capacity
@@ -557,6 +558,7 @@ int run_batch_once(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) 
   p.n_frames = n_frames;
   const unsigned long long items = (unsigned long long)n_frames * p.items_per_frame;
   const int grid = std::max(1, (int)std::min<unsigned long long>((unsigned long long)h->grid, items));
+  int64_t far = 0;
   if (h->use_cells) {
     const size_t total = (size_t)n_frames * (size_t)h->n_atoms;
     const int nc = h->cells.nc;
@@ -582,10 +584,8 @@ int run_batch_once(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) 
     ADF_CUDA_TRY(cudaMemcpyAsync(h->h_flags.data(), h->d_flags, sizeof(uint32_t) * (size_t)n_frames,
                                  cudaMemcpyDeviceToHost, h->stream));
     ADF_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    int64_t far = 0;
     for (int f = 0; f < n_frames; ++f) far += h->h_flags[(size_t)f] != 0u;
     if (far) {  // configurations with a coordinate beyond 8 box lengths: all-atoms search
-      h->frames_far += far;
       ADF_CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long), h->stream));
       p.only_flagged = 1;
       adf_kernel<false><<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
@@ -612,6 +612,7 @@ int run_batch_once(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) 
   h->pair_tests += (double)counters[2];
   h->max_neighbours = std::max(h->max_neighbours, status[1]);
   h->frames += n_frames;
+  h->frames_far += far;
   return MDS_ADF_OK;
 }
 
@@ -803,6 +804,7 @@ int mds_adf_create(mds_adf_t** out, const mds_adf_config* cfg) {
 
   AdfParams& p = h->base;
   memset(&p, 0, sizeof(p));
+  p.max_nb = h->max_nb;
   p.species = h->d_species;
   p.cos_edges = h->d_edges;
   p.work_counter = h->d_counters;

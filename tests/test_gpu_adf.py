@@ -231,7 +231,10 @@ def test_cell_search_equals_all_atoms_search_and_oracle(monkeypatch, case):
     assert np.max(diff / scale) <= WEIGHT_TOL
 
 
-def test_cell_search_hands_far_configurations_to_the_all_atoms_search(monkeypatch):
+@pytest.mark.parametrize("capacity", [None, "32"])
+def test_cell_search_hands_far_configurations_to_the_all_atoms_search(monkeypatch, capacity):
+    if capacity:  # too small for 37 neighbours: the batch is repeated with twice the room
+        monkeypatch.setenv("MDS_ADF_NEIGHBOUR_CAPACITY", capacity)
     counts, box = [300, 212], [15.0, 15.0, 15.0]
     pos = uniform(81, counts, 4, box)
     pos[1, 17, 0] += 9 * 15.0       # beyond 8 box lengths: same atom under the minimum image
