@@ -59,6 +59,10 @@ constexpr int MAX_NB_LIMIT = MDS_ADF_MAX_NEIGHBOURS;
 constexpr int N_SPANS = 18;  // 9 cell rows x up to 2 pieces where the x window wraps
 constexpr int CENTRES_PER_ITEM = 128;
 constexpr int MAX_SPECIES = 8;
+// frame_flags bits written by the cell-count kernel
+constexpr uint32_t ADF_FRAME_FAR = 1u;    // a coordinate beyond 8 box lengths: cell search declines
+constexpr uint32_t ADF_FRAME_OUT_A = 2u;  // a coordinate outside [-L/8, 9L/8]
+constexpr uint32_t ADF_FRAME_OUT_B = 4u;  // a coordinate outside [-5L/8, 5L/8]
 
 // ---- host: threshold tables -------------------------------------------------------------------
 
@@ -181,17 +185,37 @@ __device__ __forceinline__ float min_image(float d, float box) {
   return __fsub_rn(d, __fmul_rn(rintf(q), box));
 }
 
+// Signed minimum image for |d| <= 1.25 box (all coordinates of the configuration inside one of
+// the windows of mds::window_bits): there rint(d / box) is -1, 0 or 1, the reference's result has
+// magnitude min(|d|, box - |d|) bit for bit and it is d itself iff |d| <= box - |d|
+// (box - |d| is exact for |d| >= box / 2), otherwise d -+ box = -+(box - |d|).
+__device__ __forceinline__ float min_image_fast(float d, float box) {
+  const float a = fabsf(d);
+  const float b = __fsub_rn(box, a);
+  return (a <= b) ? d : (d > 0.0f ? -b : b);
+}
+
 // Test atom j (position pj, species sp_j) against centre i and append it to the warp's neighbour
 // list: unit vector, norm, species.  Warp-collective (ballot); `valid` masks lanes without an atom.
+template <bool FAST>
 __device__ __forceinline__ void consider(bool valid, float xi, float yi, float zi, float xj, float yj,
                                          float zj, int sp_i, int sp_j, const AdfParams& p,
                                          float4* my_vec, uint8_t* my_sp, int& m, int lane) {
   bool is_nb = false;
   float dx = 0.f, dy = 0.f, dz = 0.f, s = 0.f;
   if (valid) {
-    dx = min_image(__fsub_rn(xi, xj), p.box[0]);
-    dy = min_image(__fsub_rn(yi, yj), p.box[1]);
-    dz = min_image(__fsub_rn(zi, zj), p.box[2]);
+    dx = __fsub_rn(xi, xj);
+    dy = __fsub_rn(yi, yj);
+    dz = __fsub_rn(zi, zj);
+    if (FAST) {
+      dx = min_image_fast(dx, p.box[0]);
+      dy = min_image_fast(dy, p.box[1]);
+      dz = min_image_fast(dz, p.box[2]);
+    } else {
+      dx = min_image(dx, p.box[0]);
+      dy = min_image(dy, p.box[1]);
+      dz = min_image(dz, p.box[2]);
+    }
     s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
     is_nb = (s >= p.s_lo) && (s < p.s_hi) && (sp_j >= sp_i);
   }
@@ -199,12 +223,20 @@ __device__ __forceinline__ void consider(bool valid, float xi, float yi, float z
   if (is_nb) {
     const int slot = m + __popc(ballot & ((1u << lane) - 1u));
     if (slot < p.max_nb) {
-      const float n = __fsqrt_rn(s);
-      my_vec[slot] = make_float4(__fdiv_rn(dx, n), __fdiv_rn(dy, n), __fdiv_rn(dz, n), n);
+      my_vec[slot] = make_float4(dx, dy, dz, s);  // normalised after the search, all lanes busy
       my_sp[slot] = (uint8_t)sp_j;
     }
   }
   m += __popc(ballot);
+}
+
+// (r, |r|^2) -> (r / |r|, |r|) for the m entries of a neighbour list
+__device__ __forceinline__ void normalise(float4* my_vec, int m, int lane) {
+  for (int k = lane; k < m; k += 32) {
+    const float4 v = my_vec[k];
+    const float n = __fsqrt_rn(v.w);
+    my_vec[k] = make_float4(__fdiv_rn(v.x, n), __fdiv_rn(v.y, n), __fdiv_rn(v.z, n), n);
+  }
 }
 
 // acos(c) to ~7e-5 rad (Abramowitz & Stegun 4.4.45) — only the GUESS of the bin; the table decides
@@ -217,16 +249,23 @@ __device__ __forceinline__ float acos_guess(float c) {
   return c < 0.0f ? 3.14159265f - t : t;
 }
 
-// Every unordered pair (a, b), a < b, of the neighbour list, flattened over the lanes: row a holds
-// b = a + 1 .. m - 1; a lane walks positions lane, lane + 32, ... of the concatenated rows.
+// Every unordered pair (a, b), a < b, of the neighbour list, flattened over the lanes.  Row a holds
+// b = a + 1 .. m - 1 (m - 1 - a entries); rows R and m - 2 - R together hold exactly m entries, so
+// position t of the flattened list is entry c = t % m of combined row R = t / m: the pair
+// (R, R + 1 + c) for c < m - 1 - R, else entry c - (m - 1 - R) of row m - 2 - R.  (For even m the
+// middle row is its own partner; the list ends after its m / 2 entries.)
 __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t* my_sp, int m,
                                             int sp_i, const AdfParams& p, double* hist,
                                             const float* edges, const int8_t* s_combo, int lane,
                                             unsigned long long& my_triples) {
-  int a = 0, q = lane, len = m - 1;  // q: position inside row a, len: length of row a
-  while (len > 0 && q >= len) { q -= len; ++a; --len; }
-  while (len > 0) {
-    const int b = a + 1 + q;
+  const int total = (m * (m - 1)) >> 1;
+  int R = 0, c = lane;
+  for (int t = lane; t < total; t += 32) {
+    while (c >= m) { c -= m; ++R; }
+    const int first = m - 1 - R;  // entries of row R in this combined row
+    const int a = c < first ? R : m - 2 - R;
+    const int b = c < first ? R + 1 + c : a + 1 + (c - first);
+    c += 32;
     const float4 va = my_vec[a];
     const float4 vb = my_vec[b];
     const int sa = my_sp[a], sb = my_sp[b];
@@ -235,8 +274,14 @@ __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t*
     c = fminf(fmaxf(c, -1.0f), 1.0f);
     int g = (int)(acos_guess(c) * p.bin_scale);
     g = max(0, min(g, p.nbins - 1));
-    while (g < p.nbins - 1 && c <= edges[g + 1]) ++g;
-    while (g > 0 && c > edges[g]) --g;
+    // edges[0] = +inf and edges[nbins] = -2 bound both steps.  The guess is within 7e-5 rad: for
+    // bins wider than that (nbins <= 16384) one step either way settles it, otherwise walk.
+    g += (c <= edges[g + 1]) ? 1 : 0;
+    g -= (c > edges[g]) ? 1 : 0;
+    if (p.nbins > 16384) {
+      while (c <= edges[g + 1]) ++g;
+      while (c > edges[g]) --g;
+    }
     const int lo = min(sa, sb), hi = max(sa, sb);
     const int combo = s_combo[(sp_i * MAX_SPECIES + lo) * MAX_SPECIES + hi];
     float w = (sa == sb) ? 2.0f : 1.0f;
@@ -244,13 +289,16 @@ __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t*
     if (p.norm_power > 0) {
       const float pr = __fmul_rn(va.w, vb.w);
       float pw = pr;
-      for (int e = 1; e < p.norm_power; ++e) pw = __fmul_rn(pw, pr);
+      if (p.norm_power == 4) {
+        pw = __fmul_rn(pr, pr);
+        pw = __fmul_rn(pw, pw);
+      } else {
+        for (int e = 1; e < p.norm_power; ++e) pw = __fmul_rn(pw, pr);
+      }
       w = __fmul_rn(w, __frcp_rn(pw));
     }
     // float64 sums: a float32 bin that holds one large weight would swallow every later small one
     atomicAdd(&hist[combo * p.nbins + g], (double)w);
-    q += 32;
-    while (len > 0 && q >= len) { q -= len; ++a; --len; }
   }
 }
 
@@ -291,8 +339,12 @@ __global__ void __launch_bounds__(ADF_THREADS, 3) adf_kernel(const AdfParams p) 
     const unsigned long long item = s_item;
     if (item >= n_items) break;
     const int frame = (int)(item / p.items_per_frame);
-    const bool flagged = p.frame_flags != nullptr && p.frame_flags[frame] != 0u;
+    const uint32_t fbits = p.frame_flags != nullptr ? p.frame_flags[frame] : 0u;
+    const bool flagged = (fbits & ADF_FRAME_FAR) != 0u;
     if (CELLS ? flagged : (p.only_flagged && !flagged)) continue;
+    // every coordinate inside one of the two windows: |d| <= 1.25 box, the 3-op minimum image holds
+    const bool fast = CELLS && (fbits & (ADF_FRAME_OUT_A | ADF_FRAME_OUT_B)) !=
+                                   (ADF_FRAME_OUT_A | ADF_FRAME_OUT_B);
     const int c0 = (int)(item % p.items_per_frame) * CENTRES_PER_ITEM;
     const int c1 = min(p.n_atoms, c0 + CENTRES_PER_ITEM);
 
@@ -335,24 +387,30 @@ __global__ void __launch_bounds__(ADF_THREADS, 3) adf_kernel(const AdfParams p) 
           if (lane >= o) incl += v;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (lane < N_SPANS) {
-          s_span_end[warp][lane] = incl;
-          s_span_adj[warp][lane] = begin - (incl - len);
+        // only the non-empty spans are kept (half of them are the unused wrap pieces)
+        const unsigned nonempty = __ballot_sync(0xffffffffu, len > 0);
+        if (len > 0) {
+          const int k = __popc(nonempty & ((1u << lane) - 1u));
+          s_span_end[warp][k] = incl;
+          s_span_adj[warp][k] = begin - (incl - len);
         }
-        if (lane == 0) s_span_end[warp][N_SPANS] = 0x7fffffff;
         __syncwarp();
         my_tests += (unsigned long long)total;
-        int span = 0;
+        int span = 0, span_end = total > 0 ? s_span_end[warp][0] : 0;
         for (int t0 = 0; t0 < total; t0 += 32) {
           const int t = t0 + lane;
           const bool valid = t < total;
           float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
           if (valid) {
-            while (t >= s_span_end[warp][span]) ++span;
+            while (t >= span_end) span_end = s_span_end[warp][++span];
             pj = __ldg(sorted + t + s_span_adj[warp][span]);
           }
-          consider(valid, ci.x, ci.y, ci.z, pj.x, pj.y, pj.z, sp_i, __float_as_int(pj.w), p,
-                   my_vec, my_sp, m, lane);
+          if (fast)
+            consider<true>(valid, ci.x, ci.y, ci.z, pj.x, pj.y, pj.z, sp_i, __float_as_int(pj.w), p,
+                           my_vec, my_sp, m, lane);
+          else
+            consider<false>(valid, ci.x, ci.y, ci.z, pj.x, pj.y, pj.z, sp_i, __float_as_int(pj.w),
+                            p, my_vec, my_sp, m, lane);
         }
         __syncwarp();
       } else {
@@ -371,7 +429,7 @@ __global__ void __launch_bounds__(ADF_THREADS, 3) adf_kernel(const AdfParams p) 
             zj = __ldg(fpos + 3 * j + 2);
             sp_j = p.species[j];
           }
-          consider(valid, xi, yi, zi, xj, yj, zj, sp_i, sp_j, p, my_vec, my_sp, m, lane);
+          consider<false>(valid, xi, yi, zi, xj, yj, zj, sp_i, sp_j, p, my_vec, my_sp, m, lane);
         }
       }
       if (m > p.max_nb) {
@@ -379,6 +437,8 @@ __global__ void __launch_bounds__(ADF_THREADS, 3) adf_kernel(const AdfParams p) 
         m = p.max_nb;
       }
       my_max_nb = max(my_max_nb, m);
+      __syncwarp();
+      normalise(my_vec, m, lane);
       __syncwarp();
       bin_triples(my_vec, my_sp, m, sp_i, p, hist, edges, s_combo, lane, my_triples);
       __syncwarp();
@@ -416,8 +476,12 @@ __global__ void adf_cell_count_kernel(const float* __restrict__ pos, int n_atoms
        idx += (size_t)gridDim.x * blockDim.x) {
     const int f = (int)(idx / n_atoms);
     const float x = pos[3 * idx], y = pos[3 * idx + 1], z = pos[3 * idx + 2];
+    uint32_t wb = mds::window_bits(x, g.box[0]) | mds::window_bits(y, g.box[1]) |
+                  mds::window_bits(z, g.box[2]);  // bit0: outside window A, bit1: outside window B
+    uint32_t bits = wb << 1;
     if (fabsf(x) > 8.0f * g.box[0] || fabsf(y) > 8.0f * g.box[1] || fabsf(z) > 8.0f * g.box[2])
-      frame_flags[f] = 1u;
+      bits |= ADF_FRAME_FAR;
+    if (bits && (frame_flags[f] & bits) != bits) atomicOr(frame_flags + f, bits);
     const int c = mds::cell_of(x, y, z, g);
     cell_id[idx] = (uint32_t)c;
     rank[idx] = atomicAdd(cell_cnt + (size_t)f * (g.nc + 1) + c, 1u);
@@ -584,7 +648,7 @@ int run_batch_once(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) 
     ADF_CUDA_TRY(cudaMemcpyAsync(h->h_flags.data(), h->d_flags, sizeof(uint32_t) * (size_t)n_frames,
                                  cudaMemcpyDeviceToHost, h->stream));
     ADF_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    for (int f = 0; f < n_frames; ++f) far += h->h_flags[(size_t)f] != 0u;
+    for (int f = 0; f < n_frames; ++f) far += (h->h_flags[(size_t)f] & ADF_FRAME_FAR) != 0u;
     if (far) {  // configurations with a coordinate beyond 8 box lengths: all-atoms search
       ADF_CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long), h->stream));
       p.only_flagged = 1;

@@ -197,12 +197,22 @@ CELL_CASES = [
     dict(id="exactly_three_cells", counts=[400], box=[10.0, 10.0, 10.0], cutoff=3.3, nbins=50),
     dict(id="unwrapped_within_8_boxes", counts=[260, 100], box=[14.0, 14.0, 14.0], cutoff=3.0,
          nbins=72, unwrapped=True),
+    # coordinates in [-L/2, L/2): the other window in which the short minimum image is valid
+    dict(id="centred_box", counts=[280, 150], box=[13.0, 15.0, 14.0], cutoff=3.2, nbins=80,
+         shift=-0.5),
+    # one atom a little outside [0, L): neither window holds, the general minimum image is used
+    dict(id="one_atom_outside_both_windows", counts=[300], box=[12.0, 12.0, 12.0], cutoff=3.0,
+         nbins=60, stray=True),
 ]
 
 
 @pytest.mark.parametrize("case", CELL_CASES, ids=[c["id"] for c in CELL_CASES])
 def test_cell_search_equals_all_atoms_search_and_oracle(monkeypatch, case):
     pos = uniform(71 + len(case["id"]), case["counts"], 2, case["box"], case.get("unwrapped", False))
+    if case.get("shift"):
+        pos = (pos + np.float32(case["shift"]) * np.asarray(case["box"], dtype=np.float32)).astype(np.float32)
+    if case.get("stray"):
+        pos[:, 7, 1] += np.float32(1.3 * case["box"][1])
     # atoms exactly on cell and box boundaries
     pos[0, 0] = [0.0, 0.0, 0.0]
     pos[0, 1] = [case["box"][0], case["box"][1], case["box"][2]]
