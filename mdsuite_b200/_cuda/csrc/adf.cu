@@ -309,7 +309,7 @@ __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t*
 //   searched; frames with a coordinate beyond 8 box lengths are flagged and left to the other form
 //   (the cell-assignment error bound of DESIGN.md §9 needs |x| <= 8 L).
 template <bool CELLS>
-__global__ void __launch_bounds__(ADF_THREADS, 3) adf_kernel(const AdfParams p) {
+__global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* nb_vec = reinterpret_cast<float4*>(smem_raw);                       // [WARPS][max_nb]
   uint8_t* nb_sp = reinterpret_cast<uint8_t*>(nb_vec + ADF_WARPS * p.max_nb);  // [WARPS][max_nb]
@@ -481,7 +481,13 @@ __global__ void adf_cell_count_kernel(const float* __restrict__ pos, int n_atoms
     uint32_t bits = wb << 1;
     if (fabsf(x) > 8.0f * g.box[0] || fabsf(y) > 8.0f * g.box[1] || fabsf(z) > 8.0f * g.box[2])
       bits |= ADF_FRAME_FAR;
-    if (bits && (frame_flags[f] & bits) != bits) atomicOr(frame_flags + f, bits);
+    // one atomic per warp and configuration instead of one per atom
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, f);
+    bits = __reduce_or_sync(peers, bits);
+    if (bits && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31) &&
+        (frame_flags[f] & bits) != bits)
+      atomicOr(frame_flags + f, bits);
     const int c = mds::cell_of(x, y, z, g);
     cell_id[idx] = (uint32_t)c;
     rank[idx] = atomicAdd(cell_cnt + (size_t)f * (g.nc + 1) + c, 1u);

@@ -60,6 +60,7 @@ def make_experiment(tmp_path, case):
     for n, c in zip(case["names"], case["counts"]):
         chunk.add_data(pos[:, off:off + c], 0, n, "Positions")
         off += c
+    os.makedirs(str(tmp_path), exist_ok=True)
     project = mds.Project("adf_" + case["name"], storage_path=str(tmp_path))
     exp = project.add_experiment("run", timestep=0.002, temperature=300.0, units="metal",
                                  simulation_data=ScriptInput(data=chunk, metadata=md, name="mem"))

@@ -275,3 +275,50 @@ def test_clustered_atoms_in_one_cell(monkeypatch):
     want = oracle_raw(pos, counts, box, 3.0, 40, 0)
     got, st = _compute_with_path(monkeypatch, "cells", pos, counts, box, 3.0, 40, 0)
     assert np.array_equal(got, want) and st.max_neighbours > 100
+
+
+# ---- the calculator call, end to end on the GPU -------------------------------------------------
+
+def test_calculator_call_equals_the_reference_run(tmp_path):
+    """experiment.run.AngularDistributionFunction(...) with the real engine against the output of
+    the reference's own run_calculator (tests/golden/adf_golden.json)."""
+    from tests.test_adf_calculator_cpu import GOLDEN, make_experiment
+    for case in GOLDEN:
+        project, exp = make_experiment(tmp_path / case["name"], case)
+        comp = exp.run.AngularDistributionFunction(
+            number_of_configurations=case["number_of_configurations"], cutoff=case["cutoff"],
+            start=case.get("start", 1), number_of_bins=case["nbins"],
+            norm_power=case["norm_power"], batches=case["n_batches"], plot=False)
+        assert comp.keys() == ["_".join(r["subjects"]) for r in case["results"]]
+        for rec in case["results"]:
+            got = comp["_".join(rec["subjects"])]
+            want = np.array([float.fromhex(v) for v in rec["adf"]], dtype=np.float32)
+            assert got["max_peak"] == rec["max_peak"]
+            assert np.array_equal(np.array(got["angle"]),
+                                  np.array([float.fromhex(v) for v in rec["angle"]]))
+            mine = np.array(got["adf"])
+            if case["norm_power"] == 0:
+                assert np.array_equal(mine.astype(np.float32), want)
+            else:
+                assert np.max(np.abs(mine - want)) <= WEIGHT_TOL * want.max()
+
+
+def test_calculator_on_a_melt_from_a_dump(tmp_path):
+    """LAMMPS dump -> project -> ADF on the cell path; curves against the oracle's."""
+    import mdsuite_b200 as mds
+    from mdsuite_b200 import synthetic
+    sysm = synthetic.nacl_melt(4, 4, seed=12)  # 512 atoms
+    dump = tmp_path / "melt.lammpstraj"
+    synthetic.write_lammps_dump(sysm, str(dump))
+    project = mds.Project("adf_melt", storage_path=str(tmp_path))
+    exp = project.add_experiment("NaCl", timestep=0.002, temperature=1400.0, units="metal",
+                                 simulation_data=str(dump))
+    comp = exp.run.AngularDistributionFunction(number_of_configurations=3, cutoff=4.5, start=0,
+                                               number_of_bins=90, batches=3, plot=True)
+    want = adf_oracle.adf(sysm.positions, sysm.counts, ["Na", "Cl"], sysm.box, 4.5, 90, 4,
+                          [[0], [1], [3]])
+    assert comp.keys() == ["Na_Na_Na", "Na_Na_Cl", "Na_Cl_Cl", "Cl_Cl_Cl"]
+    for key in comp.keys():
+        ref = want[key.replace("_", "-")]
+        assert comp[key]["max_peak"] == ref["max_peak"]
+        assert np.max(np.abs(np.array(comp[key]["adf"]) - ref["adf"])) <= WEIGHT_TOL * ref["adf"].max()
