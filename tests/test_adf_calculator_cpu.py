@@ -119,3 +119,24 @@ def test_no_gpu_means_an_error_not_a_fallback(tmp_path):
     project, exp = make_experiment(tmp_path, GOLDEN[0])
     with pytest.raises(RuntimeError, match="no CUDA device"):
         exp.run.AngularDistributionFunction(number_of_configurations=2, cutoff=3.0, plot=False)
+
+
+def test_atom_selection_and_species_subset(tmp_path, monkeypatch):
+    """A dict atom_selection picks atoms per species (reference :218-301); the engine sees only the
+    selected atoms, species in the order of ``species=``."""
+    monkeypatch.setattr(AngularDistributionFunction, "handle_factory", OracleADFHandle)
+    case = GOLDEN[1]  # three species: O 6, H 9, C 5
+    project, exp = make_experiment(tmp_path, case)
+    selection = {"H": [0, 2, 4, 6, 8], "O": [1, 2, 3]}
+    comp = exp.run.AngularDistributionFunction(
+        number_of_configurations=2, cutoff=3.0, start=0, number_of_bins=24, norm_power=0,
+        species=["H", "O"], atom_selection=selection, batches=1, plot=False)
+    assert comp.keys() == ["H_H_H", "H_H_O", "H_O_O", "O_O_O"]
+    pos = positions_for(case)
+    frames = np.linspace(0, case["frames"] - 1, 2, dtype=int)
+    sub = np.concatenate([pos[:, 6:15][:, selection["H"]], pos[:, 0:6][:, selection["O"]]], axis=1)
+    want = adf_oracle.adf(sub, [5, 3], ["H", "O"], case["box"], 3.0, 24, 0, [list(frames)])
+    for key in comp.keys():
+        ref = want[key.replace("_", "-")]["adf"]
+        got = np.array(comp[key]["adf"], dtype=np.float32)
+        assert np.array_equal(np.nan_to_num(got, nan=-1.0), np.nan_to_num(ref, nan=-1.0))

@@ -322,3 +322,27 @@ def test_calculator_on_a_melt_from_a_dump(tmp_path):
         ref = want[key.replace("_", "-")]
         assert comp[key]["max_peak"] == ref["max_peak"]
         assert np.max(np.abs(np.array(comp[key]["adf"]) - ref["adf"])) <= WEIGHT_TOL * ref["adf"].max()
+
+
+# ---- random shapes ------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shapes_counts_are_identical(seed, monkeypatch):
+    """Random species tables, boxes, cutoffs, bin counts and coordinate ranges; whichever search the
+    library picks, and the other one when both apply."""
+    rng = np.random.Generator(np.random.Philox(1000 + seed))
+    n_species = int(rng.integers(1, 5))
+    counts = [int(c) for c in rng.integers(0, 140, n_species)]
+    if sum(counts) < 3:
+        counts[0] += 40
+    box = [float(b) for b in rng.uniform(7.0, 13.0, 3)]
+    cutoff = float(rng.uniform(1.5, 3.4))
+    nbins = int(rng.choice([1, 9, 50, 181, 500, 1024]))
+    pos = uniform(2000 + seed, counts, int(rng.integers(1, 4)), box, unwrapped=bool(seed % 3 == 0))
+    if seed % 4 == 1:
+        pos -= np.float32(0.5) * np.asarray(box, dtype=np.float32)
+    want = oracle_raw(pos, counts, box, cutoff, nbins, 0)
+    for path in (None, "allatoms") + (("cells",) if min(box) >= 3.02 * cutoff else ()):
+        got, st = _compute_with_path(monkeypatch, path, pos, counts, box, cutoff, nbins, 0)
+        assert np.array_equal(got, want), (seed, path, counts, box, cutoff, nbins)
+        assert st.triples == want.sum()
