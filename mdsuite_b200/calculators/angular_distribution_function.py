@@ -194,35 +194,49 @@ class AngularDistributionFunction(Calculator):
             factory = lambda *a, **k: cuda_adf.ADFHandle(*a, device=device, **k)  # noqa: E731
         else:
             factory = injected
+        from mdsuite_b200.distributed import (allreduce_host_sums, distributed_context,
+                                              shard_configurations)
         nbins = self.args.number_of_bins
         combos = list(itertools.combinations_with_replacement(range(len(counts)), 3))
-        angles = [None] * len(combos)
+        rank, world, dist = distributed_context()
+        # Configurations are independent up to the per-batch normalisation: every rank takes its
+        # block of every batch, and ONE allreduce of the per-batch weight sums
+        # [batch][combination][bin] (float64) makes the batches whole on all ranks.
+        batch_sums = np.zeros((len(split_arr), len(combos), nbins), dtype=np.float64)
         raw_all = []
         t0 = time.perf_counter()
         handle = factory(counts, nbins, self.args.cutoff, self.experiment.box_array,
                          norm_power=self.args.norm_power)
         try:
-            for frames in split_arr:
-                if len(frames) == 0:
+            for b, frames in enumerate(split_arr):
+                mine = shard_configurations(frames, world, rank) if dist is not None else frames
+                if len(mine) == 0:
                     continue
-                positions = self._load(paths, selections, frames, counts)
+                positions = self._load(paths, selections, mine, counts)
                 raw = handle.compute(positions)  # (frames, combinations, bins) float64
                 raw_all.append(raw)
-                batch = raw.sum(axis=0)
-                for c in range(len(combos)):
-                    hist = normalise_batch(batch[c], nbins)
-                    angles[c] = hist if angles[c] is None else angles[c] + hist
+                batch_sums[b] = raw.sum(axis=0)
             stats = handle.stats() if hasattr(handle, "stats") else None
         finally:
             handle.close()
-        self.raw = np.concatenate(raw_all, axis=0) if raw_all else None
+        if dist is not None:
+            batch_sums = allreduce_host_sums(batch_sums, device=getattr(handle, "device", None))
+        angles = [None] * len(combos)
+        for b, frames in enumerate(split_arr):
+            if len(frames) == 0:
+                continue
+            for c in range(len(combos)):
+                hist = normalise_batch(batch_sums[b, c], nbins)
+                angles[c] = hist if angles[c] is None else angles[c] + hist
+        self.raw = np.concatenate(raw_all, axis=0) if raw_all else None  # this rank's share
         elapsed = time.perf_counter() - t0
         if stats is not None:
-            self.run_stats = {"triples": stats.triples, "pair_tests": stats.pair_tests,
-                              "seconds": elapsed, "max_neighbours": stats.max_neighbours,
+            self.run_stats = {"triples_this_rank": stats.triples,
+                              "pair_tests_this_rank": stats.pair_tests, "seconds": elapsed,
+                              "max_neighbours": stats.max_neighbours,
                               "frames": int(len(self.sample_configurations)),
-                              "batches": len(split_arr)}
-            log.info(f"ADF: {stats.triples:.3e} triples in {elapsed:.3f} s")
+                              "batches": len(split_arr), "world_size": world}
+            log.info(f"ADF: {stats.triples:.3e} triples on this rank in {elapsed:.3f} s")
         self._compute_adfs(angles, combos)
 
     def _compute_adfs(self, angles, combos):

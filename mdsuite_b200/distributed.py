@@ -52,3 +52,30 @@ def allreduce_host_counts(counts: np.ndarray, group=None) -> np.ndarray:
     t = torch.from_numpy(np.ascontiguousarray(counts).view(np.int64).copy())
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t.numpy().view(np.uint64)
+
+
+def distributed_context():
+    """(rank, world, dist module or None) under an initialised torch.distributed group of more than
+    one rank, else (0, 1, None)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_rank(), dist.get_world_size(), dist
+    except ImportError:
+        pass
+    return 0, 1, None
+
+
+def allreduce_host_sums(sums: np.ndarray, device=None, group=None) -> np.ndarray:
+    """Sum of a host float64 array over the process group — the ADF's one collective: the weight
+    sums [batch][combination][bin] of the configurations every rank took.  Goes through the GPU
+    when the group's backend is NCCL."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(sums, dtype=np.float64).copy())
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.numpy()

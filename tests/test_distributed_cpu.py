@@ -77,6 +77,45 @@ def test_calculator_shards_frames_over_ranks(tmp_path):
     assert np.allclose(y0[1:], want[1:], rtol=1e-12)
 
 
+def _worker_adf(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mdsuite_b200 as mds
+    from mdsuite_b200.calculators.angular_distribution_function import AngularDistributionFunction
+    from tests.test_adf_calculator_cpu import OracleADFHandle
+    AngularDistributionFunction.handle_factory = OracleADFHandle
+    OracleADFHandle.calls = []
+    sysm = synthetic.nacl_melt(2, 8, seed=13)
+    p = mds.Project(f"adf_rank{rank}", storage_path=out_dir)
+    e = p.add_experiment("NaCl")
+    e.add_positions(sysm.positions, sysm.species, sysm.box)
+    comp = e.run.AngularDistributionFunction(number_of_configurations=7, cutoff=4.0, start=0,
+                                             number_of_bins=40, norm_power=2, batches=2, plot=False)
+    np.save(os.path.join(out_dir, f"adf{rank}.npy"),
+            np.stack([np.array(comp[k]["adf"]) for k in comp.keys()]))
+    np.save(os.path.join(out_dir, f"adf_calls{rank}.npy"), np.array(OracleADFHandle.calls))
+    dist.destroy_process_group()
+
+
+def test_adf_calculator_shards_every_batch_over_ranks(tmp_path):
+    """7 configurations in 2 batches (4 + 3), each batch split over 2 ranks (2 + 2, 2 + 1); one
+    allreduce of the per-batch weight sums; both ranks get the single-process curves."""
+    from oracle import adf_oracle
+    port = _free_port()
+    mp.spawn(_worker_adf, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a0, a1 = np.load(tmp_path / "adf0.npy"), np.load(tmp_path / "adf1.npy")
+    assert np.array_equal(a0, a1)
+    assert np.load(tmp_path / "adf_calls0.npy").tolist() == [2, 2]
+    assert np.load(tmp_path / "adf_calls1.npy").tolist() == [2, 1]
+    sysm = synthetic.nacl_melt(2, 8, seed=13)
+    frames = np.linspace(0, 7, 7, dtype=int)
+    want = adf_oracle.adf(sysm.positions, sysm.counts, ["Na", "Cl"], sysm.box, 4.0, 40, 2,
+                          [list(b) for b in np.array_split(frames, 2)])
+    for row, key in zip(a0, ["Na-Na-Na", "Na-Na-Cl", "Na-Cl-Cl", "Cl-Cl-Cl"]):
+        assert np.max(np.abs(row - want[key]["adf"])) <= 2e-6 * want[key]["adf"].max()
+
+
 def test_shard_configurations_edge_cases():
     assert shard_configurations(np.arange(3), 8, 5).size == 0  # more ranks than frames
     parts = [shard_configurations(np.arange(10), 4, r) for r in range(4)]
