@@ -302,6 +302,45 @@ def cell_list_probe(device: int, fp32_peak: float, frames: int = 160):
     }
 
 
+def adf_probe(device: int, frames: int = 64, check: bool = True):
+    """The sibling path (include/mds_adf.h): angular distribution function of a
+    cfg2-shaped NaCl melt (13 824 atoms, cutoff 6 A, 500 bins, norm_power 4) resident in HBM; triples
+    per second, and (with the CPU-baseline leg) a parity gate of the triple counts against the NumPy
+    oracle on a 512-atom melt."""
+    import torch
+    from mdsuite_b200 import synthetic
+    from mdsuite_b200._cuda import adf as cuda_adf
+    sysm = synthetic.nacl_melt(12, 4, seed=2)
+    pos = torch.from_numpy(sysm.positions).cuda(device).repeat(frames // 4, 1, 1).contiguous()
+    with cuda_adf.ADFHandle(sysm.counts, 500, 6.0, sysm.box, norm_power=4, device=device,
+                            max_frames_in_flight=frames) as h:
+        out = h.compute_device(pos)
+        t_before = h.stats().triples
+        best = None
+        for _ in range(4):
+            h.compute_device(pos, out=out)
+            ms = h.stats().kernel_ms
+            best = ms if best is None or ms < best else best
+        st = h.stats()
+    differing = None
+    if check:
+        from oracle import adf_oracle  # the checker, as in the cpu_baseline leg
+        small = synthetic.nacl_melt(4, 1, seed=3)
+        with cuda_adf.ADFHandle(small.counts, 90, 4.5, small.box, norm_power=0, device=device) as h:
+            got = h.compute(small.positions)
+        want = adf_oracle.raw_histograms(small.positions[0], small.counts, small.box, 4.5, 90, 0)
+        differing = int((got[0] != want).sum())
+    return {
+        "workload": f"cfg2-shaped NaCl melt: {sysm.n_atoms} atoms, cutoff 6.0, 500 bins, norm_power 4, "
+                    f"{frames} configurations resident in HBM, best of 4",
+        "kernel": "adf_kernel<cells>", "cells": list(st.cells),
+        "triples_per_call": t_before, "kernel_ms": best,
+        "triples_per_s": t_before / (best * 1e-3),
+        "max_neighbours": st.max_neighbours,
+        "bins_differing_vs_oracle_512_atoms": differing,
+    }
+
+
 def run_ours(args):
     import torch
     from mdsuite_b200 import _cuda
@@ -480,6 +519,14 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             cell_list = {"error": str(exc)}
 
+    # ---- the sibling structural path, the ADF (rank 0, N = 1 only) ---------------------------
+    adf = None
+    if world == 1 and not args.no_adf_probe:
+        try:
+            adf = adf_probe(local_rank, check=not args.no_cpu_baseline)
+        except Exception as exc:  # noqa: BLE001
+            adf = {"error": str(exc)}
+
     # ---- the same step through the user-level call (rank 0, N = 1 only) ---------------------
     user_api = None
     if world == 1 and not args.no_user_api:
@@ -523,7 +570,7 @@ def run_ours(args):
                          f"{12 * n_atoms * n_frames / 1e6:.0f} MB packed per step vs 126 MB L2",
                    "parallelism": f"frames sharded over {world} GPU(s), 1 NCCL allreduce/step"
                    if world > 1 else "1 GPU"},
-        "roofline": roofline, "cell_list_path": cell_list, "user_api": user_api,
+        "roofline": roofline, "cell_list_path": cell_list, "adf_path": adf, "user_api": user_api,
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
                 "h2d_bytes_per_step": int(12 * n_atoms * n_frames),
@@ -577,6 +624,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-user-api", action="store_true",
                     help="skip the Project -> Experiment -> run.RadialDistributionFunction timing")
+    ap.add_argument("--no-adf-probe", action="store_true",
+                    help="skip the short angular-distribution measurement added at N=1")
     ap.add_argument("--no-cell-probe", action="store_true",
                     help="skip the short cfg3-shaped cell-list measurement added at N=1")
     args = ap.parse_args()
