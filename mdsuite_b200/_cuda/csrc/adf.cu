@@ -162,6 +162,8 @@ struct AdfParams {
   AdfGrid grid;
   int only_flagged;         // all-atoms form: process the flagged configurations only
   int max_nb;               // capacity of a warp's neighbour list
+  int hist_in_smem;         // 0: combinations x bins do not fit in shared memory, sums go straight
+                            //    to the configuration's global histogram
   const uint8_t* species;   // [N]
   const float* cos_edges;   // [nbins + 1]
   double* out;              // [F][combos][nbins]
@@ -256,7 +258,8 @@ __device__ __forceinline__ float acos_guess(float c) {
 // middle row is its own partner; the list ends after its m / 2 entries.)
 __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t* my_sp, int m,
                                             int sp_i, const AdfParams& p, double* hist,
-                                            const float* edges, const int8_t* s_combo, int lane,
+                                            double* fout, const float* edges,
+                                            const int8_t* s_combo, int lane,
                                             unsigned long long& my_triples) {
   const int total = (m * (m - 1)) >> 1;
   int R = 0, c = lane;
@@ -298,7 +301,8 @@ __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t*
       w = __fmul_rn(w, __frcp_rn(pw));
     }
     // float64 sums: a float32 bin that holds one large weight would swallow every later small one
-    atomicAdd(&hist[combo * p.nbins + g], (double)w);
+    if (p.hist_in_smem) atomicAdd(&hist[combo * p.nbins + g], (double)w);
+    else atomicAdd(&fout[combo * p.nbins + g], (double)w);
   }
 }
 
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
   float4* nb_vec = reinterpret_cast<float4*>(smem_raw);                       // [WARPS][max_nb]
   uint8_t* nb_sp = reinterpret_cast<uint8_t*>(nb_vec + ADF_WARPS * p.max_nb);  // [WARPS][max_nb]
   double* hist = reinterpret_cast<double*>(nb_sp + ADF_WARPS * p.max_nb);      // [combos][nbins]
-  float* edges = reinterpret_cast<float*>(hist + p.n_combos * p.nbins);        // [nbins + 1]
+  float* edges = reinterpret_cast<float*>(hist + (p.hist_in_smem ? p.n_combos * p.nbins : 0));
   __shared__ unsigned long long s_item;
   __shared__ int s_span_end[ADF_WARPS][N_SPANS + 1];  // running end of every span in the flattened list
   __shared__ int s_span_adj[ADF_WARPS][N_SPANS];      // sorted slot = flattened index + adj
@@ -322,7 +326,8 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hist_len = p.n_combos * p.nbins;
-  for (int k = tid; k < hist_len; k += ADF_THREADS) hist[k] = 0.0;
+  if (p.hist_in_smem)
+    for (int k = tid; k < hist_len; k += ADF_THREADS) hist[k] = 0.0;
   for (int k = tid; k <= p.nbins; k += ADF_THREADS) edges[k] = p.cos_edges[k];
   for (int k = tid; k < MAX_SPECIES * MAX_SPECIES * MAX_SPECIES; k += ADF_THREADS)
     s_combo[k] = p.combo_of[k];
@@ -440,13 +445,14 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
       __syncwarp();
       normalise(my_vec, m, lane);
       __syncwarp();
-      bin_triples(my_vec, my_sp, m, sp_i, p, hist, edges, s_combo, lane, my_triples);
+      bin_triples(my_vec, my_sp, m, sp_i, p, hist, p.out + (size_t)frame * hist_len, edges, s_combo,
+                  lane, my_triples);
       __syncwarp();
     }
     // ---- flush this item's sums into the configuration's histogram ----
     __syncthreads();
     double* fout = p.out + (size_t)frame * hist_len;
-    for (int k = tid; k < hist_len; k += ADF_THREADS) {
+    for (int k = tid; p.hist_in_smem && k < hist_len; k += ADF_THREADS) {
       const double v = hist[k];
       if (v != 0.0) {
         atomicAdd(fout + k, v);
@@ -558,6 +564,7 @@ struct mds_adf {
   bool use_cells = false;
   AdfGrid cells;
   int max_nb = 0;          // capacity of a warp's neighbour list in the current configuration
+  bool hist_in_smem = true;
   size_t smem_limit = 0;
   // device
   cudaStream_t stream = nullptr;
@@ -584,18 +591,24 @@ struct mds_adf {
 
 namespace {
 
-size_t smem_for(const mds_adf* h, int max_nb) {
+size_t smem_for(const mds_adf* h, int max_nb, bool hist_in_smem) {
   return (size_t)ADF_WARPS * (size_t)max_nb * (sizeof(float4) + 1) +
-         sizeof(double) * (size_t)h->n_combos * h->nbins + sizeof(float) * ((size_t)h->nbins + 1);
+         (hist_in_smem ? sizeof(double) * (size_t)h->n_combos * h->nbins : 0) +
+         sizeof(float) * ((size_t)h->nbins + 1);
 }
 
 // shared-memory layout, launch attributes and grid for a neighbour-list capacity
 int configure(mds_adf* h, int max_nb) {
-  const size_t bytes = smem_for(h, max_nb);
+  // the CTA's histogram lives in shared memory when it leaves room for two CTAs per SM, else the
+  // sums go straight to global memory (many species x many bins)
+  bool hist_in_smem = smem_for(h, max_nb, true) <= h->smem_limit / 2;
+  const char* env = getenv("MDS_ADF_HIST");
+  if (env && !strcmp(env, "global")) hist_in_smem = false;
+  const size_t bytes = smem_for(h, max_nb, hist_in_smem);
   if (bytes > h->smem_limit)
     return fail(MDS_ADF_ERR_UNSUPPORTED,
-                "%d combinations x %d bins with %d neighbours per atom need %zu bytes of shared "
-                "memory (limit %zu)", h->n_combos, h->nbins, max_nb, bytes, h->smem_limit);
+                "%d bins with %d neighbours per atom need %zu bytes of shared memory (limit %zu)",
+                h->nbins, max_nb, bytes, h->smem_limit);
   // the attribute belongs to the function, not to the handle: always allow the device maximum
   if (cudaFuncSetAttribute(adf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)h->smem_limit) != cudaSuccess ||
@@ -613,6 +626,8 @@ int configure(mds_adf* h, int max_nb) {
   h->smem_bytes = bytes;
   h->grid = std::min(per_sm, per_sm_b) * h->sm_count;
   h->base.max_nb = max_nb;
+  h->hist_in_smem = hist_in_smem;
+  h->base.hist_in_smem = hist_in_smem ? 1 : 0;
   return MDS_ADF_OK;
 }
 
@@ -799,7 +814,7 @@ int mds_adf_create(mds_adf_t** out, const mds_adf_config* cfg) {
     while (cap < MAX_NB_LIMIT && (double)cap < 2.5 * expected + 32.0) cap *= 2;
     const char* env = getenv("MDS_ADF_NEIGHBOUR_CAPACITY");
     if (env && atoi(env) >= 32 && atoi(env) <= MAX_NB_LIMIT) cap = atoi(env);
-    while (cap > 64 && smem_for(h, cap) > h->smem_limit) cap /= 2;
+    while (cap > 64 && smem_for(h, cap, false) > h->smem_limit) cap /= 2;
     rc = configure(h, cap);
     if (rc != MDS_ADF_OK) return cleanup(rc);
   }
@@ -875,6 +890,7 @@ int mds_adf_create(mds_adf_t** out, const mds_adf_config* cfg) {
   AdfParams& p = h->base;
   memset(&p, 0, sizeof(p));
   p.max_nb = h->max_nb;
+  p.hist_in_smem = h->hist_in_smem ? 1 : 0;
   p.species = h->d_species;
   p.cos_edges = h->d_edges;
   p.work_counter = h->d_counters;

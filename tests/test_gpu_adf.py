@@ -346,3 +346,33 @@ def test_random_shapes_counts_are_identical(seed, monkeypatch):
         got, st = _compute_with_path(monkeypatch, path, pos, counts, box, cutoff, nbins, 0)
         assert np.array_equal(got, want), (seed, path, counts, box, cutoff, nbins)
         assert st.triples == want.sum()
+
+
+# ---- histograms that do not fit in shared memory ------------------------------------------------
+
+def test_many_species_use_the_global_histogram():
+    """6 species = 56 combinations x 500 bins x 8 bytes do not fit beside the neighbour lists: the
+    sums go straight to the configuration's global histogram."""
+    counts = [30, 25, 20, 28, 22, 26]
+    box = [9.0, 9.0, 9.0]
+    pos = uniform(301, counts, 2, box)
+    got, st = check(pos, counts, box, 3.0, 500, 0)
+    assert got.shape[1] == 56
+    check(pos, counts, box, 3.0, 500, 4)
+
+
+def test_global_histogram_equals_shared_histogram(monkeypatch):
+    counts, box = [300, 260], [15.0, 15.0, 15.0]
+    pos = uniform(302, counts, 3, box)
+    shared, _ = check(pos, counts, box, 3.2, 120, 0)
+    monkeypatch.setenv("MDS_ADF_HIST", "global")
+    glob, _ = check(pos, counts, box, 3.2, 120, 0)
+    assert np.array_equal(shared, glob)
+
+
+def test_very_fine_bins_walk_the_table():
+    """20 000 bins are narrower than the arccosine guess is accurate: the bin is found by walking
+    the threshold table, not by one step."""
+    counts, box = [120], [9.0, 9.0, 9.0]
+    pos = uniform(303, counts, 2, box)
+    check(pos, counts, box, 3.3, 20000, 0)
