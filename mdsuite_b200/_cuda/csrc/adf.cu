@@ -7,7 +7,7 @@
 //   neighbour iff float16(n) != 0 and float16(n) < float16(r_cut)   <=>  s_lo <= s < s_hi
 //   u = r / n (per component);  c = clip((ux1*ux2 + uy1*uy2) + uz1*uz2, -1, 1)
 //   theta = float32(acos(c)), bin by np.histogram over [0, 3.15]    <=>  c against cos_edges[]
-//   weight = 1 / (n1 * n2)^norm_power
+//   weight = 1 / (n1 * n2)^norm_power   (formed as n1^-p * n2^-p, see normalise())
 // The two "<=>" are threshold tables built on the host with the same IEEE operations, so the kernel
 // needs neither a float16 conversion nor an exact arccosine: it guesses the bin with acosf() and
 // settles it by comparing c with the table.
@@ -232,12 +232,26 @@ __device__ __forceinline__ void consider(bool valid, float xi, float yi, float z
   m += __popc(ballot);
 }
 
-// (r, |r|^2) -> (r / |r|, |r|) for the m entries of a neighbour list
-__device__ __forceinline__ void normalise(float4* my_vec, int m, int lane) {
+// (r, |r|^2) -> (r / |r|, |r|^-norm_power) for the m entries of a neighbour list.  The weight of a
+// triple, 1 / (|r_ij| |r_ik|)^p, is formed as |r_ij|^-p * |r_ik|^-p: a few float32 roundings away
+// from the contract's value (<= 4e-7 relative, inside the tolerance of the weighted sums; the
+// counts, norm_power = 0, do not depend on it).
+__device__ __forceinline__ void normalise(float4* my_vec, int m, int lane, int norm_power) {
   for (int k = lane; k < m; k += 32) {
     const float4 v = my_vec[k];
     const float n = __fsqrt_rn(v.w);
-    my_vec[k] = make_float4(__fdiv_rn(v.x, n), __fdiv_rn(v.y, n), __fdiv_rn(v.z, n), n);
+    float q = 1.0f;
+    if (norm_power > 0) {
+      float pw = n;
+      if (norm_power == 4) {
+        pw = __fmul_rn(n, n);
+        pw = __fmul_rn(pw, pw);
+      } else {
+        for (int e = 1; e < norm_power; ++e) pw = __fmul_rn(pw, n);
+      }
+      q = __frcp_rn(pw);
+    }
+    my_vec[k] = make_float4(__fdiv_rn(v.x, n), __fdiv_rn(v.y, n), __fdiv_rn(v.z, n), q);
   }
 }
 
@@ -262,13 +276,14 @@ __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t*
                                             const int8_t* s_combo, int lane,
                                             unsigned long long& my_triples) {
   const int total = (m * (m - 1)) >> 1;
-  int R = 0, c = lane;
+  unsigned n_triples = 0;  // <= 2 * 1024 * 1023 / 2 per centre
+  int R = 0, col = lane;
   for (int t = lane; t < total; t += 32) {
-    while (c >= m) { c -= m; ++R; }
+    while (col >= m) { col -= m; ++R; }
     const int first = m - 1 - R;  // entries of row R in this combined row
-    const int a = c < first ? R : m - 2 - R;
-    const int b = c < first ? R + 1 + c : a + 1 + (c - first);
-    c += 32;
+    const int a = col < first ? R : m - 2 - R;
+    const int b = col < first ? R + 1 + col : a + 1 + (col - first);
+    col += 32;
     const float4 va = my_vec[a];
     const float4 vb = my_vec[b];
     const int sa = my_sp[a], sb = my_sp[b];
@@ -287,23 +302,12 @@ __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t*
     }
     const int lo = min(sa, sb), hi = max(sa, sb);
     const int combo = s_combo[(sp_i * MAX_SPECIES + lo) * MAX_SPECIES + hi];
-    float w = (sa == sb) ? 2.0f : 1.0f;
-    my_triples += (sa == sb) ? 2ull : 1ull;
-    if (p.norm_power > 0) {
-      const float pr = __fmul_rn(va.w, vb.w);
-      float pw = pr;
-      if (p.norm_power == 4) {
-        pw = __fmul_rn(pr, pr);
-        pw = __fmul_rn(pw, pw);
-      } else {
-        for (int e = 1; e < p.norm_power; ++e) pw = __fmul_rn(pw, pr);
-      }
-      w = __fmul_rn(w, __frcp_rn(pw));
-    }
-    // float64 sums: a float32 bin that holds one large weight would swallow every later small one
+    const float w = __fmul_rn((sa == sb) ? 2.0f : 1.0f, __fmul_rn(va.w, vb.w));
+    n_triples += (sa == sb) ? 2u : 1u;
     if (p.hist_in_smem) atomicAdd(&hist[combo * p.nbins + g], (double)w);
     else atomicAdd(&fout[combo * p.nbins + g], (double)w);
   }
+  my_triples += n_triples;
 }
 
 // CELLS = false: every atom of the configuration is tested against the centre (any input; the
@@ -443,7 +447,7 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
       }
       my_max_nb = max(my_max_nb, m);
       __syncwarp();
-      normalise(my_vec, m, lane);
+      normalise(my_vec, m, lane, p.norm_power);
       __syncwarp();
       bin_triples(my_vec, my_sp, m, sp_i, p, hist, p.out + (size_t)frame * hist_len, edges, s_combo,
                   lane, my_triples);
