@@ -137,8 +137,12 @@ int neighbour_window_norm(float cutoff, float* n_lo, float* n_hi) {
     return fail(MDS_ADF_ERR_INVALID, "cutoff %g is zero as a float16", (double)cutoff);
   float hi = cut16;  // float16(hi) == cut16, not below it; walk down to the first float that is
   while (half_round(nextafterf(hi, -INFINITY)) >= cut16) hi = nextafterf(hi, -INFINITY);
-  float lo = 5.9604645e-8f;  // 2^-24, the smallest float16 subnormal
-  while (lo > 0.0f && half_round(nextafterf(lo, -INFINITY)) != 0.0f) lo = nextafterf(lo, -INFINITY);
+  // smallest float whose float16 is not zero: 2^-25 is the tie between 0 and the smallest
+  // subnormal 2^-24 and goes to the even one, 0; the next float up rounds to 2^-24
+  const float tie = ldexpf(1.0f, -25);
+  const float lo = nextafterf(tie, INFINITY);
+  if (half_round(tie) != 0.0f || half_round(lo) == 0.0f)
+    return fail(MDS_ADF_ERR_INVALID, "internal: unexpected float16 rounding at 2^-25");
   *n_lo = lo;
   *n_hi = hi;
   return MDS_ADF_OK;
@@ -586,6 +590,8 @@ struct mds_adf {
   uint32_t* d_flags = nullptr;    // [batch]
   std::vector<uint32_t> h_flags;
   int64_t frames_far = 0;
+  int work_frames = 0;     // configurations the cell-build buffers hold
+  int staging_frames = 0;  // configurations d_pos / d_out hold (host entry point only)
   // statistics
   int64_t frames = 0, launches = 0;
   double triples = 0, pair_tests = 0;
@@ -594,6 +600,39 @@ struct mds_adf {
 };
 
 namespace {
+
+// Grow the per-configuration device buffers to `frames` configurations (<= batch_frames):
+// allocation is tens of milliseconds per 100 MB, so a handle only pays for what it is given.
+int ensure_frames(mds_adf* h, int frames, bool staging) {
+  auto grow = [&](int have) { return std::min(h->batch_frames, std::max(frames, have * 2)); };
+  if (h->use_cells && frames > h->work_frames) {
+    const int n = grow(h->work_frames);
+    ADF_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_sorted); cudaFree(h->d_cell_id); cudaFree(h->d_rank);
+    cudaFree(h->d_cell_off); cudaFree(h->d_flags);
+    h->d_sorted = nullptr; h->d_cell_id = nullptr; h->d_rank = nullptr;
+    h->d_cell_off = nullptr; h->d_flags = nullptr;
+    h->work_frames = 0;
+    const size_t atoms = (size_t)h->n_atoms * (size_t)n;
+    ADF_CUDA_TRY(cudaMalloc(&h->d_sorted, sizeof(float4) * atoms));
+    ADF_CUDA_TRY(cudaMalloc(&h->d_cell_id, sizeof(uint32_t) * atoms));
+    ADF_CUDA_TRY(cudaMalloc(&h->d_rank, sizeof(uint32_t) * atoms));
+    ADF_CUDA_TRY(cudaMalloc(&h->d_cell_off, sizeof(uint32_t) * ((size_t)h->cells.nc + 1) * (size_t)n));
+    ADF_CUDA_TRY(cudaMalloc(&h->d_flags, sizeof(uint32_t) * (size_t)n));
+    h->work_frames = n;
+  }
+  if (staging && frames > h->staging_frames) {
+    const int n = grow(h->staging_frames);
+    ADF_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_pos); cudaFree(h->d_out);
+    h->d_pos = nullptr; h->d_out = nullptr;
+    h->staging_frames = 0;
+    ADF_CUDA_TRY(cudaMalloc(&h->d_pos, sizeof(float) * 3 * (size_t)h->n_atoms * (size_t)n));
+    ADF_CUDA_TRY(cudaMalloc(&h->d_out, sizeof(double) * (size_t)h->n_combos * h->nbins * (size_t)n));
+    h->staging_frames = n;
+  }
+  return MDS_ADF_OK;
+}
 
 size_t smem_for(const mds_adf* h, int max_nb, bool hist_in_smem) {
   return (size_t)ADF_WARPS * (size_t)max_nb * (sizeof(float4) + 1) +
@@ -866,18 +905,10 @@ int mds_adf_create(mds_adf_t** out, const mds_adf_config* cfg) {
   ADF_TRY_CREATE(cudaEventCreate(&h->ev1));
   ADF_TRY_CREATE(cudaEventCreate(&h->ev_k0));
   ADF_TRY_CREATE(cudaEventCreate(&h->ev_k1));
-  ADF_TRY_CREATE(cudaMalloc(&h->d_pos, frame_bytes * (size_t)bf));
-  ADF_TRY_CREATE(cudaMalloc(&h->d_out, out_frame_bytes * (size_t)bf));
   ADF_TRY_CREATE(cudaMalloc(&h->d_species, (size_t)n_atoms));
   ADF_TRY_CREATE(cudaMalloc(&h->d_edges, sizeof(float) * ((size_t)h->nbins + 1)));
   ADF_TRY_CREATE(cudaMalloc(&h->d_counters, 3 * sizeof(unsigned long long)));
-  if (h->use_cells) {
-    ADF_TRY_CREATE(cudaMalloc(&h->d_sorted, sizeof(float4) * (size_t)n_atoms * (size_t)bf));
-    ADF_TRY_CREATE(cudaMalloc(&h->d_cell_id, sizeof(uint32_t) * (size_t)n_atoms * (size_t)bf));
-    ADF_TRY_CREATE(cudaMalloc(&h->d_rank, sizeof(uint32_t) * (size_t)n_atoms * (size_t)bf));
-    ADF_TRY_CREATE(cudaMalloc(&h->d_cell_off, sizeof(uint32_t) * ((size_t)h->cells.nc + 1) * (size_t)bf));
-    ADF_TRY_CREATE(cudaMalloc(&h->d_flags, sizeof(uint32_t) * (size_t)bf));
-  }
+  // the per-configuration buffers are sized by the calls that come (ensure_frames)
   ADF_TRY_CREATE(cudaMalloc(&h->d_status, 2 * sizeof(int)));
   ADF_TRY_CREATE(cudaMemset(h->d_status, 0, 2 * sizeof(int)));
   {
@@ -952,6 +983,10 @@ int mds_adf_compute(mds_adf_t* h, const float* xyz, int64_t n_frames, double* ou
   const size_t out_frame = (size_t)h->n_combos * h->nbins;
   ADF_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
   float kernel_ms = 0.f;
+  {
+    const int rc = ensure_frames(h, (int)std::min<int64_t>(h->batch_frames, n_frames), true);
+    if (rc != MDS_ADF_OK) return rc;
+  }
   for (int64_t f0 = 0; f0 < n_frames; f0 += h->batch_frames) {
     const int nf = (int)std::min<int64_t>(h->batch_frames, n_frames - f0);
     ADF_CUDA_TRY(cudaMemcpyAsync(h->d_pos, xyz + (size_t)f0 * frame_floats,
@@ -986,6 +1021,10 @@ int mds_adf_compute_device(mds_adf_t* h, const float* d_xyz, int64_t n_frames, d
   ADF_CUDA_TRY(cudaEventRecord(h->ev_k0, h->stream));
   const size_t frame_floats = (size_t)h->n_atoms * 3;
   const size_t out_frame = (size_t)h->n_combos * h->nbins;
+  {
+    const int rc = ensure_frames(h, (int)std::min<int64_t>(h->batch_frames, n_frames), false);
+    if (rc != MDS_ADF_OK) return rc;
+  }
   for (int64_t f0 = 0; f0 < n_frames; f0 += h->batch_frames) {
     const int nf = (int)std::min<int64_t>(h->batch_frames, n_frames - f0);
     const int rc = run_batch(h, d_xyz + (size_t)f0 * frame_floats, nf, d_out + (size_t)f0 * out_frame);

@@ -167,9 +167,13 @@ class AngularDistributionFunction(Calculator):
         split_arr = np.array_split(self.sample_configurations, self._number_of_batches(paths))
         return paths, selections, split_arr
 
-    def _load(self, paths, selections, frames, counts) -> np.ndarray:
-        """(len(frames), N, 3) float32, species concatenated in args.species order (:459-487)."""
-        out = np.empty((len(frames), sum(counts), 3), dtype=np.float32)
+    def _load(self, paths, selections, frames, counts, staging=None) -> np.ndarray:
+        """(len(frames), N, 3) float32, species concatenated in args.species order (:459-487);
+        written into ``staging`` (page-locked, reused by every batch) when given."""
+        if staging is not None:
+            out = staging[:len(frames)]
+        else:
+            out = np.empty((len(frames), sum(counts), 3), dtype=np.float32)
         off = 0
         for p, sel, n in zip(paths, selections, counts):
             out[:, off:off + n] = self.experiment.database.load_frames(p, frames, atom_selection=sel)
@@ -207,15 +211,33 @@ class AngularDistributionFunction(Calculator):
         t0 = time.perf_counter()
         handle = factory(counts, nbins, self.args.cutoff, self.experiment.box_array,
                          norm_power=self.args.norm_power)
+        # Two buffers for the largest batch (page-locked for long runs): the next batch is read from
+        # the store by a worker thread while the GPU works on the current one, and no batch
+        # allocates.
+        my_batches = [(b, shard_configurations(frames, world, rank) if dist is not None else frames)
+                      for b, frames in enumerate(split_arr)]
+        my_batches = [(b, f) for b, f in my_batches if len(f)]
+        staging = [None, None]
+        if injected is None and my_batches:
+            import torch
+            largest = max(len(f) for _, f in my_batches)
+            # page-locking costs ~0.5 ms per MB: worth it from about eight batches on
+            pin = len(my_batches) >= 8 and largest * sum(counts) * 12 <= (1 << 30)
+            staging = [torch.empty((largest, sum(counts), 3), dtype=torch.float32,
+                                   pin_memory=pin).numpy() for _ in range(2)]
         try:
-            for b, frames in enumerate(split_arr):
-                mine = shard_configurations(frames, world, rank) if dist is not None else frames
-                if len(mine) == 0:
-                    continue
-                positions = self._load(paths, selections, mine, counts)
-                raw = handle.compute(positions)  # (frames, combinations, bins) float64
-                raw_all.append(raw)
-                batch_sums[b] = raw.sum(axis=0)
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=1) as pool:
+                def fetch(k):
+                    return pool.submit(self._load, paths, selections, my_batches[k][1], counts,
+                                       staging[k % 2])
+                pending = fetch(0) if my_batches else None
+                for k, (b, mine) in enumerate(my_batches):
+                    positions = pending.result()
+                    pending = fetch(k + 1) if k + 1 < len(my_batches) else None
+                    raw = handle.compute(positions)  # (frames, combinations, bins) float64
+                    raw_all.append(raw)
+                    batch_sums[b] = raw.sum(axis=0)
             stats = handle.stats() if hasattr(handle, "stats") else None
         finally:
             handle.close()
