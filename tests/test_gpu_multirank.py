@@ -39,6 +39,14 @@ for name, sysm, cutoff, nbins in (
     comp = calc(number_of_configurations=sysm.n_frames, number_of_bins=nbins, cutoff=cutoff, plot=False)
     np.save(os.path.join(out, f"{name}_y{rank}.npy"),
             np.array([comp[k]["y"] for k in comp.keys()], dtype=float))
+# the ADF: every batch's configurations are split over the ranks, one allreduce of the batch sums
+melt = synthetic.nacl_melt(3, 9, seed=24)
+project = mds.Project(f"adf_rank{rank}", storage_path=out)
+exp = project.add_experiment("e")
+exp.add_positions(melt.positions, melt.species, melt.box)
+adf = exp.run.AngularDistributionFunction(number_of_configurations=8, cutoff=4.0, start=0,
+                                          number_of_bins=60, norm_power=4, batches=3, plot=False)
+np.save(os.path.join(out, f"adf{rank}.npy"), np.array([adf[k]["adf"] for k in adf.keys()], dtype=float))
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -76,3 +84,14 @@ def test_two_ranks_nccl_calculator(tmp_path):
         want = rdf_oracle.normalise(counts, names, sysm.counts, sysm.box, cutoff, sysm.n_frames)
         for row, key in zip(y0, want):
             assert np.allclose(row[1:], np.array(want[key]["y"])[1:], rtol=1e-12, atol=0)
+
+    # ADF: both ranks hold the same curves, equal to the single-process oracle's
+    from oracle import adf_oracle
+    melt = synthetic.nacl_melt(3, 9, seed=24)
+    a0, a1 = np.load(tmp_path / "adf0.npy"), np.load(tmp_path / "adf1.npy")
+    assert np.array_equal(a0, a1)
+    frames = np.linspace(0, 8, 8, dtype=int)
+    want = adf_oracle.adf(melt.positions, melt.counts, ["Na", "Cl"], melt.box, 4.0, 60, 4,
+                          [list(b) for b in np.array_split(frames, 3)])
+    for row, key in zip(a0, ["Na-Na-Na", "Na-Na-Cl", "Na-Cl-Cl", "Cl-Cl-Cl"]):
+        assert np.max(np.abs(row - want[key]["adf"])) <= 2e-6 * want[key]["adf"].max()
