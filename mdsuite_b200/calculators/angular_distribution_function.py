@@ -35,7 +35,9 @@ from mdsuite_b200.utils.meta_functions import join_path
 log = logging.getLogger(__name__)
 
 BIN_RANGE = (0.0, 3.15)  # "from 0 to a chemists pi" (reference :215)
-MEMORY_FRACTION = 0.2  # of the free host memory, as the reference's MemoryManager default
+# of the free host memory: MemoryManager takes it from the global config
+# (memory_management/memory_manager.py:108, utils/config.py:47)
+MEMORY_FRACTION = 0.5
 
 
 @dataclass
