@@ -159,7 +159,7 @@ struct AdfGrid {
 
 struct AdfParams {
   const float* pos;         // [F][N][3]
-  const float4* sorted;     // [F][N] (x, y, z, species bits), atoms ordered by cell (cell path)
+  const float4* sorted;     // [F][N] (x, y, z, species | cell << 3), atoms ordered by cell (cell path)
   const uint32_t* cell_off; // [F][nc + 1] first sorted slot of every cell (cell path)
   const uint32_t* frame_flags;  // [F] != 0: a coordinate beyond 8 box lengths (cell path declines)
   unsigned long long* pair_tests;
@@ -361,16 +361,23 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
     const int c0 = (int)(item % p.items_per_frame) * CENTRES_PER_ITEM;
     const int c1 = min(p.n_atoms, c0 + CENTRES_PER_ITEM);
 
-    for (int i = c0 + warp; i < c1; i += ADF_WARPS) {
+    // A warp takes consecutive centres of the sorted order: they mostly share a cell, and the span
+    // table of the 27-cell stencil is rebuilt only when the cell changes.
+    constexpr int PER_WARP = CENTRES_PER_ITEM / ADF_WARPS;
+    int prev_cell = -1, total = 0;
+    for (int i = c0 + warp * PER_WARP; i < min(c1, c0 + (warp + 1) * PER_WARP); ++i) {
       int m = 0, sp_i;
       if (CELLS) {
         const float4* sorted = p.sorted + (size_t)frame * p.n_atoms;
         const uint32_t* off = p.cell_off + (size_t)frame * (p.grid.nc + 1);
         const float4 ci = __ldg(sorted + i);
-        sp_i = __float_as_int(ci.w);
-        const int cx = mds::cell_coord(ci.x, p.grid.box[0], p.grid.nx);
-        const int cy = mds::cell_coord(ci.y, p.grid.box[1], p.grid.ny);
-        const int cz = mds::cell_coord(ci.z, p.grid.box[2], p.grid.nz);
+        sp_i = __float_as_int(ci.w) & (MAX_SPECIES - 1);
+        const int cell = __float_as_int(ci.w) >> 3;
+        if (cell != prev_cell) {
+        prev_cell = cell;
+        const int cx = cell % p.grid.nx;
+        const int cy = (cell / p.grid.nx) % p.grid.ny;
+        const int cz = cell / (p.grid.nx * p.grid.ny);
         // The x window [cx - 1, cx + 1] of a cell row is one contiguous span of the sorted array, or
         // two where it wraps around the box: 18 spans at most.  Lane s < 18 fetches the bounds of
         // span s (one round trip for all of them); the spans are then walked as ONE flattened
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
           const int v = __shfl_up_sync(0xffffffffu, incl, o);
           if (lane >= o) incl += v;
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        total = __shfl_sync(0xffffffffu, incl, 31);
         // only the non-empty spans are kept (half of them are the unused wrap pieces)
         const unsigned nonempty = __ballot_sync(0xffffffffu, len > 0);
         if (len > 0) {
@@ -408,6 +415,7 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
           s_span_adj[warp][k] = begin - (incl - len);
         }
         __syncwarp();
+        }
         my_tests += (unsigned long long)total;
         int span = 0, span_end = total > 0 ? s_span_end[warp][0] : 0;
         for (int t0 = 0; t0 < total; t0 += 32) {
@@ -419,11 +427,11 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
             pj = __ldg(sorted + t + s_span_adj[warp][span]);
           }
           if (fast)
-            consider<true>(valid, ci.x, ci.y, ci.z, pj.x, pj.y, pj.z, sp_i, __float_as_int(pj.w), p,
-                           my_vec, my_sp, m, lane);
+            consider<true>(valid, ci.x, ci.y, ci.z, pj.x, pj.y, pj.z, sp_i,
+                           __float_as_int(pj.w) & (MAX_SPECIES - 1), p, my_vec, my_sp, m, lane);
           else
-            consider<false>(valid, ci.x, ci.y, ci.z, pj.x, pj.y, pj.z, sp_i, __float_as_int(pj.w),
-                            p, my_vec, my_sp, m, lane);
+            consider<false>(valid, ci.x, ci.y, ci.z, pj.x, pj.y, pj.z, sp_i,
+                            __float_as_int(pj.w) & (MAX_SPECIES - 1), p, my_vec, my_sp, m, lane);
         }
         __syncwarp();
       } else {
@@ -545,8 +553,9 @@ __global__ void adf_cell_scatter_kernel(const float* __restrict__ pos,
     const size_t f = idx / n_atoms;
     const int a = (int)(idx - f * n_atoms);
     const uint32_t slot = cell_off[f * (nc + 1) + cell_id[idx]] + rank[idx];
+    // w carries the species (3 bits) and the cell id above it (< 2^21 cells)
     sorted[f * n_atoms + slot] = make_float4(pos[3 * idx], pos[3 * idx + 1], pos[3 * idx + 2],
-                                             __int_as_float((int)species[a]));
+                                             __int_as_float((int)species[a] | ((int)cell_id[idx] << 3)));
   }
 }
 
