@@ -377,3 +377,36 @@ def test_very_fine_bins_walk_the_table():
     counts, box = [120], [9.0, 9.0, 9.0]
     pos = uniform(303, counts, 2, box)
     check(pos, counts, box, 3.3, 20000, 0)
+
+
+def test_cfg2_size_totals_against_blockwise_neighbour_counts():
+    """13 824-atom melt (the cfg2 shape): per-combination totals of the triple counts against
+    n_B (n_B - 1) / n_B n_C sums from neighbour counts computed blockwise in NumPy with the same
+    float32 arithmetic and the same squared-distance window."""
+    from mdsuite_b200 import synthetic
+    sysm = synthetic.nacl_melt(12, 2, seed=2)
+    cutoff = 6.0
+    with _adf().ADFHandle(sysm.counts, 500, cutoff, sysm.box, norm_power=0) as h:
+        got = h.compute(sysm.positions)
+        st = h.stats()
+    assert st.cells == (12, 12, 12) and st.frames_far == 0
+    s_lo, s_hi = _adf().neighbour_window(cutoff)
+    box = np.asarray(sysm.box, dtype=np.float32)
+    species = np.repeat([0, 1], sysm.counts)
+    for f in range(2):
+        pos = sysm.positions[f]
+        n0 = np.zeros(len(pos), dtype=np.int64)
+        n1 = np.zeros(len(pos), dtype=np.int64)
+        for lo in range(0, len(pos), 1024):
+            r = pos[lo:lo + 1024, None, :] - pos[None, :, :]
+            r = r - np.rint(r / box) * box
+            sq = r * r
+            s = (sq[..., 0] + sq[..., 1]) + sq[..., 2]
+            nb = (s >= s_lo) & (s < s_hi)
+            n0[lo:lo + 1024] = (nb & (species[None, :] == 0)).sum(1)
+            n1[lo:lo + 1024] = (nb & (species[None, :] == 1)).sum(1)
+        c0, c1 = species == 0, species == 1
+        want = [np.sum(n0[c0] * (n0[c0] - 1)), np.sum(n0[c0] * n1[c0]),
+                np.sum(n1[c0] * (n1[c0] - 1)), np.sum(n1[c1] * (n1[c1] - 1))]
+        assert got[f].sum(axis=1).tolist() == [float(w) for w in want]
+    assert st.triples == got.sum()
