@@ -23,13 +23,11 @@ from __future__ import annotations
 
 import logging
 import pathlib
-from typing import Dict, Iterator, List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-from mdsuite_b200.database.simulation_database import (PropertyInfo, SpeciesInfo,
-                                                       TrajectoryChunkData, TrajectoryMetadata)
-from mdsuite_b200.file_io.file_read import FileProcessor
+from mdsuite_b200.file_io.tabular_text_files import NativeTabularTextFile
 
 log = logging.getLogger(__name__)
 
@@ -122,7 +120,7 @@ def _declared_columns(header: str) -> Optional[int]:
     return None
 
 
-class EXTXYZFile(FileProcessor):
+class EXTXYZFile(NativeTabularTextFile):
     def __init__(self, file_path, custom_data_map: dict = None, chunk_bytes: int = 256 << 20,
                  n_threads: int = 0):
         """``custom_data_map`` maps further property names to the names used in the file's
@@ -137,9 +135,6 @@ class EXTXYZFile(FileProcessor):
         self._mdata = None
         self._layout = None
         self._dump = None
-
-    def __str__(self):
-        return self.file_path
 
     def _open(self):
         if self._dump is None:
@@ -183,44 +178,3 @@ class EXTXYZFile(FileProcessor):
                             species_idx=species_idx, species=species, props=props, box_l=box_l,
                             sample_rate=sample_rate)
         return self._layout
-
-    def _get_metadata(self) -> TrajectoryMetadata:
-        lay = self._analyse()
-        species_list = [SpeciesInfo(name=n, n_particles=len(idx),
-                                    properties=[PropertyInfo(p, len(c)) for p, c in lay["props"].items()])
-                        for n, idx in lay["species"].items()]
-        return TrajectoryMetadata(n_configurations=lay["n_configs"], species_list=species_list,
-                                  box_l=lay["box_l"], sample_rate=lay["sample_rate"])
-
-    # ---- streaming (reference tabular_text_files.py:122-220) ---------------------------------
-    def get_configurations_generator(self) -> Iterator[TrajectoryChunkData]:
-        lay = self._analyse()
-        dump = self._open()
-        n, species_list = lay["n_particles"], self.metadata.species_list
-        prop_items = list(lay["props"].items())
-        all_cols = [c for _, cols in prop_items for c in cols]
-        if not all_cols:
-            return
-        per_frame = max(1, n * len(all_cols) * 4)
-        chunk_frames = max(1, min(lay["n_configs"], self.chunk_bytes // per_frame))
-        # the native reader scatters line k to row dest[k]: species-contiguous, so the per-species
-        # slices below are plain views
-        dest = np.empty(n, dtype=np.int32)
-        bounds, off = {}, 0
-        for name, idx in lay["species"].items():
-            dest[np.asarray(idx, dtype=np.int64)] = np.arange(off, off + len(idx), dtype=np.int32)
-            bounds[name] = (off, off + len(idx))
-            off += len(idx)
-        done = 0
-        while done < lay["n_configs"]:
-            k = min(chunk_frames, lay["n_configs"] - done)
-            table = dump.read_columns(done, k, all_cols, dest=dest, sort_by_id=False)
-            chunk = TrajectoryChunkData(species_list, k)
-            off = 0
-            for prop, cols in prop_items:
-                values = table[:, :, off:off + len(cols)]
-                off += len(cols)
-                for name, (lo, hi) in bounds.items():
-                    chunk.add_data(values[:, lo:hi], 0, name, prop)
-            done += k
-            yield chunk
