@@ -215,13 +215,8 @@ class RadialDistributionFunction(Calculator):
     # ---- the GPU batch loop -----------------------------------------------------------------
     def _distributed_context(self):
         """(rank, world, dist module or None) under torch.distributed, else (0, 1, None)."""
-        try:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                return dist.get_rank(), dist.get_world_size(), dist
-        except ImportError:
-            pass
-        return 0, 1, None
+        from mdsuite_b200.distributed import distributed_context
+        return distributed_context()
 
     def prepare_computation(self):
         """Paths, per-species selections and the store (reference :565-599)."""
