@@ -29,8 +29,7 @@ from typing import List, Union
 
 import numpy as np
 
-from mdsuite_b200.calculators.calculator import Calculator, call
-from mdsuite_b200.utils.meta_functions import join_path
+from mdsuite_b200.calculators.calculator import Calculator, call, resolve_species_data
 
 log = logging.getLogger(__name__)
 
@@ -153,19 +152,7 @@ class AngularDistributionFunction(Calculator):
         return int(self.args.number_of_configurations / batch_size)
 
     def prepare_computation(self):
-        if self.args.molecules and not getattr(self.experiment, "molecules", None):
-            raise ValueError("molecules=True needs molecule groups in the experiment "
-                             "(the MolecularMap transformation is outside this package's scope)")
-        paths = [join_path(item, self.loaded_property) for item in self.args.species]
-        for p in paths:
-            if not self.experiment.database.check_existence(p):
-                raise KeyError(f"dataset {p} not found in the trajectory store")
-        if isinstance(self.args.atom_selection, dict):
-            selections = [list(self.args.atom_selection[item]) for item in self.args.species]
-        elif isinstance(self.args.atom_selection, slice) and self.args.atom_selection == slice(None):
-            selections = [None] * len(paths)
-        else:
-            raise ValueError("atom_selection must be np.s_[:] or a dict {species: [indices]}")
+        paths, selections = resolve_species_data(self.experiment, self.args, self.loaded_property)
         split_arr = np.array_split(self.sample_configurations, self._number_of_batches(paths))
         return paths, selections, split_arr
 

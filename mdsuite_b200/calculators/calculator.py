@@ -120,6 +120,27 @@ class Calculator:
                                    y_data=val[self.result_series_keys[1]], title=selected_species)
 
 
+def resolve_species_data(experiment, args, loaded_property: str):
+    """Store paths and per-species atom selections of a trajectory calculator (reference
+    calculators/radial_distribution_function.py:565-599, angular_distribution_function.py:565-575):
+    ``atom_selection`` is ``np.s_[:]`` or a dict {species: [indices]}."""
+    from mdsuite_b200.utils.meta_functions import join_path
+    if args.molecules and not getattr(experiment, "molecules", None):
+        raise ValueError("molecules=True needs molecule groups in the experiment "
+                         "(the MolecularMap transformation is outside this package's scope)")
+    paths = [join_path(item, loaded_property) for item in args.species]
+    for p in paths:
+        if not experiment.database.check_existence(p):
+            raise KeyError(f"dataset {p} not found in the trajectory store")
+    if isinstance(args.atom_selection, dict):
+        selections = [list(args.atom_selection[item]) for item in args.species]
+    elif isinstance(args.atom_selection, slice) and args.atom_selection == slice(None):
+        selections = [None] * len(paths)
+    else:
+        raise ValueError("atom_selection must be np.s_[:] or a dict {species: [indices]}")
+    return paths, selections
+
+
 def _count_subjects(subjects):
     seen = {}
     for s in subjects:

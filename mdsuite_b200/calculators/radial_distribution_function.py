@@ -33,9 +33,9 @@ from typing import List, Optional, Union
 
 import numpy as np
 
-from mdsuite_b200.calculators.calculator import Calculator, call
+from mdsuite_b200.calculators.calculator import Calculator, call, resolve_species_data
 from mdsuite_b200.memory_management.memory_manager import FrameBatcher, MemoryManager
-from mdsuite_b200.utils.meta_functions import join_path, split_array
+from mdsuite_b200.utils.meta_functions import split_array
 
 log = logging.getLogger(__name__)
 
@@ -220,20 +220,7 @@ class RadialDistributionFunction(Calculator):
 
     def prepare_computation(self):
         """Paths, per-species selections and the store (reference :565-599)."""
-        if self.args.molecules and not getattr(self.experiment, "molecules", None):
-            raise ValueError("molecules=True needs molecule groups in the experiment "
-                             "(the MolecularMap transformation is outside this package's scope)")
-        paths = [join_path(item, self.loaded_property) for item in self.args.species]
-        for p in paths:
-            if not self.experiment.database.check_existence(p):
-                raise KeyError(f"dataset {p} not found in the trajectory store")
-        if isinstance(self.args.atom_selection, dict):
-            selections = [list(self.args.atom_selection[item]) for item in self.args.species]
-        elif isinstance(self.args.atom_selection, slice) and self.args.atom_selection == slice(None):
-            selections = [None] * len(paths)
-        else:
-            raise ValueError("atom_selection must be np.s_[:] or a dict {species: [indices]}")
-        return paths, selections
+        return resolve_species_data(self.experiment, self.args, self.loaded_property)
 
     def run_calculator(self):
         """Reference :828-887 with the TensorFlow loop replaced by the CUDA library."""
