@@ -314,6 +314,51 @@ __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t*
   my_triples += n_triples;
 }
 
+// Span table of the 27-cell stencil around `cell` for one warp.  The x window [cx - 1, cx + 1] of
+// a cell row is one contiguous span of the sorted array, or two where it wraps around the box: 18
+// spans at most.  Lane s < 18 fetches the bounds of span s (one round trip for all of them); the
+// non-empty spans (half of them are the unused wrap pieces) are stored as running ends of ONE
+// flattened candidate list plus the offset that maps a list position to a sorted slot.  Returns
+// the length of the list.  Warp-collective.
+__device__ __forceinline__ int build_span_table(int cell, const AdfGrid& g, const uint32_t* off,
+                                                int lane, int* span_end, int* span_adj) {
+  const int cx = cell % g.nx;
+  const int cy = (cell / g.nx) % g.ny;
+  const int cz = cell / (g.nx * g.ny);
+  int len = 0, begin = 0;
+  if (lane < N_SPANS) {
+    const int r = lane >> 1, part = lane & 1;
+    int z = cz + r / 3 - 1, y = cy + r % 3 - 1;
+    z += (z < 0) ? g.nz : 0;
+    z -= (z >= g.nz) ? g.nz : 0;
+    y += (y < 0) ? g.ny : 0;
+    y -= (y >= g.ny) ? g.ny : 0;
+    int x0, x1;
+    if (part == 0) { x0 = max(cx - 1, 0); x1 = min(cx + 1, g.nx - 1); }
+    else if (cx == 0) { x0 = x1 = g.nx - 1; }
+    else if (cx == g.nx - 1) { x0 = x1 = 0; }
+    else { x0 = 0; x1 = -1; }
+    if (x1 >= x0) {
+      const int row = (z * g.ny + y) * g.nx;
+      begin = (int)__ldg(off + row + x0);
+      len = (int)__ldg(off + row + x1 + 1) - begin;
+    }
+  }
+  int incl = len;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const unsigned nonempty = __ballot_sync(0xffffffffu, len > 0);
+  if (len > 0) {
+    const int k = __popc(nonempty & ((1u << lane) - 1u));
+    span_end[k] = incl;
+    span_adj[k] = begin - (incl - len);
+  }
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, incl, 31);
+}
+
 // CELLS = false: every atom of the configuration is tested against the centre (any input; the
 //   frames flagged in p.frame_flags only, if p.only_flagged).
 // CELLS = true: the configuration was counting-sorted into cells of width >= 1.002 x the largest
@@ -374,47 +419,8 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
         sp_i = __float_as_int(ci.w) & (MAX_SPECIES - 1);
         const int cell = __float_as_int(ci.w) >> 3;
         if (cell != prev_cell) {
-        prev_cell = cell;
-        const int cx = cell % p.grid.nx;
-        const int cy = (cell / p.grid.nx) % p.grid.ny;
-        const int cz = cell / (p.grid.nx * p.grid.ny);
-        // The x window [cx - 1, cx + 1] of a cell row is one contiguous span of the sorted array, or
-        // two where it wraps around the box: 18 spans at most.  Lane s < 18 fetches the bounds of
-        // span s (one round trip for all of them); the spans are then walked as ONE flattened
-        // list, 32 candidates per step, so that the loads of a centre are independent.
-        int len = 0, begin = 0;
-        if (lane < N_SPANS) {
-          const int r = lane >> 1, part = lane & 1;
-          int z = cz + r / 3 - 1, y = cy + r % 3 - 1;
-          z += (z < 0) ? p.grid.nz : 0;
-          z -= (z >= p.grid.nz) ? p.grid.nz : 0;
-          y += (y < 0) ? p.grid.ny : 0;
-          y -= (y >= p.grid.ny) ? p.grid.ny : 0;
-          int x0, x1;
-          if (part == 0) { x0 = max(cx - 1, 0); x1 = min(cx + 1, p.grid.nx - 1); }
-          else if (cx == 0) { x0 = x1 = p.grid.nx - 1; }
-          else if (cx == p.grid.nx - 1) { x0 = x1 = 0; }
-          else { x0 = 0; x1 = -1; }
-          if (x1 >= x0) {
-            const int row = (z * p.grid.ny + y) * p.grid.nx;
-            begin = (int)__ldg(off + row + x0);
-            len = (int)__ldg(off + row + x1 + 1) - begin;
-          }
-        }
-        int incl = len;
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += v;
-        }
-        total = __shfl_sync(0xffffffffu, incl, 31);
-        // only the non-empty spans are kept (half of them are the unused wrap pieces)
-        const unsigned nonempty = __ballot_sync(0xffffffffu, len > 0);
-        if (len > 0) {
-          const int k = __popc(nonempty & ((1u << lane) - 1u));
-          s_span_end[warp][k] = incl;
-          s_span_adj[warp][k] = begin - (incl - len);
-        }
-        __syncwarp();
+          prev_cell = cell;
+          total = build_span_table(cell, p.grid, off, lane, s_span_end[warp], s_span_adj[warp]);
         }
         my_tests += (unsigned long long)total;
         int span = 0, span_end = total > 0 ? s_span_end[warp][0] : 0;
