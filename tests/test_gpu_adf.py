@@ -410,3 +410,18 @@ def test_cfg2_size_totals_against_blockwise_neighbour_counts():
                 np.sum(n1[c0] * (n1[c0] - 1)), np.sum(n1[c1] * (n1[c1] - 1))]
         assert got[f].sum(axis=1).tolist() == [float(w) for w in want]
     assert st.triples == got.sum()
+
+
+def test_handle_reuse_with_growing_and_empty_batches():
+    """One handle, calls of 1, 6, 0 and 3 configurations: the per-configuration device buffers grow
+    on demand, an empty call returns an empty result, nothing leaks between calls."""
+    counts, box = [260, 200], [14.0, 14.0, 14.0]
+    pos = uniform(401, counts, 6, box)
+    want = oracle_raw(pos, counts, box, 3.1, 64, 0)
+    with _adf().ADFHandle(counts, 64, 3.1, box, norm_power=0) as h:
+        assert np.array_equal(h.compute(pos[:1]), want[:1])
+        assert np.array_equal(h.compute(pos), want)
+        empty = h.compute(pos[:0])
+        assert empty.shape == (0, 4, 64)
+        assert np.array_equal(h.compute(pos[2:5]), want[2:5])
+        assert h.stats().frames == 10
