@@ -17,61 +17,72 @@
 
 namespace mds {
 
+// Thread layout without integer division: blockIdx.y walks the OUTER index, the x dimension the
+// INNER one — frame-major input: outer = frame, inner = packed slot; atom-major input: outer =
+// packed slot, inner = frame (consecutive threads walk the frames of one atom: contiguous 12 B
+// records in the source).
 __global__ void __launch_bounds__(256) rdf_pack_kernel(const PackParams p) {
-  const long long total = (long long)p.n_frames * p.n_packed;
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-       g += (long long)gridDim.x * blockDim.x) {
-    long long f, q;
-    if (p.layout == MDS_LAYOUT_ATOM_MAJOR_XYZ) {
-      // consecutive threads walk frames of one atom: contiguous 12 B records in the source
-      q = g / p.n_frames;
-      f = g % p.n_frames;
-    } else {
-      f = g / p.n_packed;
-      q = g % p.n_packed;
-    }
-    float* dst = p.out + (f * p.frame_stride + (q & ~3LL)) * 3 + (q & 3);
-    const long long a = p.src_index[q];
-    if (a < 0) {  // padding slot at the end of a species segment: never inside the cutoff
-      const float nan = __int_as_float(0x7fc00000);
-      dst[0] = nan; dst[4] = nan; dst[8] = nan;
-      continue;
-    }
-    const float* src = (p.layout == MDS_LAYOUT_ATOM_MAJOR_XYZ)
-                           ? p.xyz + (a * p.n_frames_total + p.frame0 + f) * 3
-                           : p.xyz + ((p.frame0 + f) * p.n_atoms + a) * 3;
-    const float x = __ldg(src), y = __ldg(src + 1), z = __ldg(src + 2);
-    dst[0] = x; dst[4] = y; dst[8] = z;
-    uint32_t bits = window_bits(x, p.box[0]) | window_bits(y, p.box[1]) | window_bits(z, p.box[2]);
-    if (p.cell_off) {
-      // cell-list path: rank of the atom inside its (frame, species, cell).  Lanes of a warp that
-      // hit the same counter (neighbouring atoms of an ordered trajectory share a cell) are
-      // merged with __match_any_sync: one global atomic per distinct counter and warp.
-      const int key = p.species[q] * p.grid.nc + cell_of(x, y, z, p.grid);
-      uint32_t* counter = p.cell_off + f * p.off_stride + key;
+  const bool atom_major = p.layout == MDS_LAYOUT_ATOM_MAJOR_XYZ;
+  const long long inner_n = atom_major ? p.n_frames : (long long)p.n_packed;
+  const long long outer_n = atom_major ? (long long)p.n_packed : p.n_frames;
+  const int lane = threadIdx.x & 31;
+  for (long long outer = blockIdx.y; outer < outer_n; outer += gridDim.y) {
+    for (long long inner = (long long)blockIdx.x * blockDim.x + threadIdx.x; inner < inner_n;
+         inner += (long long)gridDim.x * blockDim.x) {
+      const long long f = atom_major ? inner : outer;
+      const long long q = atom_major ? outer : inner;
+      float* dst = p.out + (f * p.frame_stride + (q & ~3LL)) * 3 + (q & 3);
+      const long long a = p.src_index[q];
+      if (a < 0) {  // padding slot at the end of a species segment: never inside the cutoff
+        const float nan = __int_as_float(0x7fc00000);
+        dst[0] = nan; dst[4] = nan; dst[8] = nan;
+        continue;
+      }
+      const float* src = atom_major ? p.xyz + (a * p.n_frames_total + p.frame0 + f) * 3
+                                    : p.xyz + ((p.frame0 + f) * p.n_atoms + a) * 3;
+      const float x = __ldg(src), y = __ldg(src + 1), z = __ldg(src + 2);
+      dst[0] = x; dst[4] = y; dst[8] = z;
+      uint32_t bits = window_bits(x, p.box[0]) | window_bits(y, p.box[1]) | window_bits(z, p.box[2]);
       const unsigned active = __activemask();
-      const unsigned peers = __match_any_sync(active, (unsigned long long)counter);
-      const int leader = __ffs(peers) - 1;
-      const int lane = threadIdx.x & 31;
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(peers));
-      base = __shfl_sync(peers, base, leader);
-      p.rank[f * p.frame_stride + q] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-      // a coordinate further than 8 box lengths out (or infinite): the cell margin no longer
-      // covers the float32 rounding of the reference's own arithmetic -> all-pairs for this frame
-      if (fabsf(x) > 8.0f * p.box[0] || fabsf(y) > 8.0f * p.box[1] || fabsf(z) > 8.0f * p.box[2])
-        bits |= MDS_FRAME_FAR;
+      if (p.cell_off) {
+        // cell-list path: rank of the atom inside its (frame, species, cell).  Lanes of a warp that
+        // hit the same counter (neighbouring atoms of an ordered trajectory share a cell) are
+        // merged with __match_any_sync: one global atomic per distinct counter and warp.
+        const int key = p.species[q] * p.grid.nc + cell_of(x, y, z, p.grid);
+        uint32_t* counter = p.cell_off + f * p.off_stride + key;
+        const unsigned peers = __match_any_sync(active, (unsigned long long)counter);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        p.rank[f * p.frame_stride + q] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        // a coordinate further than 8 box lengths out (or infinite): the cell margin no longer
+        // covers the float32 rounding of the reference's own arithmetic -> all-pairs for this frame
+        if (fabsf(x) > 8.0f * p.box[0] || fabsf(y) > 8.0f * p.box[1] || fabsf(z) > 8.0f * p.box[2])
+          bits |= MDS_FRAME_FAR;
+      }
+      // frame flags: one atomic per warp and frame (a wrapped frame sets a window bit for most of
+      // its atoms; per-atom atomics on the frame's word serialise)
+      const unsigned same_frame = __match_any_sync(active, f);
+      bits = __reduce_or_sync(same_frame, bits);
+      if (bits && lane == __ffs(same_frame) - 1 && (p.frame_flags[f] & bits) != bits)
+        atomicOr(p.frame_flags + f, bits);
     }
-    if (bits && (p.frame_flags[f] & bits) != bits) atomicOr(p.frame_flags + f, bits);
   }
 }
 
 cudaError_t launch_pack(const PackParams& p, cudaStream_t stream) {
-  const long long total = (long long)p.n_frames * p.n_packed;
-  if (total <= 0) return cudaSuccess;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 64) blocks = 148 * 64;
-  rdf_pack_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  const bool atom_major = p.layout == MDS_LAYOUT_ATOM_MAJOR_XYZ;
+  const long long inner_n = atom_major ? p.n_frames : (long long)p.n_packed;
+  const long long outer_n = atom_major ? (long long)p.n_packed : p.n_frames;
+  if (inner_n <= 0 || outer_n <= 0) return cudaSuccess;
+  long long bx = (inner_n + 255) / 256;
+  if (bx > 148 * 64) bx = 148 * 64;
+  // enough CTAs to fill the machine, at most 65535 in y
+  long long by = (148LL * 64 + bx - 1) / bx;
+  if (by > outer_n) by = outer_n;
+  if (by > 65535) by = 65535;
+  rdf_pack_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
