@@ -21,13 +21,18 @@ def main():
     ap.add_argument("--power", type=int, default=4)
     ap.add_argument("--repeats", type=int, default=3)
     ap.add_argument("--cpu-atoms-cells", type=int, default=4)
+    ap.add_argument("--lj", action="store_true",
+                    help="cfg3-shaped 100 000-atom LJ fluid (one species) instead of the NaCl melt")
     args = ap.parse_args()
     import torch
     from mdsuite_b200 import synthetic
     from mdsuite_b200._cuda import adf as cuda_adf
     from oracle import adf_oracle
 
-    sysm = synthetic.nacl_melt(args.cells, args.frames, seed=2)
+    if args.lj:
+        sysm = synthetic.lj_fluid(47, args.frames, seed=3, n_atoms=100_000)
+    else:
+        sysm = synthetic.nacl_melt(args.cells, args.frames, seed=2)
     pos_d = torch.from_numpy(sysm.positions).cuda()
     with cuda_adf.ADFHandle(sysm.counts, args.bins, args.cutoff, sysm.box, norm_power=args.power,
                             max_frames_in_flight=args.frames) as h:
@@ -51,7 +56,7 @@ def main():
     cpu_triples = adf_oracle.raw_histograms(small.positions[0], small.counts, small.box, args.cutoff,
                                             args.bins, 0).sum()
     print(json.dumps({
-        "workload": f"nacl_{sysm.n_atoms}_atoms_{args.frames}_frames_rc{args.cutoff}_B{args.bins}",
+        "workload": f"{sysm.name}_{sysm.n_atoms}_atoms_{args.frames}_frames_rc{args.cutoff}_B{args.bins}",
         "triples_per_call": triples_per_call, "kernel_ms": ms,
         "triples_per_s": triples_per_call / (ms * 1e-3),
         "allatoms_equivalent_pair_tests_per_s": args.frames * sysm.n_atoms ** 2 / (ms * 1e-3),
