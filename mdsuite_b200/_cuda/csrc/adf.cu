@@ -274,6 +274,8 @@ __device__ __forceinline__ float acos_guess(float c) {
 // position t of the flattened list is entry c = t % m of combined row R = t / m: the pair
 // (R, R + 1 + c) for c < m - 1 - R, else entry c - (m - 1 - R) of row m - 2 - R.  (For even m the
 // middle row is its own partner; the list ends after its m / 2 entries.)
+// ONE_SPECIES: a single combination, every pair counts twice — no species bytes, no table.
+template <bool ONE_SPECIES>
 __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t* my_sp, int m,
                                             int sp_i, const AdfParams& p, double* hist,
                                             double* fout, const float* edges,
@@ -290,7 +292,6 @@ __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t*
     col += 32;
     const float4 va = my_vec[a];
     const float4 vb = my_vec[b];
-    const int sa = my_sp[a], sb = my_sp[b];
     float c = __fadd_rn(__fadd_rn(__fmul_rn(va.x, vb.x), __fmul_rn(va.y, vb.y)),
                         __fmul_rn(va.z, vb.z));
     c = fminf(fmaxf(c, -1.0f), 1.0f);
@@ -304,10 +305,18 @@ __device__ __forceinline__ void bin_triples(const float4* my_vec, const uint8_t*
       while (c <= edges[g + 1]) ++g;
       while (c > edges[g]) --g;
     }
-    const int lo = min(sa, sb), hi = max(sa, sb);
-    const int combo = s_combo[(sp_i * MAX_SPECIES + lo) * MAX_SPECIES + hi];
-    const float w = __fmul_rn((sa == sb) ? 2.0f : 1.0f, __fmul_rn(va.w, vb.w));
-    n_triples += (sa == sb) ? 2u : 1u;
+    int combo = 0;
+    float w = __fmul_rn(va.w, vb.w);
+    if (ONE_SPECIES) {
+      w = __fmul_rn(2.0f, w);
+      n_triples += 2u;
+    } else {
+      const int sa = my_sp[a], sb = my_sp[b];
+      const int lo = min(sa, sb), hi = max(sa, sb);
+      combo = s_combo[(sp_i * MAX_SPECIES + lo) * MAX_SPECIES + hi];
+      w = __fmul_rn((sa == sb) ? 2.0f : 1.0f, w);
+      n_triples += (sa == sb) ? 2u : 1u;
+    }
     if (p.hist_in_smem) atomicAdd(&hist[combo * p.nbins + g], (double)w);
     else atomicAdd(&fout[combo * p.nbins + g], (double)w);
   }
@@ -365,7 +374,7 @@ __device__ __forceinline__ int build_span_table(int cell, const AdfGrid& g, cons
 //   norm that can pass the float16 test (x fastest), and only the 27 cells around the centre are
 //   searched; frames with a coordinate beyond 8 box lengths are flagged and left to the other form
 //   (the cell-assignment error bound of DESIGN.md §9 needs |x| <= 8 L).
-template <bool CELLS>
+template <bool CELLS, bool ONE_SPECIES>
 __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* nb_vec = reinterpret_cast<float4*>(smem_raw);                       // [WARPS][max_nb]
@@ -467,7 +476,7 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
       __syncwarp();
       normalise(my_vec, m, lane, p.norm_power);
       __syncwarp();
-      bin_triples(my_vec, my_sp, m, sp_i, p, hist, p.out + (size_t)frame * hist_len, edges, s_combo,
+      bin_triples<ONE_SPECIES>(my_vec, my_sp, m, sp_i, p, hist, p.out + (size_t)frame * hist_len, edges, s_combo,
                   lane, my_triples);
       __syncwarp();
     }
@@ -655,6 +664,12 @@ size_t smem_for(const mds_adf* h, int max_nb, bool hist_in_smem) {
          sizeof(float) * ((size_t)h->nbins + 1);
 }
 
+typedef void (*adf_kernel_t)(const AdfParams);
+adf_kernel_t adf_kernel_for(bool cells, bool one_species) {
+  if (cells) return one_species ? adf_kernel<true, true> : adf_kernel<true, false>;
+  return one_species ? adf_kernel<false, true> : adf_kernel<false, false>;
+}
+
 // shared-memory layout, launch attributes and grid for a neighbour-list capacity
 int configure(mds_adf* h, int max_nb) {
   // the CTA's histogram lives in shared memory when it leaves room for two CTAs per SM, else the
@@ -668,21 +683,23 @@ int configure(mds_adf* h, int max_nb) {
                 "%d bins with %d neighbours per atom need %zu bytes of shared memory (limit %zu)",
                 h->nbins, max_nb, bytes, h->smem_limit);
   // the attribute belongs to the function, not to the handle: always allow the device maximum
-  if (cudaFuncSetAttribute(adf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)h->smem_limit) != cudaSuccess ||
-      cudaFuncSetAttribute(adf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)h->smem_limit) != cudaSuccess)
-    return fail(MDS_ADF_ERR_CUDA, "cudaFuncSetAttribute failed: %s",
-                cudaGetErrorString(cudaGetLastError()));
-  int per_sm = 0, per_sm_b = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adf_kernel<true>, ADF_THREADS, bytes) !=
-          cudaSuccess || per_sm < 1 ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, adf_kernel<false>, ADF_THREADS,
-                                                    bytes) != cudaSuccess || per_sm_b < 1)
-    return fail(MDS_ADF_ERR_CUDA, "the ADF kernel does not fit on an SM");
+  const bool one = h->n_species == 1;
+  int per_sm = 1 << 30;
+  for (int cells = 0; cells < 2; ++cells) {
+    adf_kernel_t k = adf_kernel_for(cells != 0, one);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit) !=
+        cudaSuccess)
+      return fail(MDS_ADF_ERR_CUDA, "cudaFuncSetAttribute failed: %s",
+                  cudaGetErrorString(cudaGetLastError()));
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, ADF_THREADS, bytes) != cudaSuccess ||
+        n < 1)
+      return fail(MDS_ADF_ERR_CUDA, "the ADF kernel does not fit on an SM");
+    per_sm = std::min(per_sm, n);
+  }
   h->max_nb = max_nb;
   h->smem_bytes = bytes;
-  h->grid = std::min(per_sm, per_sm_b) * h->sm_count;
+  h->grid = per_sm * h->sm_count;
   h->base.max_nb = max_nb;
   h->hist_in_smem = hist_in_smem;
   h->base.hist_in_smem = hist_in_smem ? 1 : 0;
@@ -720,7 +737,7 @@ int run_batch_once(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) 
     p.cell_off = h->d_cell_off;
     p.frame_flags = h->d_flags;
     p.grid = h->cells;
-    adf_kernel<true><<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
+    adf_kernel_for(true, h->n_species == 1)<<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
     ADF_CUDA_TRY(cudaGetLastError());
     h->launches += 4;
     h->h_flags.resize((size_t)n_frames);
@@ -731,12 +748,12 @@ int run_batch_once(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) 
     if (far) {  // configurations with a coordinate beyond 8 box lengths: all-atoms search
       ADF_CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long), h->stream));
       p.only_flagged = 1;
-      adf_kernel<false><<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
+      adf_kernel_for(false, h->n_species == 1)<<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
       ADF_CUDA_TRY(cudaGetLastError());
       h->launches += 1;
     }
   } else {
-    adf_kernel<false><<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
+    adf_kernel_for(false, h->n_species == 1)<<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
     ADF_CUDA_TRY(cudaGetLastError());
     h->launches += 1;
   }
@@ -857,8 +874,8 @@ int mds_adf_create(mds_adf_t** out, const mds_adf_config* cfg) {
   {
     // dynamic shared memory available to the kernels: the opt-in maximum minus their static part
     cudaFuncAttributes fa, fb;
-    if (cudaFuncGetAttributes(&fa, adf_kernel<true>) != cudaSuccess ||
-        cudaFuncGetAttributes(&fb, adf_kernel<false>) != cudaSuccess)
+    if (cudaFuncGetAttributes(&fa, adf_kernel_for(true, cfg->n_species == 1)) != cudaSuccess ||
+        cudaFuncGetAttributes(&fb, adf_kernel_for(false, cfg->n_species == 1)) != cudaSuccess)
       return cleanup(fail(MDS_ADF_ERR_CUDA, "cudaFuncGetAttributes failed: %s",
                           cudaGetErrorString(cudaGetLastError())));
     h->smem_limit = (size_t)prop.sharedMemPerBlockOptin - std::max(fa.sharedSizeBytes, fb.sharedSizeBytes);
