@@ -504,30 +504,30 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
 
 // ---- cell build: count + rank, scan, scatter (one configuration = one segment) ----------------
 
+// blockIdx.y walks the configurations, the x dimension the atoms of one (no integer division)
 __global__ void adf_cell_count_kernel(const float* __restrict__ pos, int n_atoms, int n_frames,
                                       AdfGrid g, uint32_t* __restrict__ cell_cnt,
                                       uint32_t* __restrict__ cell_id, uint32_t* __restrict__ rank,
                                       uint32_t* __restrict__ frame_flags) {
-  const size_t total = (size_t)n_atoms * n_frames;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int f = (int)(idx / n_atoms);
-    const float x = pos[3 * idx], y = pos[3 * idx + 1], z = pos[3 * idx + 2];
-    uint32_t wb = mds::window_bits(x, g.box[0]) | mds::window_bits(y, g.box[1]) |
-                  mds::window_bits(z, g.box[2]);  // bit0: outside window A, bit1: outside window B
-    uint32_t bits = wb << 1;
-    if (fabsf(x) > 8.0f * g.box[0] || fabsf(y) > 8.0f * g.box[1] || fabsf(z) > 8.0f * g.box[2])
-      bits |= ADF_FRAME_FAR;
-    // one atomic per warp and configuration instead of one per atom
-    const unsigned active = __activemask();
-    const unsigned peers = __match_any_sync(active, f);
-    bits = __reduce_or_sync(peers, bits);
-    if (bits && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31) &&
-        (frame_flags[f] & bits) != bits)
-      atomicOr(frame_flags + f, bits);
-    const int c = mds::cell_of(x, y, z, g);
-    cell_id[idx] = (uint32_t)c;
-    rank[idx] = atomicAdd(cell_cnt + (size_t)f * (g.nc + 1) + c, 1u);
+  for (int f = blockIdx.y; f < n_frames; f += gridDim.y) {
+    const size_t base = (size_t)f * n_atoms;
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_atoms; a += gridDim.x * blockDim.x) {
+      const size_t idx = base + a;
+      const float x = pos[3 * idx], y = pos[3 * idx + 1], z = pos[3 * idx + 2];
+      uint32_t wb = mds::window_bits(x, g.box[0]) | mds::window_bits(y, g.box[1]) |
+                    mds::window_bits(z, g.box[2]);  // bit0: outside window A, bit1: outside window B
+      uint32_t bits = wb << 1;
+      if (fabsf(x) > 8.0f * g.box[0] || fabsf(y) > 8.0f * g.box[1] || fabsf(z) > 8.0f * g.box[2])
+        bits |= ADF_FRAME_FAR;
+      // one atomic per warp instead of one per atom (all lanes of a warp are in configuration f)
+      const unsigned act = __activemask();
+      bits = __reduce_or_sync(act, bits);
+      if (bits && (int)(threadIdx.x & 31) == __ffs(act) - 1 && (frame_flags[f] & bits) != bits)
+        atomicOr(frame_flags + f, bits);
+      const int c = mds::cell_of(x, y, z, g);
+      cell_id[idx] = (uint32_t)c;
+      rank[idx] = atomicAdd(cell_cnt + (size_t)f * (g.nc + 1) + c, 1u);
+    }
   }
 }
 
@@ -562,15 +562,16 @@ __global__ void adf_cell_scatter_kernel(const float* __restrict__ pos,
                                         const uint32_t* __restrict__ cell_id,
                                         const uint32_t* __restrict__ rank,
                                         float4* __restrict__ sorted) {
-  const size_t total = (size_t)n_atoms * n_frames;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const size_t f = idx / n_atoms;
-    const int a = (int)(idx - f * n_atoms);
-    const uint32_t slot = cell_off[f * (nc + 1) + cell_id[idx]] + rank[idx];
-    // w carries the species (3 bits) and the cell id above it (< 2^21 cells)
-    sorted[f * n_atoms + slot] = make_float4(pos[3 * idx], pos[3 * idx + 1], pos[3 * idx + 2],
-                                             __int_as_float((int)species[a] | ((int)cell_id[idx] << 3)));
+  for (int f = blockIdx.y; f < n_frames; f += gridDim.y) {
+    const size_t base = (size_t)f * n_atoms;
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_atoms; a += gridDim.x * blockDim.x) {
+      const size_t idx = base + a;
+      const uint32_t cell = cell_id[idx];
+      const uint32_t slot = cell_off[(size_t)f * (nc + 1) + cell] + rank[idx];
+      // w carries the species (3 bits) and the cell id above it (< 2^21 cells)
+      sorted[base + slot] = make_float4(pos[3 * idx], pos[3 * idx + 1], pos[3 * idx + 2],
+                                        __int_as_float((int)species[a] | ((int)cell << 3)));
+    }
   }
 }
 
@@ -720,12 +721,13 @@ int run_batch_once(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) 
   const int grid = std::max(1, (int)std::min<unsigned long long>((unsigned long long)h->grid, items));
   int64_t far = 0;
   if (h->use_cells) {
-    const size_t total = (size_t)n_frames * (size_t)h->n_atoms;
     const int nc = h->cells.nc;
     ADF_CUDA_TRY(cudaMemsetAsync(h->d_flags, 0, sizeof(uint32_t) * (size_t)n_frames, h->stream));
     ADF_CUDA_TRY(cudaMemsetAsync(h->d_cell_off, 0, sizeof(uint32_t) * (size_t)n_frames * (nc + 1),
                                  h->stream));
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 16);
+    const int bx = (int)std::min<int64_t>((h->n_atoms + 255) / 256, (int64_t)h->sm_count * 16);
+    const int by = std::max(1, std::min({n_frames, 65535, (h->sm_count * 16 + bx - 1) / bx}));
+    const dim3 blocks((unsigned)bx, (unsigned)by);
     adf_cell_count_kernel<<<blocks, 256, 0, h->stream>>>(d_xyz, (int)h->n_atoms, n_frames, h->cells,
                                                          h->d_cell_off, h->d_cell_id, h->d_rank,
                                                          h->d_flags);
