@@ -53,11 +53,14 @@ int fail(int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                      \
   } while (0)
 
-constexpr int ADF_WARPS = 8;
-constexpr int ADF_THREADS = ADF_WARPS * 32;
+// CTA shapes: 8 warps (5 CTAs per SM) by default; 4 warps (10 CTAs per SM) when combinations x bins
+// is small — twice as many CTA-private histograms per SM halve the retries of the float64
+// compare-and-swap atomics (one species, 500 bins: 8.4 instead of 9.7 ms on the 100k-atom LJ
+// fluid; four combinations: 1.93 instead of 1.78 ms, hence the threshold).
+constexpr int CENTRES_PER_WARP = 16;  // consecutive centres of an item one warp works through
+constexpr int SMALL_HIST_LEN = 1024;  // combinations x bins up to which 4-warp CTAs are used
 constexpr int MAX_NB_LIMIT = MDS_ADF_MAX_NEIGHBOURS;
 constexpr int N_SPANS = 18;  // 9 cell rows x up to 2 pieces where the x window wraps
-constexpr int CENTRES_PER_ITEM = 128;
 constexpr int MAX_SPECIES = 8;
 // frame_flags bits written by the cell-count kernel
 constexpr uint32_t ADF_FRAME_FAR = 1u;    // a coordinate beyond 8 box lengths: cell search declines
@@ -374,8 +377,10 @@ __device__ __forceinline__ int build_span_table(int cell, const AdfGrid& g, cons
 //   norm that can pass the float16 test (x fastest), and only the 27 cells around the centre are
 //   searched; frames with a coordinate beyond 8 box lengths are flagged and left to the other form
 //   (the cell-assignment error bound of DESIGN.md §9 needs |x| <= 8 L).
-template <bool CELLS, bool ONE_SPECIES>
-__global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) {
+template <bool CELLS, bool ONE_SPECIES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 10 : 5) adf_kernel(const AdfParams p) {
+  constexpr int ADF_WARPS = WARPS, ADF_THREADS = WARPS * 32;
+  constexpr int CENTRES_PER_ITEM = WARPS * CENTRES_PER_WARP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* nb_vec = reinterpret_cast<float4*>(smem_raw);                       // [WARPS][max_nb]
   uint8_t* nb_sp = reinterpret_cast<uint8_t*>(nb_vec + ADF_WARPS * p.max_nb);  // [WARPS][max_nb]
@@ -417,7 +422,7 @@ __global__ void __launch_bounds__(ADF_THREADS, 5) adf_kernel(const AdfParams p) 
 
     // A warp takes consecutive centres of the sorted order: they mostly share a cell, and the span
     // table of the 27-cell stencil is rebuilt only when the cell changes.
-    constexpr int PER_WARP = CENTRES_PER_ITEM / ADF_WARPS;
+    constexpr int PER_WARP = CENTRES_PER_WARP;
     int prev_cell = -1, total = 0;
     for (int i = c0 + warp * PER_WARP; i < min(c1, c0 + (warp + 1) * PER_WARP); ++i) {
       int m = 0, sp_i;
@@ -596,6 +601,7 @@ struct mds_adf {
   int grid = 0;
   bool use_cells = false;
   AdfGrid cells;
+  int warps = 8;           // warps per CTA of the pair kernel (4 for small histograms)
   int max_nb = 0;          // capacity of a warp's neighbour list in the current configuration
   bool hist_in_smem = true;
   size_t smem_limit = 0;
@@ -660,15 +666,19 @@ int ensure_frames(mds_adf* h, int frames, bool staging) {
 }
 
 size_t smem_for(const mds_adf* h, int max_nb, bool hist_in_smem) {
-  return (size_t)ADF_WARPS * (size_t)max_nb * (sizeof(float4) + 1) +
+  return (size_t)h->warps * (size_t)max_nb * (sizeof(float4) + 1) +
          (hist_in_smem ? sizeof(double) * (size_t)h->n_combos * h->nbins : 0) +
          sizeof(float) * ((size_t)h->nbins + 1);
 }
 
 typedef void (*adf_kernel_t)(const AdfParams);
-adf_kernel_t adf_kernel_for(bool cells, bool one_species) {
-  if (cells) return one_species ? adf_kernel<true, true> : adf_kernel<true, false>;
-  return one_species ? adf_kernel<false, true> : adf_kernel<false, false>;
+adf_kernel_t adf_kernel_for(bool cells, bool one_species, int warps) {
+  if (warps == 4) {
+    if (cells) return one_species ? adf_kernel<true, true, 4> : adf_kernel<true, false, 4>;
+    return one_species ? adf_kernel<false, true, 4> : adf_kernel<false, false, 4>;
+  }
+  if (cells) return one_species ? adf_kernel<true, true, 8> : adf_kernel<true, false, 8>;
+  return one_species ? adf_kernel<false, true, 8> : adf_kernel<false, false, 8>;
 }
 
 // shared-memory layout, launch attributes and grid for a neighbour-list capacity
@@ -687,13 +697,13 @@ int configure(mds_adf* h, int max_nb) {
   const bool one = h->n_species == 1;
   int per_sm = 1 << 30;
   for (int cells = 0; cells < 2; ++cells) {
-    adf_kernel_t k = adf_kernel_for(cells != 0, one);
+    adf_kernel_t k = adf_kernel_for(cells != 0, one, h->warps);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_limit) !=
         cudaSuccess)
       return fail(MDS_ADF_ERR_CUDA, "cudaFuncSetAttribute failed: %s",
                   cudaGetErrorString(cudaGetLastError()));
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, ADF_THREADS, bytes) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, h->warps * 32, bytes) != cudaSuccess ||
         n < 1)
       return fail(MDS_ADF_ERR_CUDA, "the ADF kernel does not fit on an SM");
     per_sm = std::min(per_sm, n);
@@ -739,7 +749,7 @@ int run_batch_once(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) 
     p.cell_off = h->d_cell_off;
     p.frame_flags = h->d_flags;
     p.grid = h->cells;
-    adf_kernel_for(true, h->n_species == 1)<<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
+    adf_kernel_for(true, h->n_species == 1, h->warps)<<<grid, h->warps * 32, h->smem_bytes, h->stream>>>(p);
     ADF_CUDA_TRY(cudaGetLastError());
     h->launches += 4;
     h->h_flags.resize((size_t)n_frames);
@@ -750,12 +760,12 @@ int run_batch_once(mds_adf* h, const float* d_xyz, int n_frames, double* d_out) 
     if (far) {  // configurations with a coordinate beyond 8 box lengths: all-atoms search
       ADF_CUDA_TRY(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long), h->stream));
       p.only_flagged = 1;
-      adf_kernel_for(false, h->n_species == 1)<<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
+      adf_kernel_for(false, h->n_species == 1, h->warps)<<<grid, h->warps * 32, h->smem_bytes, h->stream>>>(p);
       ADF_CUDA_TRY(cudaGetLastError());
       h->launches += 1;
     }
   } else {
-    adf_kernel_for(false, h->n_species == 1)<<<grid, ADF_THREADS, h->smem_bytes, h->stream>>>(p);
+    adf_kernel_for(false, h->n_species == 1, h->warps)<<<grid, h->warps * 32, h->smem_bytes, h->stream>>>(p);
     ADF_CUDA_TRY(cudaGetLastError());
     h->launches += 1;
   }
@@ -876,8 +886,11 @@ int mds_adf_create(mds_adf_t** out, const mds_adf_config* cfg) {
   {
     // dynamic shared memory available to the kernels: the opt-in maximum minus their static part
     cudaFuncAttributes fa, fb;
-    if (cudaFuncGetAttributes(&fa, adf_kernel_for(true, cfg->n_species == 1)) != cudaSuccess ||
-        cudaFuncGetAttributes(&fb, adf_kernel_for(false, cfg->n_species == 1)) != cudaSuccess)
+    h->warps = h->n_combos * h->nbins <= SMALL_HIST_LEN ? 4 : 8;
+    const char* wenv = getenv("MDS_ADF_WARPS");
+    if (wenv && (atoi(wenv) == 4 || atoi(wenv) == 8)) h->warps = atoi(wenv);
+    if (cudaFuncGetAttributes(&fa, adf_kernel_for(true, cfg->n_species == 1, h->warps)) != cudaSuccess ||
+        cudaFuncGetAttributes(&fb, adf_kernel_for(false, cfg->n_species == 1, h->warps)) != cudaSuccess)
       return cleanup(fail(MDS_ADF_ERR_CUDA, "cudaFuncGetAttributes failed: %s",
                           cudaGetErrorString(cudaGetLastError())));
     h->smem_limit = (size_t)prop.sharedMemPerBlockOptin - std::max(fa.sharedSizeBytes, fb.sharedSizeBytes);
@@ -967,7 +980,10 @@ int mds_adf_create(mds_adf_t** out, const mds_adf_config* cfg) {
   p.pair_tests = h->d_counters + 2;
   p.status = h->d_status;
   p.n_atoms = (int)n_atoms;
-  p.items_per_frame = (int)((n_atoms + CENTRES_PER_ITEM - 1) / CENTRES_PER_ITEM);
+  {
+    const int64_t per_item = (int64_t)h->warps * CENTRES_PER_WARP;
+    p.items_per_frame = (int)((n_atoms + per_item - 1) / per_item);
+  }
   p.nbins = h->nbins;
   p.n_combos = h->n_combos;
   p.norm_power = h->norm_power;
