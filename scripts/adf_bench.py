@@ -43,9 +43,12 @@ def main():
             h.compute_device(pos_d, out=out)
             times.append(h.stats().kernel_ms)
         st = h.stats()
-        host_t = time.perf_counter()
-        h.compute(sysm.positions)
-        host_ms = (time.perf_counter() - host_t) * 1e3
+        host_ms = None
+        for _ in range(3):  # the first call also allocates the staging buffers
+            host_t = time.perf_counter()
+            h.compute(sysm.positions)
+            dt = (time.perf_counter() - host_t) * 1e3
+            host_ms = dt if host_ms is None else min(host_ms, dt)
     triples_per_call = t0
     ms = float(np.median(times))
     small = synthetic.nacl_melt(args.cpu_atoms_cells, 1, seed=3)
@@ -61,7 +64,7 @@ def main():
         "triples_per_s": triples_per_call / (ms * 1e-3),
         "allatoms_equivalent_pair_tests_per_s": args.frames * sysm.n_atoms ** 2 / (ms * 1e-3),
         "host_call_ms": host_ms, "max_neighbours": st.max_neighbours, "cells": list(st.cells),
-        "pair_tests_per_call": st.pair_tests / (args.repeats + 2),
+        "pair_tests_per_call": st.pair_tests / (args.repeats + 4),
         "cpu_oracle": {"atoms": small.n_atoms, "seconds": cpu_s,
                        "triples_per_s": float(cpu_triples) / cpu_s, "kind": "port (NumPy)"},
         "checksum": float(raw.sum())}))
