@@ -21,7 +21,7 @@ namespace mds {
 // INNER one — frame-major input: outer = frame, inner = packed slot; atom-major input: outer =
 // packed slot, inner = frame (consecutive threads walk the frames of one atom: contiguous 12 B
 // records in the source).
-__global__ void __launch_bounds__(256) rdf_pack_kernel(const PackParams p) {
+__global__ void __launch_bounds__(256, 8) rdf_pack_kernel(const PackParams p) {
   const bool atom_major = p.layout == MDS_LAYOUT_ATOM_MAJOR_XYZ;
   const long long inner_n = atom_major ? p.n_frames : (long long)p.n_packed;
   const long long outer_n = atom_major ? (long long)p.n_packed : p.n_frames;
