@@ -42,10 +42,12 @@ COLUMN_NAMES = {
 
 class LAMMPSTrajectoryFileOracle(FileProcessor):
     def __init__(self, file_path, trajectory_is_sorted_by_ids: bool = False,
-                 chunk_configurations: int = 64):
+                 chunk_configurations: int = 64, custom_data_map: dict = None):
         self.file_path = str(pathlib.Path(file_path))
         self.trajectory_is_sorted_by_ids = trajectory_is_sorted_by_ids
         self.chunk_configurations = chunk_configurations
+        self.column_names = dict(COLUMN_NAMES)
+        self.column_names.update({k: list(v) for k, v in (custom_data_map or {}).items()})
         self._mdata = None
         self._layout = None
 
@@ -86,7 +88,7 @@ class LAMMPSTrajectoryFileOracle(FileProcessor):
         for i, name in enumerate(first[:, species_col]):
             species.setdefault(str(name), []).append(i)
         props = {}
-        for prop, names in COLUMN_NAMES.items():
+        for prop, names in self.column_names.items():
             if all(n in columns for n in names):
                 props[prop] = [columns.index(n) for n in names]
         self._layout = dict(n_particles=n_particles, n_configs=n_configs, columns=columns,

@@ -15,6 +15,7 @@ dtype float32), hex encoded.
 
 Runs only where /root/reference exists.  Re-run:  python tests/golden/make_reader_golden.py
 """
+import copy
 import importlib.util
 import json
 import os
@@ -35,7 +36,17 @@ FILES = [
     # a property the reference does not know ("Z:I:1") in front of known ones: its column counter
     # does not advance (extxyz_files.py:279-288), so "pos" is read from columns 1-3 — recorded as is
     ("extxyz_unknown_property.extxyz", "extxyz", {}),
+    # reader keyword arguments: rows taken in file order; user-defined properties
+    ("lammps_golden.lammpstraj", "lammps", {"trajectory_is_sorted_by_ids": True}),
+    ("lammps_unsorted_types.lammpstraj", "lammps",
+     {"custom_data_map": {"Scaled_Charge_Pair": ["q", "xs"]}}),
+    ("extxyz_custom_property.extxyz", "extxyz", {"custom_data_map": {"Reduced_Momentum": "redmom"}}),
 ]
+
+
+def case_key(fname, kwargs):
+    """Key of a case in reader_golden.json: the file name, plus its keyword arguments if any."""
+    return fname if not kwargs else fname + "?" + json.dumps(kwargs, sort_keys=True)
 
 
 def load_reference():
@@ -111,9 +122,13 @@ def main():
     for fname, kind, kwargs in FILES:
         path = os.path.join(HERE, fname)
         cls = lammps.LAMMPSTrajectoryFile if kind == "lammps" else extxyz.EXTXYZFile
-        golden[fname] = run(cls(path, **kwargs))
-        print(fname, golden[fname]["n_configurations"], golden[fname]["box_l"],
-              golden[fname]["sample_rate"], [s["name"] for s in golden[fname]["species"]])
+        key = case_key(fname, kwargs)
+        # the reference writes column indices into the user's custom_data_map lists: give it a copy
+        golden[key] = run(cls(path, **copy.deepcopy(kwargs)))
+        golden[key]["file"] = fname
+        golden[key]["kwargs"] = kwargs
+        print(key, golden[key]["n_configurations"], golden[key]["box_l"],
+              golden[key]["sample_rate"], [s["name"] for s in golden[key]["species"]])
     with open(os.path.join(HERE, "reader_golden.json"), "w") as fh:
         json.dump(golden, fh, indent=1)
         fh.write("\n")

@@ -45,12 +45,19 @@ def _read_all(proc):
     return md, data
 
 
-@pytest.mark.parametrize("which", ["product", "oracle"])
-@pytest.mark.parametrize("fname", sorted(REFERENCE))
-def test_reader_equals_the_reference_reader(fname, which):
-    want = REFERENCE[fname]
+def _make(case_key, which):
+    """The reader under test for a case of reader_golden.json (file name + keyword arguments)."""
+    want = REFERENCE[case_key]
+    fname, kwargs = want.get("file", case_key), dict(want.get("kwargs", {}))
     cls = READERS[os.path.splitext(fname)[1]][which]
-    md, data = _read_all(cls(os.path.join(GOLDEN, fname)))
+    return cls(os.path.join(GOLDEN, fname), **kwargs), want, fname
+
+
+@pytest.mark.parametrize("which", ["product", "oracle"])
+@pytest.mark.parametrize("case_key", sorted(REFERENCE))
+def test_reader_equals_the_reference_reader(case_key, which):
+    proc, want, fname = _make(case_key, which)
+    md, data = _read_all(proc)
     assert md.n_configurations == want["n_configurations"]
     assert [float(v) for v in md.box_l] == want["box_l"]
     assert md.sample_rate == want["sample_rate"]
@@ -71,10 +78,10 @@ def test_reader_equals_the_reference_reader(fname, which):
             assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (fname, sp, prop)
 
 
-@pytest.mark.parametrize("fname", sorted(k for k in REFERENCE if k.endswith(".extxyz")))
-def test_species_line_indices_equal_the_reference(fname):
-    proc = EXTXYZFile(os.path.join(GOLDEN, fname))
-    assert proc._analyse()["species"] == REFERENCE[fname]["species_line_idx"]
+@pytest.mark.parametrize("case_key", sorted(k for k in REFERENCE if ".extxyz" in k))
+def test_species_line_indices_equal_the_reference(case_key):
+    proc, want, _ = _make(case_key, "product")
+    assert proc._analyse()["species"] == want["species_line_idx"]
 
 
 @pytest.mark.parametrize("case", [
