@@ -217,3 +217,18 @@ def test_molecules_true_reads_molecule_datasets(project, tmp_path):
     want = rdf_oracle.normalise(counts, ["NaCl"], [n_mol], sysm.box, 6.0, 12, length_unit=1e-10)
     assert np.allclose(np.array(comp["NaCl_NaCl"]["y"])[1:], np.array(want["NaCl_NaCl"]["y"])[1:],
                        rtol=1e-12)
+
+
+def test_unit_systems_equal_the_reference():
+    """tests/golden/units_golden.json is the reference's units_dict (make_units_golden.py)."""
+    import dataclasses
+    from mdsuite_b200.calculators import rdf_postprocessing as post
+    from mdsuite_b200.utils import units
+    with open(os.path.join(os.path.dirname(__file__), "golden", "units_golden.json")) as fh:
+        want = json.load(fh)
+    assert sorted(units.units_dict) == sorted(want["systems"])
+    for name, ref in want["systems"].items():
+        mine = dict(dataclasses.asdict(units.units_dict[name]), volume=units.units_dict[name].volume)
+        assert mine == ref, name
+    assert post.BOLTZMANN_SI == want["boltzmann_constant"]
+    assert post.GOLDEN_RATIO == want["golden_ratio"]
