@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MDS_RDF_ABI_VERSION 3
+#define MDS_RDF_ABI_VERSION 4
 
 #if defined(MDS_BUILD) && defined(__GNUC__)
 #define MDS_API __attribute__((visibility("default")))
@@ -102,10 +102,16 @@ typedef struct mds_rdf_stats {
   float pair_kernel_ms;        /* sum of pair-kernel launch durations since the previous stats_get */
   int32_t pair_kernel_launches; /* pair-kernel launches since the previous stats_get */
   int32_t dense;               /* 1: branch-free binning (most pairs inside the cutoff) */
-  int32_t frames_far;          /* cell path: frames with a coordinate beyond 8 box lengths, which
-                                  were handed to the all-pairs kernel */
+  int32_t frames_far;          /* cell path: frames handed to the all-pairs kernel — a coordinate
+                                  beyond 8 box lengths, or a cell too crowded to stage */
   int32_t cells[3];            /* cell path: cells per dimension (0 on the all-pairs path) */
   int32_t item_shards;         /* shard count set with mds_rdf_set_item_shard (1: none) */
+  int32_t cell_stencil[3];     /* cell path: stencil half-widths — the cell kernel tests atoms whose
+                                  cells are at most this many cells apart (1 or 2 per dimension) */
+  int32_t reserved0;
+  double pairs_tested;         /* distances actually computed: = pairs_evaluated on the all-pairs
+                                  path; on the cell path the kernel works on 64-atom chunks and tests
+                                  a superset of the candidate pairs (cell kernel launches only) */
 } mds_rdf_stats;
 
 typedef struct mds_rdf mds_rdf_t;

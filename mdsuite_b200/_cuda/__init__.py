@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # (make -C csrc checked; see rdf_common.cuh MDS_CHECKED)
 LIB_PATH = os.environ.get("MDS_RDF_LIB") or os.path.join(_HERE, "libmds_rdf.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MDS_OK = 0
 PARITY_SKIP_FIRST = 0x1
 PATH_ALLPAIRS = 0x2
@@ -80,6 +80,9 @@ class _Stats(ctypes.Structure):
         ("frames_far", ctypes.c_int32),
         ("cells", ctypes.c_int32 * 3),
         ("item_shards", ctypes.c_int32),
+        ("cell_stencil", ctypes.c_int32 * 3),
+        ("reserved0", ctypes.c_int32),
+        ("pairs_tested", ctypes.c_double),
     ]
 
 
@@ -104,6 +107,8 @@ class RDFStats:
     frames_far: int = 0
     cells: tuple = (0, 0, 0)
     item_shards: int = 1
+    cell_stencil: tuple = (0, 0, 0)
+    pairs_tested: float = 0.0
 
     @property
     def path_name(self) -> str:
@@ -336,7 +341,7 @@ class RDFHandle:
                         st.pairs_binned, st.frames_general_minimage, st.kernel_launches,
                         st.kernel_ms, st.submit_ms, st.n_pairs, st.nbins, st.sm_count, st.variant,
                         st.pair_kernel_ms, st.pair_kernel_launches, st.dense, st.frames_far,
-                        tuple(st.cells), st.item_shards)
+                        tuple(st.cells), st.item_shards, tuple(st.cell_stencil), st.pairs_tested)
 
     def threshold_table(self):
         """(edges[0..nbins] float32, s_cut): the squared-distance thresholds the kernels use."""

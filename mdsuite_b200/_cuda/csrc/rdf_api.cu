@@ -110,6 +110,9 @@ struct mds_rdf {
   bool dense = true;  // expected in-cutoff fraction is high: predicated binning
   int path = MDS_RDF_PATH_ALLPAIRS;
   mds::CellGrid grid = {0, 0, 0, 0, {0, 0, 0}};
+  int kcell[3] = {0, 0, 0};       // stencil half-widths of the cell path (cells per cutoff)
+  int cap_atoms = 0;              // positions a CTA of the cell kernel stages in shared memory
+  uint32_t crowded_limit = 0;     // atoms per cell above which a frame goes to the all-pairs kernel
   int64_t off_stride = 0;         // uint32 entries per frame of the cell-offset table
   uint32_t flush_threshold = 1u << 30;
   uint32_t shard_index = 0, shard_count = 1;  // item sharding (mds_rdf_set_item_shard)
@@ -129,9 +132,9 @@ struct mds_rdf {
   // cell-list path only
   float4* d_sorted[2] = {nullptr, nullptr};
   uint32_t* d_cell_off[2] = {nullptr, nullptr};
-  int2* d_pair_ab = nullptr;
+  int4* d_pair_ab = nullptr;
   unsigned long long* d_work64 = nullptr;    // ring of 64-bit work counters
-  unsigned long long* d_evaluated = nullptr; // candidate pairs distance-tested by the cell kernel
+  unsigned long long* d_evaluated = nullptr; // [2] pairs evaluated (candidates on the cell path) / tested
   unsigned long long* d_batch_far = nullptr; // [2] far frames of the batch in each buffer
   size_t raw_bytes = 0;
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
@@ -373,7 +376,7 @@ int process_batch_allpairs(mds_rdf* h, const float* d_xyz, int layout, int64_t f
                            int64_t n_frames, int64_t n_frames_total, int buf) {
   CUDA_TRY(cudaMemsetAsync(h->d_flags[buf], 0, sizeof(uint32_t) * (size_t)n_frames, h->s_compute));
   const mds::PackParams pp = pack_params(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf);
-  CUDA_TRY(mds::launch_pack(pp, h->s_compute));
+  CUDA_TRY(mds::launch_pack(pp, h->sm_count, h->s_compute));
   CUDA_TRY(mds::launch_count_general(h->d_flags[buf], (int)n_frames, h->d_general, nullptr,
                                      h->s_compute));
   h->launches += 2;
@@ -403,7 +406,8 @@ int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t fram
                         int64_t n_frames, int64_t n_frames_total, int buf) {
   CUDA_TRY(cudaMemsetAsync(h->d_flags[buf], 0, sizeof(uint32_t) * (size_t)n_frames, h->s_compute));
   const mds::PackParams pp = pack_params(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf);
-  CUDA_TRY(mds::launch_cell_build(pp, h->n_species, h->d_sorted[buf], h->s_compute));
+  CUDA_TRY(mds::launch_cell_build(pp, h->n_species, h->d_sorted[buf], h->crowded_limit, h->sm_count,
+                                  h->s_compute));
   CUDA_TRY(mds::launch_count_general(h->d_flags[buf], (int)n_frames, h->d_general,
                                      h->d_batch_far + buf, h->s_compute));
   h->launches += 4;
@@ -418,6 +422,8 @@ int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t fram
     cp.off_stride = h->off_stride;
     cp.frame_flags = h->d_flags[buf];
     cp.nx = h->grid.nx; cp.ny = h->grid.ny; cp.nz = h->grid.nz; cp.nc = h->grid.nc;
+    cp.kx = h->kcell[0]; cp.ky = h->kcell[1]; cp.kz = h->kcell[2];
+    cp.cap_atoms = h->cap_atoms;
     cp.pair_ab = h->d_pair_ab;
     cp.edges = h->d_edges;
     cp.counts = h->d_counts;
@@ -571,17 +577,17 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   h->inv_step_hi = (float)((double)h->nbins / (double)h->cutoff / (double)mds::kBinGuessBias);
 
   // ---- path: all-pairs tiles or cell list ------------------------------------------------
-  // Cell width >= 1.001 x cutoff, at least 3 cells per dimension so that the 27
-  // neighbours of a cell are distinct, at most 128 per dimension.
+  // The cell path needs >= 3 cutoff-sized (1.001 x cutoff) cells per dimension.
+  // Its grid is finer: K cells per cutoff length (K = 1 or 2 per dimension, the stencil
+  // half-width of rdf_cells.cu), at most 128 K per dimension — the bound the margin rests on.
   {
-    int n[3];
+    int n1[3];
     bool cell_ok = true;
     for (int k = 0; k < 3; ++k) {
-      const double w_min = (double)h->cutoff * 1.001;
-      n[k] = (int)std::min(128.0, std::floor((double)h->box[k] / w_min));
-      if (n[k] < 3) cell_ok = false;
+      n1[k] = (int)std::min(128.0, std::floor((double)h->box[k] / ((double)h->cutoff * 1.001)));
+      if (n1[k] < 3) cell_ok = false;
     }
-    const long long nc = cell_ok ? (long long)n[0] * n[1] * n[2] : 0;
+    const long long nc1 = cell_ok ? (long long)n1[0] * n1[1] * n1[2] : 0;
     const bool forced_cells = (cfg->flags & MDS_RDF_PATH_CELLLIST) != 0;
     const bool forced_all = (cfg->flags & MDS_RDF_PATH_ALLPAIRS) != 0;
     if (forced_cells && !cell_ok) {
@@ -591,15 +597,45 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
                   "(cutoff %g, box %g %g %g)", (double)cfg->cutoff, (double)cfg->box[0],
                   (double)cfg->box[1], (double)cfg->box[2]);
     }
-    // the cell kernel tests ~27/nc of all pairs at roughly half the all-pairs kernel's rate
-    const bool auto_cells = cell_ok && nc >= 64 && h->n_real >= 1024;
+    // the cell kernel tests a small fraction of all pairs at roughly half the all-pairs kernel's rate
+    const bool auto_cells = cell_ok && nc1 >= 64 && h->n_real >= 1024;
     h->path = (forced_cells || (!forced_all && auto_cells)) ? MDS_RDF_PATH_CELLLIST
                                                             : MDS_RDF_PATH_ALLPAIRS;
     if (h->path == MDS_RDF_PATH_CELLLIST) {
+      // Half-width cells test 15.6 instead of 27 cutoff-cell volumes per atom, but every row cell
+      // costs a fixed amount; below ~1.5 atoms of the most populous species per fine cell the
+      // classical grid wins (MDS_RDF_CELL_K = 1 | 2 | "kx,ky,kz" overrides).
+      int max_pcnt = 0;
+      for (int c : h->pcnt) max_pcnt = std::max(max_pcnt, c);
+      int K[3] = {2, 2, 2};
+      if ((double)max_pcnt / ((double)nc1 * 8.0) < 1.5) K[0] = K[1] = K[2] = 1;
+      if (const char* env = getenv("MDS_RDF_CELL_K")) {
+        int a = 0, b = 0, c = 0;
+        const int got = sscanf(env, "%d,%d,%d", &a, &b, &c);
+        if (got == 1) b = c = a;
+        if ((got == 1 || got == 3) && a >= 1 && a <= 2 && b >= 1 && b <= 2 && c >= 1 && c <= 2) {
+          K[0] = a; K[1] = b; K[2] = c;
+        }
+      }
+      int n[3];
+      for (int k = 0; k < 3; ++k) {
+        const double w_min = (double)h->cutoff * 1.001 / (double)K[k];
+        n[k] = (int)std::min(128.0 * K[k], std::floor((double)h->box[k] / w_min));
+        // (n1 >= 3 implies n >= 2 K + 1: the cells of a stencil are distinct)
+        h->kcell[k] = K[k];
+      }
+      const long long nc = (long long)n[0] * n[1] * n[2];
       h->grid.nx = n[0]; h->grid.ny = n[1]; h->grid.nz = n[2];
       h->grid.nc = (int)nc;
       for (int k = 0; k < 3; ++k) h->grid.box[k] = h->box[k];
       h->off_stride = (((int64_t)h->n_species * nc + 1) + 3) & ~3LL;
+      h->cap_atoms = 2048;
+      if (const char* env = getenv("MDS_RDF_CELL_CAP")) {
+        const int v = atoi(env);
+        if (v >= 256 && v <= mds::cells_max_cap()) h->cap_atoms = v;
+      }
+      // one row cell (+ its kx own-pencil neighbours) against one neighbour pencil must fit
+      h->crowded_limit = (uint32_t)(h->cap_atoms / (3 * K[0] + 2));
     }
     if (const char* env = getenv("MDS_RDF_FLUSH_THRESHOLD")) {
       const long long v = atoll(env);
@@ -614,7 +650,7 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   auto smem_need = [&](int pairs) {
     // the all-pairs kernel also serves the cell path's fallback launches: size for the larger
     const size_t a = mds::allpairs_smem_bytes(h->nbins, pairs, true);
-    return cells ? std::max(a, mds::cells_smem_bytes(h->nbins, pairs, true)) : a;
+    return cells ? std::max(a, mds::cells_smem_bytes(h->nbins, pairs, true, h->cap_atoms)) : a;
   };
   h->hist_in_smem = true;
   h->pair_group = h->n_pairs;
@@ -686,28 +722,36 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   const size_t n_counts = (size_t)h->n_pairs * (size_t)h->nbins;
   CREATE_TRY(cudaMalloc(&h->d_counts, n_counts * sizeof(unsigned long long)));
   CREATE_TRY(cudaMemset(h->d_counts, 0, n_counts * sizeof(unsigned long long)));
-  CREATE_TRY(cudaMalloc(&h->d_evaluated, sizeof(unsigned long long)));
-  CREATE_TRY(cudaMemset(h->d_evaluated, 0, sizeof(unsigned long long)));
+  CREATE_TRY(cudaMalloc(&h->d_evaluated, 2 * sizeof(unsigned long long)));
+  CREATE_TRY(cudaMemset(h->d_evaluated, 0, 2 * sizeof(unsigned long long)));
   CREATE_TRY(cudaMalloc(&h->d_general, 2 * sizeof(unsigned long long)));
   CREATE_TRY(cudaMemset(h->d_general, 0, 2 * sizeof(unsigned long long)));
   if (cells) {
-    // (row species, column species) of every pair.  For a != b either orientation counts the same
-    // pairs (full 27-cell shell); rows fill lane slots in groups of 8 (passes of 32), so the
-    // species whose average cell occupancy packs better becomes the row species
-    // (SPC water, 8 A cutoff: O 19 per cell -> 24 slots, H 38 -> 40 slots: H rows, -17 % work).
-    auto lane_efficiency = [&](int s) {
-      const double n = (double)h->pcnt[s] / (double)h->grid.nc;
-      if (n <= 0.0) return 0.0;
-      const double full = std::floor(n / 32.0) * 32.0;
-      const double slots = full + std::ceil((n - full) / 8.0) * 8.0;
-      return n / std::max(slots, 8.0);
-    };
-    std::vector<int2> ab;
+    // (row species, column species, x cells per staged segment) of every pair.  For a != b either
+    // orientation counts the same pairs (full shell); the more populous species takes the rows,
+    // so the less populous one is what a CTA stages 25-fold.  The segment length is the largest
+    // whose staged atoms — neighbour pencils incl. ghost cells + the row pencil — fill 3/4 of the
+    // CTA's capacity at average density; denser places are split by the kernel itself.
+    const int K0 = h->kcell[0], wy = 2 * h->kcell[1] + 1, wz = 2 * h->kcell[2] + 1;
+    std::vector<int4> ab;
     for (int a = 0; a < h->n_species; ++a)
-      for (int b = a; b < h->n_species; ++b)
-        ab.push_back(lane_efficiency(b) > lane_efficiency(a) ? make_int2(b, a) : make_int2(a, b));
-    CREATE_TRY(cudaMalloc(&h->d_pair_ab, ab.size() * sizeof(int2)));
-    CREATE_TRY(cudaMemcpy(h->d_pair_ab, ab.data(), ab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+      for (int b = a; b < h->n_species; ++b) {
+        const int row = (h->pcnt[b] > h->pcnt[a]) ? b : a, col = (row == a) ? b : a;
+        const double rho_r = (double)h->pcnt[row] / (double)h->grid.nc;
+        const double rho_c = (double)h->pcnt[col] / (double)h->grid.nc;
+        const int P = (a == b) ? h->kcell[2] * wy + h->kcell[1] : wy * wz;
+        const int seg_max = std::min(h->grid.nx, mds::cells_max_seg());
+        int seg = 1;
+        for (int sg = 1; sg <= seg_max; ++sg) {
+          const double staged = P * (sg + 2 * K0) * rho_c + (sg + K0) * rho_r;
+          if (staged <= 0.75 * h->cap_atoms && (sg + 2 * K0) * P <= 1024) seg = sg;
+        }
+        const int pieces = (h->grid.nx + seg - 1) / seg;  // even pieces
+        seg = (h->grid.nx + pieces - 1) / pieces;
+        ab.push_back(make_int4(row, col, seg, 0));
+      }
+    CREATE_TRY(cudaMalloc(&h->d_pair_ab, ab.size() * sizeof(int4)));
+    CREATE_TRY(cudaMemcpy(h->d_pair_ab, ab.data(), ab.size() * sizeof(int4), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMalloc(&h->d_work64, sizeof(unsigned long long) * WORK_RING));
     CREATE_TRY(cudaMemset(h->d_work64, 0, sizeof(unsigned long long) * WORK_RING));
     CREATE_TRY(cudaMalloc(&h->d_batch_far, 2 * sizeof(unsigned long long)));
@@ -932,7 +976,7 @@ int mds_rdf_reset(mds_rdf_t* h) {
   CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, bytes, h->s_compute));
   CUDA_TRY(cudaMemsetAsync(h->d_general, 0, 2 * sizeof(unsigned long long), h->s_compute));
   if (h->d_evaluated)
-    CUDA_TRY(cudaMemsetAsync(h->d_evaluated, 0, sizeof(unsigned long long), h->s_compute));
+    CUDA_TRY(cudaMemsetAsync(h->d_evaluated, 0, 2 * sizeof(unsigned long long), h->s_compute));
   h->frames_done = 0;
   h->launches = 0;
   h->timing_valid = false;
@@ -971,9 +1015,12 @@ int mds_rdf_stats_get(mds_rdf_t* h, mds_rdf_stats* out) {
     // counted on the device: reference pairs of every (item, frame) unit the all-pairs kernel
     // processed (all of them, or this handle's item shard, or the far frames handed over by the
     // cell path) + the candidate pairs the cell kernel tested
-    unsigned long long ev = 0;
-    CUDA_TRY(cudaMemcpy(&ev, h->d_evaluated, sizeof(ev), cudaMemcpyDeviceToHost));
-    out->pairs_evaluated = (double)ev;
+    unsigned long long ev[2] = {0, 0};
+    CUDA_TRY(cudaMemcpy(ev, h->d_evaluated, sizeof(ev), cudaMemcpyDeviceToHost));
+    out->pairs_evaluated = (double)ev[0];
+    // the cell kernel tests whole 64-column chunks against contiguous row ranges: a superset of
+    // the candidate pairs (rdf_cells.cu)
+    out->pairs_tested = h->path == MDS_RDF_PATH_CELLLIST ? (double)ev[1] : (double)ev[0];
   }
   out->pairs_allpairs_equiv /= (double)h->shard_count;
   out->pairs_binned = binned;
@@ -1002,6 +1049,7 @@ int mds_rdf_stats_get(mds_rdf_t* h, mds_rdf_stats* out) {
   out->cells[0] = h->grid.nx;
   out->cells[1] = h->grid.ny;
   out->cells[2] = h->grid.nz;
+  for (int k = 0; k < 3; ++k) out->cell_stencil[k] = h->kcell[k];
   out->item_shards = (int32_t)h->shard_count;
   return MDS_OK;
 }

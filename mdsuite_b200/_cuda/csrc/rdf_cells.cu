@@ -1,47 +1,52 @@
 // Cell-list RDF path for sm_100a (north-star kernel (b)): large N, cutoff much smaller than the
 // box.  The reference has no such path — it evaluates all N(N-1)/2 pairs of every frame
-// (SURVEY.md §5 "Long-context"); this path evaluates only pairs of atoms in adjacent cells and
+// (SURVEY.md §5 "Long-context"); this path evaluates only pairs of atoms in nearby cells and
 // must return the SAME integer histogram, bit for bit.
 //
 // Why it is exact: a cell list only decides WHICH pairs are distance-tested.  Every tested pair
 // runs the reference's float32 arithmetic on the raw coordinates (rdf_common.cuh; reference
 // utils/linalg.py:84-99, calculators/radial_distribution_function.py:667-689), and the squared
-// distance is symmetric in (i, j) bit for bit.  The grid is conservative: cell width >= 1.001 x
-// cutoff, so for |coordinate| <= 8 box lengths every pair the reference would bin sits in
-// adjacent cells (DESIGN.md §9 derives the margin).  Frames with coordinates further out are
-// flagged by the pack kernel and handed to the all-pairs kernel instead.
+// distance is symmetric in (i, j) bit for bit.  The grid is conservative: K cells span at least
+// 1.001 x cutoff in every dimension (K = 1 or 2, the stencil half-width), so for |coordinate| <=
+// 8 box lengths every pair the reference would bin sits in cells at most K apart (DESIGN.md §9
+// derives the margin).  Frames with coordinates further out are flagged by the pack kernel and
+// handed to the all-pairs kernel instead.
 //
 // Per batch of frames:
 //   rdf_pack_kernel        (rdf_pack.cu) raw xyz -> quad-block positions; per-(frame, species,
 //                          cell) counts and ranks with one global atomic per atom; frame flags
-//   rdf_cell_scan_kernel   exclusive scan of the counts of a frame -> cell offsets (one CTA/frame)
+//   rdf_cell_scan_kernel   exclusive scan of the counts of a frame -> cell offsets (one CTA/frame);
+//                          flags frames with an absurdly crowded cell for the all-pairs kernel
 //   rdf_cell_scatter_kernel counting-sort scatter -> atoms ordered by (species, cell), x fastest
-//   rdf_cells_kernel       persistent warps; one work item = (frame, species pair, cell): the
-//                          cell's atoms are register rows (8 row groups x 4 column phases per
-//                          warp, R = ceil(n/8) rows per lane), the neighbour cells' atoms are a
-//                          flattened column stream (x-adjacent cells are contiguous in the sorted
-//                          array, so 27 cells are <= 18 spans) staged 32 atoms at a time through
-//                          a per-warp double-buffered shared tile; binning as in the all-pairs
-//                          kernel (threshold table + ATOMS.POPC.INC, branch-free with a sink slot).
+//   rdf_cells_kernel       persistent CTAs; one work item = (frame, species pair, pencil of cells
+//                          along x).  See "the pair kernel" below.
 #include "rdf_common.cuh"
 #include "rdf_launch.h"
 #include "mds_rdf.h"
 
 namespace mds {
 
-// Exclusive scan of the n_keys counts of one frame (in place) + total at [n_keys].
+// Exclusive scan of the n_keys counts of one frame (in place) + total at [n_keys].  Also the
+// largest count of the frame: above `crowded_limit` the pencil kernel could not stage even one
+// row cell with one neighbour pencil, so the frame goes to the all-pairs kernel (MDS_FRAME_FAR).
 __global__ void __launch_bounds__(1024) rdf_cell_scan_kernel(uint32_t* cell_off, int64_t off_stride,
-                                                             int n_keys) {
+                                                             int n_keys, uint32_t* frame_flags,
+                                                             uint32_t crowded_limit) {
   uint32_t* a = cell_off + (long long)blockIdx.x * off_stride;
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t chunk_total;
+  __shared__ uint32_t s_max;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t carry = 0;
+  if (threadIdx.x == 0) s_max = 0u;
+  uint32_t carry = 0, mx = 0;
   for (int base = 0; base < n_keys; base += 4096) {
     const int i0 = base + threadIdx.x * 4;
     uint32_t v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n_keys) ? a[i0 + k] : 0u;
+    for (int k = 0; k < 4; ++k) {
+      v[k] = (i0 + k < n_keys) ? a[i0 + k] : 0u;
+      mx = max(mx, v[k]);
+    }
     const uint32_t t = v[0] + v[1] + v[2] + v[3];
     uint32_t inc = t;
 #pragma unroll
@@ -72,7 +77,13 @@ __global__ void __launch_bounds__(1024) rdf_cell_scan_kernel(uint32_t* cell_off,
     carry += chunk_total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) a[n_keys] = carry;
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0 && mx > crowded_limit) atomicMax(&s_max, mx);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a[n_keys] = carry;
+    if (s_max > crowded_limit) atomicOr(frame_flags + blockIdx.x, MDS_FRAME_FAR);
+  }
 }
 
 __global__ void __launch_bounds__(256) rdf_cell_scatter_kernel(const PackParams p,
@@ -92,123 +103,143 @@ __global__ void __launch_bounds__(256) rdf_cell_scatter_kernel(const PackParams 
 }
 
 // ---- the pair kernel -------------------------------------------------------------------------
+//
+// Geometry.  Cells are at least 1.001 cutoff / K wide (K = kx, ky, kz per dimension), so the
+// partners of an atom lie in the (2kx+1)(2ky+1)(2kz+1) cells around its own.  With K = 2 that
+// block has 125/8 = 15.6 times the volume of a cutoff-sized cell instead of the 27 of the
+// classical K = 1 scheme: 42 % fewer candidate pairs for the same binned pairs.  Small cells only
+// pay if few atoms can share one column set efficiently, which decides the layout:
+//
+// * One work item is a PENCIL: the nx cells with the same (y, z).  The atoms of a pencil are
+//   contiguous in the sorted array (x fastest), and so are those of each of the (2ky+1)(2kz+1)
+//   pencils around it (same-species pairs: the half shell, kz (2ky+1) + ky pencils, plus the
+//   pencil itself for the +x half).
+// * The CTA stages those pencils ONCE in shared memory, re-ordered slab by slab: slab c holds the
+//   atoms of x-cell c of all neighbour pencils.  The column set of row cell cx is then ONE
+//   contiguous range, slabs cx-kx .. cx+kx (ghost slabs at both ends take care of the periodic
+//   wrap), found with two table reads.  Every atom is read from global memory once per
+//   neighbouring pencil (25 times per frame for K = 2) instead of once per neighbouring cell.
+// * Columns sit on lanes, rows are broadcast: a warp takes one row cell, each lane loads two
+//   columns of the range into registers (64 per chunk) and loops over the n atoms of the cell,
+//   one LDS.128 per row with every lane on the same address; each (row, two columns) goes through
+//   the packed FADD2 / FMUL2 sequence.  A row cell with 3 atoms keeps all 32 lanes busy, which a
+//   rows-in-registers layout cannot do.
+// * Staging is a table of (slab, pencil) entries: counts from the cell-offset table, one
+//   block-wide exclusive scan, then 16-byte cp.async copies that are all in flight at once.
+// * Same-species items: the own cell's atoms come first in the column range; the col > row mask
+//   of that block is applied by poisoning column r with NaN when row r is reached (rows are
+//   visited in increasing order, and column r is not needed by any later row).
+// * Binning as in the all-pairs kernel: threshold table + ATOMS.POPC.INC, branch-free, sink slot.
+//
+// Shared memory per CTA is fixed (cap_atoms staged positions); a pencil is processed in x
+// segments of at most `seg` row cells (chosen per species pair at handle creation from the
+// average density) and, where a frame is denser than average, in fewer cells or with a subset of
+// the neighbour pencils per pass — the kernel measures every candidate segment against the
+// capacity before staging it, so no density distribution can overflow the buffers.
 
 constexpr int CELL_THREADS = 256;
 constexpr int CELL_WARPS = CELL_THREADS / 32;
-constexpr int CH = 32;         // column atoms per staged chunk: CH / 32 float4 loads per lane
-constexpr int CPL = CH / 32;   // columns staged per lane and chunk
-constexpr int MAX_SPANS = 20;  // >= 18 (9 cell rows x 2 pieces when the x window wraps)
-constexpr int RG = 8;          // row groups per warp (lanes with the same lane % RG share rows)
-constexpr int PH = 32 / RG;    // column phases per warp
-constexpr int RMAX = 4;        // rows per lane: one pass covers RG * RMAX = 32 rows of a cell
+constexpr int MAXW = 72;        // x cells of a staged segment incl. ghost cells (seg <= 64, kx <= 4)
+constexpr int MAX_ENT = 1024;   // (slab, pencil) entries of a staged segment
+constexpr int EPT = MAX_ENT / CELL_THREADS;  // entries per thread in the scan
+// fixed-size tables at the start of the CTA's shared memory (E, Esrc, ro, ao, s_pen, misc)
+constexpr int MAX_CAP = 4096;                    // staged atoms per CTA, at most
+constexpr int MAX_UNITS = 2 * (MAX_CAP / 32) + 2;  // 32-column chunks of a staged segment
+constexpr int ROWS_CAP = 512;                    // row atoms of a staged segment (+ pair padding)
+constexpr int CELLS_FIXED_BYTES =
+    ((2 * MAX_ENT + 2 * (MAXW + 1) + 32 + 24 + 2 * MAX_UNITS) * 4 + 127) & ~127;
 
-// One chunk of staged columns (quad blocks in the warp's shared tile) against the register rows
-// of a warp.  Lane layout: row group rg = lane % RG (rows rg, rg + RG, ...), column phase
-// ph = lane / RG (column pairs 2 ph, 2 ph + 2 PH, ...): three LDS.64 with PH distinct addresses
-// serve 2 R pair evaluations per lane through the packed FADD2 / FMUL2 sequence of pair2_s.
-// With RG = 4 a cell of n atoms occupies 4 ceil(n / 4) row slots, i.e. at most 3 idle ones.
-template <int R, bool FAST, bool DIAG, bool HIST_SMEM>
-__device__ __forceinline__ void cell_chunk(const float* __restrict__ tl, int cnt, int q0, int ph,
-                                           const float (&xi)[RMAX], const float (&yi)[RMAX],
-                                           const float (&zi)[RMAX], const int (&il)[RMAX],
-                                           float bx, float by, float bz, float s_cut,
-                                           float inv_step, uint32_t c_edge, uint32_t c_hist,
-                                           uint32_t four, const float* __restrict__ edges_g,
-                                           unsigned long long* hist_g,
-                                           unsigned long long& issued) {
+struct BinConsts {
+  float bx, by, bz, s_cut, inv_step;
+  uint32_t c_edge, c_hist, four;
+  const float* edges_g;
+  unsigned long long* hist_g;
+};
+
+// One chunk of 32 columns (one per lane, in registers) against n2 consecutive PAIRS of row atoms
+// (structure-of-arrays in shared memory, pair-aligned): three LDS.64 with every lane on the same
+// address give the register pairs of the packed FADD2 / FMUL2 sequence, two rows per pass.
+// MASK: the column only counts against rows [lo, lo + len) of the 2 n2 (same-species chunks of the
+// own pencil: rows before the column itself; chunks whose rows could alias a periodic image).
+template <bool FAST, bool MASK, bool HIST_SMEM>
+__device__ __forceinline__ void rows_vs_column(const float* __restrict__ rx,
+                                               const float* __restrict__ ry,
+                                               const float* __restrict__ rz, int n2, float4 c, int lo,
+                                               uint32_t len, const BinConsts& k,
+                                               unsigned long long& issued) {
   (void)issued;
   float hi = 0.f;
-#pragma unroll 1
-  for (int c0 = ph * 2; c0 < cnt; c0 += 2 * PH) {
-    const float* b = tl + (c0 >> 2) * QUAD_FLOATS + (c0 & 2);
-    const float2 X = *reinterpret_cast<const float2*>(b);
-    const float2 Y = *reinterpret_cast<const float2*>(b + 4);
-    const float2 Z = *reinterpret_cast<const float2*>(b + 8);
-    const int q = q0 + c0;  // position in the column stream; the own cell comes first
+  const float nan = __int_as_float(0x7fc00000);
+  const f32x2 xj = pack2(c.x, c.x), yj = pack2(c.y, c.y), zj = pack2(c.z, c.z);
+#pragma unroll 2
+  for (int r = 0; r < n2; ++r) {
+    f32x2 xi = *reinterpret_cast<const f32x2*>(rx + 2 * r);
+    const f32x2 yi = *reinterpret_cast<const f32x2*>(ry + 2 * r);
+    const f32x2 zi = *reinterpret_cast<const f32x2*>(rz + 2 * r);
+    if (MASK) {
+      float x0, x1;
+      unpack2(xi, x0, x1);
+      x0 = ((uint32_t)(2 * r - lo) < len) ? x0 : nan;
+      x1 = ((uint32_t)(2 * r + 1 - lo) < len) ? x1 : nan;
+      xi = pack2(x0, x1);
+    }
+    float s[2];
+    if (FAST) {
+      pair2_fast_packed(xi, yi, zi, xj, yj, zj, k.bx, k.by, k.bz, s[0], s[1]);
+    } else {
+      float x0, x1, y0, y1, z0, z1;
+      unpack2(xi, x0, x1); unpack2(yi, y0, y1); unpack2(zi, z0, z1);
+      pair2_s<false>(x0, x1, y0, y1, z0, z1, c.x, c.y, c.z, k.bx, k.by, k.bz, s[0], s[1]);
+    }
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float s[2];
-      pair2_s<FAST>(X.x, X.y, Y.x, Y.y, Z.x, Z.y, xi[r], yi[r], zi[r], bx, by, bz, s[0], s[1]);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        if (HIST_SMEM) {
-          bin_count_dense<DIAG, false>(s[c], s_cut, inv_step, 0.f, c_edge, c_hist, four, q + c,
-                                       il[r], hi);
-          MDS_CHK(issued += 1;)
-        } else {
-          bool in = s[c] < s_cut;  // false for NaN (padding rows / columns, NaN input)
-          if (DIAG) in = in && (q + c > il[r]);
-          if (in) atomicAdd(hist_g + bin_of_s(s[c], inv_step, edges_g), 1ull);
-        }
+    for (int q = 0; q < 2; ++q) {
+      if (HIST_SMEM) {
+        bin_count_dense<false, false>(s[q], k.s_cut, k.inv_step, 0.f, k.c_edge, k.c_hist, k.four, 0,
+                                      0, hi);
+        MDS_CHK(issued += 1;)
+      } else {
+        if (s[q] < k.s_cut)  // false for NaN (slots past the end, masked rows, NaN input)
+          atomicAdd(k.hist_g + bin_of_s(s[q], k.inv_step, k.edges_g), 1ull);
       }
     }
   }
 }
 
-// Everything a warp needs to walk the column stream of its current work item.
-struct WarpStream {
-  float* tile;             // [2][CH * 3] this warp's staging tile (quad blocks)
-  const int* t_qend;       // span table: stream position where span k ends ...
-  const int* t_off;        // ... and (first sorted index of span k) - (stream position of its start)
-  const float4* fpos;      // sorted atoms of the frame
-  int total;               // stream length
-  int lane, ph, st_off;
-  float bx, by, bz, s_cut, inv_step;
-  uint32_t c_edge, c_hist, four;
-  const float* edges_g;
-  unsigned long long* hist_g;
-  unsigned long long* issued;  // histogram atomics issued by this thread (checked builds)
-};
-
-// Columns [qs, qe) of the stream against the register rows of the warp: lanes gather 32 columns
-// at a time (one LDG.128 each, issued a whole chunk ahead of its use), transpose them into the
-// quad-block tile, and every lane then evaluates its (row group, column phase) share.  DIAG
-// applies the col > row mask (only the pass's own block of the own cell needs it).
-template <int R, bool FAST, bool DIAG, bool HIST_SMEM>
-__device__ __forceinline__ void cell_stream(const WarpStream& w, int qs, int qe,
-                                            const float (&xi)[RMAX], const float (&yi)[RMAX],
-                                            const float (&zi)[RMAX], const int (&il)[RMAX]) {
-  const float4 nan4 = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
-                                  __int_as_float(0x7fc00000), 0.f);
-  int k = 0, cur_end = w.t_qend[0], cur_off = w.t_off[0];
-  auto fetch = [&](int q) {  // q is visited in increasing order
-    float4 v = nan4;  // slots past the end hold NaN atoms (never inside the cutoff)
-    if (q < qe) {
-      while (q >= cur_end) {
-        ++k;
-        cur_end = w.t_qend[k];
-        cur_off = w.t_off[k];
-      }
-      v = __ldg(w.fpos + cur_off + q);
-    }
-    return v;
-  };
-  auto stage = [&](float* t, const float4 (&v)[CPL]) {
-#pragma unroll
-    for (int u = 0; u < CPL; ++u) {  // column lane + 32 u -> quad block 8 u + lane / 4
-      float* o = t + u * (8 * QUAD_FLOATS) + w.st_off;
-      o[0] = v[u].x; o[4] = v[u].y; o[8] = v[u].z;
-    }
-  };
-  float4 nxt[CPL];
-#pragma unroll
-  for (int u = 0; u < CPL; ++u) nxt[u] = fetch(qs + 32 * u + w.lane);
-  __syncwarp();  // the previous stream's readers are done with the tile
-  stage(w.tile, nxt);
-  __syncwarp();
-  int st = 0;
-#pragma unroll 1
-  for (int q0 = qs; q0 < qe; q0 += CH, st ^= 1) {
-    const int cnt = min(CH, qe - q0);
-#pragma unroll
-    for (int u = 0; u < CPL; ++u) nxt[u] = fetch(q0 + CH + 32 * u + w.lane);
-    const float* tl = w.tile + st * (CH * 3);
-    cell_chunk<R, FAST, DIAG, HIST_SMEM>(tl, cnt, q0, w.ph, xi, yi, zi, il, w.bx, w.by, w.bz,
-                                         w.s_cut, w.inv_step, w.c_edge, w.c_hist, w.four,
-                                         w.edges_g, w.hist_g, *w.issued);
-    if (q0 + CH < qe) stage(w.tile + (st ^ 1) * (CH * 3), nxt);  // warp-uniform condition
-    __syncwarp();
+// Largest c in [0, n) with t[c * stride] <= q, for a non-decreasing table with t[0] = 0 and
+// q < (the total, which is not stored when stride > 1): the cell / slab that holds position q.
+__device__ __forceinline__ int find_cell(const int* t, int stride, int n, int q) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (t[mid * stride] <= q) lo = mid; else hi = mid;
   }
+  return lo;
+}
+
+// Inclusive scan in place of t[1 .. n] (t[0] = 0 set by the caller), by one warp.
+__device__ __forceinline__ void warp_scan_table(int* t, int n, int lane) {
+  int carry = 0;
+  for (int base = 1; base <= n; base += 32) {
+    const int i = base + lane;
+    int v = (i <= n) ? t[i] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (i <= n) t[i] = v + carry;
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+}
+
+// 16-byte asynchronous global -> shared copy (LDGSTS): the staging copies of a thread are all in
+// flight at once instead of one round trip per atom.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // Move what has accumulated in the CTA's shared histogram to the global counts while other warps
@@ -235,225 +266,337 @@ __device__ __forceinline__ void flush_hist_warp(uint32_t* s_hist, const CellsPar
   }
 }
 
+// misc slots of the CTA
+enum { M_EVALS = 0, M_CEDGE = 1, M_HIST0 = 2, M_FOUR = 4, M_FRAME = 6, M_PEN = 7, M_PR = 8,
+       M_NEXT_CELL = 9, M_WSUM = 16, M_MISC_WORDS = 24 };
+
+// 128-bit load from a shared-memory byte address
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+
 template <bool HIST_SMEM>
 __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsParams p) {
+  // fixed-size tables first (constant offsets), then the staged atoms, then table + histograms
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* tiles = reinterpret_cast<float*>(smem_raw);                // [WARPS][2][CH * 3] quad blocks
-  int* span_tab = reinterpret_cast<int*>(tiles + CELL_WARPS * 2 * CH * 3);   // [WARPS][2][MAX_SPANS]
-  uint32_t* s_evals = reinterpret_cast<uint32_t*>(span_tab + CELL_WARPS * 2 * MAX_SPANS);  // [8]
-  float* s_edges = reinterpret_cast<float*>(s_evals + 8);
+  int* E = reinterpret_cast<int*>(smem_raw);           // [MAX_ENT] atoms per (slab, pencil) -> offsets
+  int* Esrc = E + MAX_ENT;                             // [MAX_ENT] first sorted index of the entry
+  int* ro = Esrc + MAX_ENT;                            // [MAXW + 1] row-pencil offsets per x cell
+  int* s_pen = ro + 2 * (MAXW + 1);                        // [32] offset-table position of neighbour pencil q
+  uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_pen + 32);  // [M_MISC_WORDS]
+  int2* s_unit = reinterpret_cast<int2*>(s_misc + M_MISC_WORDS);  // [MAX_UNITS] (first row, rows | masked << 30)
+  float* RX = reinterpret_cast<float*>(smem_raw + CELLS_FIXED_BYTES);  // [3][ROWS_CAP] row atoms, SoA
+  float* RY = RX + ROWS_CAP;
+  float* RZ = RY + ROWS_CAP;
+  float4* S = reinterpret_cast<float4*>(RZ + ROWS_CAP);  // [cap] the rows' pencil, then the slabs
+  float* s_edges = reinterpret_cast<float*>(S + p.cap_atoms);
   const int n_edges = p.nbins + 2;
   uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_edges + ((n_edges + 3) & ~3));
   const int hist_stride = p.nbins + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rg = lane % RG, ph = lane / RG;
   unsigned long long issued = 0;  // only counted in checked builds
   MDS_CHK(__shared__ unsigned long long s_chk[2]; if (tid == 0) { s_chk[0] = 0; s_chk[1] = 0; })
+
+  const int nx = p.nx, ny = p.ny, nc = p.nc;
+  const int kx = p.kx, ky = p.ky, kz = p.kz;
+  const int npen = ny * p.nz;
+  const int wy = 2 * ky + 1;
+  const unsigned long long total_items =
+      (unsigned long long)p.n_frames * (unsigned long long)p.pair_cnt * (unsigned long long)npen;
+  // thread 0: take the next work item off the global counter and leave it decoded in the slots
+  auto fetch_item = [&]() {
+    const unsigned long long idx = atomicAdd(p.work_counter, 1ull) * p.shard_count + p.shard_index;
+    int frame = -1, pen = 0, pr = 0;
+    if (idx < total_items) {
+      pen = (int)(idx % (unsigned long long)npen);
+      const unsigned long long t = idx / (unsigned long long)npen;
+      pr = (int)(t % (unsigned long long)p.pair_cnt);
+      frame = (int)(t / (unsigned long long)p.pair_cnt);
+    }
+    s_misc[M_FRAME] = (uint32_t)frame;
+    s_misc[M_PEN] = (uint32_t)pen;
+    s_misc[M_PR] = (uint32_t)pr;
+  };
 
   if (HIST_SMEM) {
     for (int k = tid; k < n_edges; k += CELL_THREADS) s_edges[k] = p.edges[k];
     for (int k = tid; k < p.pair_cnt * hist_stride; k += CELL_THREADS) s_hist[k] = 0u;
   }
   if (tid == 0) {
-    s_evals[0] = 0u;
+    s_misc[M_EVALS] = 0u;
     // address constants of the binning sequence, made opaque to ptxas (see rdf_allpairs.cu)
-    s_evals[1] = smem_u32(s_edges + 1) - kMagic4;
-    s_evals[2] = smem_u32(s_hist) - kMagic4;
-    s_evals[4] = 4u;
-    s_evals[5] = 4u;
+    s_misc[M_CEDGE] = smem_u32(s_edges + 1) - kMagic4;
+    s_misc[M_HIST0] = smem_u32(s_hist) - kMagic4;
+    s_misc[M_FOUR] = 4u;
+    s_misc[M_FOUR + 1] = 4u;
+    fetch_item();
   }
   __syncthreads();
 
-  float* tile = tiles + warp * 2 * CH * 3;
-  const int st_off = (lane >> 2) * QUAD_FLOATS + (lane & 3);  // this lane's slot in a staged chunk
+  BinConsts bc;
+  bc.c_edge = *reinterpret_cast<volatile uint32_t*>(s_misc + M_CEDGE);
+  const uint32_t hist0 = *reinterpret_cast<volatile uint32_t*>(s_misc + M_HIST0);
+  bc.four = *reinterpret_cast<volatile uint32_t*>(s_misc + M_FOUR + (lane & 1));
+  bc.bx = p.box[0]; bc.by = p.box[1]; bc.bz = p.box[2];
+  bc.s_cut = p.s_cut;
+  bc.inv_step = p.inv_step;
+  bc.edges_g = p.edges;
+  const uint32_t publish_every = max(1u, p.flush_threshold >> 6);
+  const uint32_t s_addr = smem_u32(S);
+  unsigned long long evaluated = 0;  // per-thread share of the statistics: candidate pairs ...
+  unsigned long long tested = 0;     // ... and pairs distance-tested (lane 0 of every warp)
+  uint32_t unpublished = 0;          // candidate pairs since this warp last told the CTA
   const float4 nan4 = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
                                   __int_as_float(0x7fc00000), 0.f);
-  int* t_qend = span_tab + warp * 2 * MAX_SPANS;
-  int* t_off = t_qend + MAX_SPANS;
-  const uint32_t c_edge = *reinterpret_cast<volatile uint32_t*>(s_evals + 1);
-  const uint32_t hist0 = *reinterpret_cast<volatile uint32_t*>(s_evals + 2);
-  const uint32_t four = *reinterpret_cast<volatile uint32_t*>(s_evals + 4 + (lane & 1));
-  const float bx = p.box[0], by = p.box[1], bz = p.box[2];
-  const float s_cut = p.s_cut, inv_step = p.inv_step;
-  const int nx = p.nx, ny = p.ny, nz = p.nz, nc = p.nc;
-  const unsigned long long total_items =
-      (unsigned long long)p.n_frames * (unsigned long long)p.pair_cnt * (unsigned long long)nc;
-  const uint32_t publish_every = max(1u, p.flush_threshold >> 6);
-  unsigned long long evaluated = 0;  // warp-uniform statistics
-  uint32_t unpublished = 0;          // candidate pairs since this warp last told the CTA
 
-  WarpStream ws;
-  ws.tile = tile;
-  ws.t_qend = t_qend;
-  ws.t_off = t_off;
-  ws.lane = lane;
-  ws.ph = ph;
-  ws.st_off = st_off;
-  ws.bx = bx; ws.by = by; ws.bz = bz;
-  ws.s_cut = s_cut;
-  ws.inv_step = inv_step;
-  ws.c_edge = c_edge;
-  ws.four = four;
-  ws.edges_g = p.edges;
-  ws.issued = &issued;
+  for (;;) {
+    __syncthreads();  // previous item finished; its successor is in the slots
+    const int frame = (int)*reinterpret_cast<volatile uint32_t*>(s_misc + M_FRAME);
+    const int pen = (int)*reinterpret_cast<volatile uint32_t*>(s_misc + M_PEN);
+    const int pr = (int)*reinterpret_cast<volatile uint32_t*>(s_misc + M_PR);
+    int4 ab = make_int4(0, 0, 1, 0);
+    if (frame >= 0) ab = p.pair_ab[p.pair_lo + pr];  // row species, column species, segment length
+    const bool same = ab.x == ab.y;
+    const int cy = pen % ny, cz = pen / ny;
+    // neighbour pencils (column species): the half shell for same-species pairs (dz = 0: dy = 1 ..
+    // ky, then dz = 1 .. kz with every dy), all (2ky+1)(2kz+1) of them otherwise
+    const int P = same ? kz * wy + ky : wy * (2 * kz + 1);
+    if (tid < P) {
+      int dy, dz;
+      if (same) {
+        if (tid < ky) { dy = tid + 1; dz = 0; }
+        else { const int m = tid - ky; dz = 1 + m / wy; dy = m % wy - ky; }
+      } else {
+        dz = tid / wy - kz;
+        dy = tid % wy - ky;
+      }
+      int yy = cy + dy, zz = cz + dz;
+      yy += (yy < 0) ? ny : 0; yy -= (yy >= ny) ? ny : 0;
+      zz += (zz < 0) ? p.nz : 0; zz -= (zz >= p.nz) ? p.nz : 0;
+      s_pen[tid] = ab.y * nc + (zz * ny + yy) * nx;
+    }
+    __syncthreads();  // everyone has read the slots; the pencil table is written
+    if (frame < 0) break;
+    if (tid == 0) fetch_item();  // in flight during this item
+    const uint32_t fl = p.frame_flags[frame];
+    if (fl & MDS_FRAME_FAR) continue;  // the all-pairs kernel takes this frame
+    const bool fast = (fl & 3u) != 3u;
+    const uint32_t* __restrict__ off = p.cell_off + (long long)frame * p.off_stride;
+    const float4* __restrict__ fpos = p.spos + (long long)frame * p.frame_stride;
+    const uint32_t* __restrict__ Frow = off + ab.x * nc + (cz * ny + cy) * nx;  // own pencil, row species
+    bc.c_hist = hist0 + (uint32_t)(pr * hist_stride) * 4u;
+    bc.hist_g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
 
-  unsigned long long nxt_raw = 0;
-  if (lane == 0) nxt_raw = atomicAdd(p.work_counter, 1ull);
-  unsigned long long idx = __shfl_sync(0xffffffffu, nxt_raw, 0) * p.shard_count + p.shard_index;
-
-  while (idx < total_items) {
-    if (lane == 0) nxt_raw = atomicAdd(p.work_counter, 1ull);  // in flight during this item
-    do {
-      const int c = (int)(idx % (unsigned long long)nc);
-      const unsigned long long t = idx / (unsigned long long)nc;
-      const int pr = (int)(t % (unsigned long long)p.pair_cnt);
-      const int frame = (int)(t / (unsigned long long)p.pair_cnt);
-      const uint32_t fl = p.frame_flags[frame];
-      if (fl & MDS_FRAME_FAR) break;  // the all-pairs kernel takes this frame
-      const bool fast = (fl & 3u) != 3u;
-      const int2 ab = p.pair_ab[p.pair_lo + pr];
-      const bool same = ab.x == ab.y;
-      const uint32_t* __restrict__ off = p.cell_off + (long long)frame * p.off_stride;
-      const int r0 = (int)off[ab.x * nc + c];
-      const int n = (int)off[ab.x * nc + c + 1] - r0;
-      if (n == 0) break;
-      const float4* __restrict__ fpos = p.spos + (long long)frame * p.frame_stride;
-
-      // ---- span table of the column stream (lane l builds span l) ----
-      const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-      int start = 0, len = 0;
-      {
-        const int n_spans = same ? 10 : 18;
-        if (lane < n_spans) {
-          int dy, dz, part, x0, x1;
-          bool whole_row_piece = true;
-          if (same) {
-            if (lane < 2) {  // own cell (the diagonal block), then the +x neighbour
-              dy = 0; dz = 0; part = 0; whole_row_piece = false;
-              x0 = (lane == 0) ? cx : (cx + 1 == nx ? 0 : cx + 1);
-              x1 = x0 + 1;
-            } else {
-              const int m = (lane - 2) >> 1;  // (dy, dz): (1,0) (-1,1) (0,1) (1,1)
-              part = lane & 1;
-              dy = (m == 0) ? 1 : m - 2;
-              dz = (m == 0) ? 0 : 1;
-            }
-          } else {
-            const int m = lane >> 1;
-            part = lane & 1;
-            dy = m % 3 - 1;
-            dz = m / 3 - 1;
-          }
-          if (whole_row_piece) {
-            // cells cx-1 .. cx+1 of the row, split in two where the window wraps around
-            if (cx == 0)           { x0 = part ? 0 : nx - 1; x1 = part ? 2 : nx; }
-            else if (cx == nx - 1) { x0 = part ? 0 : nx - 2; x1 = part ? 1 : nx; }
-            else                   { x0 = part ? 0 : cx - 1; x1 = part ? 0 : cx + 2; }
-          }
-          int yy = cy + dy, zz = cz + dz;
-          yy += (yy < 0) ? ny : 0; yy -= (yy >= ny) ? ny : 0;
-          zz += (zz < 0) ? nz : 0; zz -= (zz >= nz) ? nz : 0;
-          const int kb = ab.y * nc + (zz * ny + yy) * nx;
-          if (x1 > x0) {
-            start = (int)off[kb + x0];
-            len = (int)off[kb + x1] - start;
+    int x0 = 0, p_lo = 0;
+    while (x0 < nx) {
+      // ---- stage Sx row cells against neighbour pencils [p_lo, p_hi): count, scan, and make it
+      // smaller while it does not fit (cells are given up first, so a pencil subset, p_lo > 0,
+      // only ever follows a one-cell pass)
+      int Sx = p_lo > 0 ? 1 : min(ab.z, nx - x0), p_hi = P;
+      const bool with_own = same && p_lo == 0;  // the pass that also takes the own pencil's +x half
+      int Wa, Wr, Pn, n_r, n_a, n_ent;
+      for (;;) {
+        Pn = p_hi - p_lo;
+        Wa = Sx + 2 * kx;
+        Wr = with_own ? Sx + kx : Sx;
+        while (Wa * Pn > MAX_ENT) {  // (uniform) keep the entry table in bounds
+          if (Sx > 1) Sx >>= 1; else p_hi = p_lo + (Pn >> 1);
+          Pn = p_hi - p_lo; Wa = Sx + 2 * kx; Wr = with_own ? Sx + kx : Sx;
+        }
+        n_ent = Wa * Pn;
+        // phase 1: atoms per (pencil, x cell) entry — warps walk pencils, lanes x cells (neighbouring
+        // lanes read neighbouring offsets); stored slab-major (x cell, pencil) for the scan
+        for (int pi = warp; pi < Pn; pi += CELL_WARPS) {
+          const uint32_t* F = off + s_pen[p_lo + pi];
+          for (int c = lane; c < Wa; c += 32) {
+            int xw = x0 - kx + c;
+            xw += (xw < 0) ? nx : 0; xw -= (xw >= nx) ? nx : 0;
+            const int src = (int)F[xw];
+            E[c * Pn + pi] = (int)F[xw + 1] - src;
+            Esrc[c * Pn + pi] = src;
           }
         }
-      }
-      int qend = len;
+        for (int c = tid; c < Wr; c += CELL_THREADS) {
+          int xw = x0 + c;
+          xw -= (xw >= nx) ? nx : 0;
+          ro[c + 1] = (int)(Frow[xw + 1] - Frow[xw]);
+        }
+        if (tid == 0) { ro[0] = 0; s_misc[M_NEXT_CELL] = 0u; }
+        __syncthreads();
+        // phase 2: exclusive scan of the entry table (4 consecutive entries per thread)
+        int v[EPT], tsum = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, qend, o);
-        if (lane >= o) qend += v;
-      }
-      const int total = __shfl_sync(0xffffffffu, qend, 31);
-      __syncwarp();  // previous item's readers of the table are done
-      if (lane < MAX_SPANS) {
-        t_qend[lane] = qend;
-        t_off[lane] = start - (qend - len);
-      }
-      __syncwarp();
-
-      ws.fpos = fpos;
-      ws.total = total;
-      ws.c_hist = hist0 + (uint32_t)(pr * hist_stride) * 4u;
-      ws.hist_g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
-
-      // ---- row passes of up to 32 atoms of the cell ----
-      for (int rp = 0; rp < n; rp += RG * RMAX) {
-        const int nr = min(RG * RMAX, n - rp);
-        const int R = fast ? (nr + RG - 1) / RG : RMAX;
-        float xi[RMAX], yi[RMAX], zi[RMAX];
-        int il[RMAX];
+        for (int j = 0; j < EPT; ++j) {
+          const int e = tid * EPT + j;
+          v[j] = (e < n_ent) ? E[e] : 0;
+          tsum += v[j];
+        }
+        int inc = tsum;
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-          il[r] = rp + rg + RG * r;
-          if (il[r] < n) {
-            const float4 v = __ldg(fpos + r0 + il[r]);
-            xi[r] = v.x; yi[r] = v.y; zi[r] = v.z;
-          } else {
-            xi[r] = yi[r] = zi[r] = __int_as_float(0x7fc00000);  // NaN: never in cutoff
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_misc[M_WSUM + warp] = (uint32_t)inc;
+        if (warp == 0) warp_scan_table(ro, Wr, lane);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < CELL_WARPS; ++w) {
+          const int ws = (int)s_misc[M_WSUM + w];
+          before += (w < warp) ? ws : 0;
+          total += ws;
+        }
+        int run = before + inc - tsum;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+          const int e = tid * EPT + j;
+          if (e < n_ent) E[e] = run;
+          run += v[j];
+        }
+        n_a = total;
+        n_r = ro[Wr];
+        __syncthreads();  // offsets visible; also: everyone has read the warp sums and ro
+        if (n_r + n_a <= p.cap_atoms && ro[Sx] <= ROWS_CAP - 2) break;
+        if (Sx > 1) Sx >>= 1;
+        else if (Pn > 1) p_hi = p_lo + (Pn >> 1);
+        else __trap();  // the scan kernel hands such frames to the all-pairs kernel
+      }
+      // ---- phase 3: copy (asynchronous, 16 B per atom) ----------------------------------------
+      for (int e = tid; e < n_ent; e += CELL_THREADS) {
+        const int d0 = E[e], cnt = ((e + 1 < n_ent) ? E[e + 1] : n_a) - d0;
+        float4* dst = S + n_r + d0;
+        const float4* src = fpos + Esrc[e];
+        for (int i = 0; i < cnt; ++i) cp_async16(dst + i, src + i);
+      }
+      for (int c = tid; c < Wr; c += CELL_THREADS) {
+        int xw = x0 + c;
+        xw -= (xw >= nx) ? nx : 0;
+        const int src = (int)Frow[xw], cnt = ro[c + 1] - ro[c];
+        float4* dst = S + ro[c];
+        for (int i = 0; i < cnt; ++i) cp_async16(dst + i, fpos + src + i);
+      }
+      // ---- work units: chunks of 32 consecutive columns, first of the own pencil (same-species
+      // pairs: columns after the row, up to kx cells ahead), then of the slab array.  Both arrays
+      // are ordered by x cell, so the rows a chunk can pair with are a contiguous range: the cells
+      // from (first cell of the chunk - stencil width) to its last cell.  Rows of that range that
+      // are further than the stencil from a particular column are tested in vain (they can never be
+      // inside the cutoff) — unless the pencil is so short that "further" wraps around to a
+      // periodic image, in which case the chunk runs with per-column row ranges (masked).
+      const int n_rows = ro[Sx];
+      const int U_own = with_own ? (n_r + 31) >> 5 : 0;
+      const int U = U_own + ((n_a + 31) >> 5);
+      for (int u = tid; u < U; u += CELL_THREADS) {
+        int rb, re, masked;
+        if (u < U_own) {
+          const int q0 = u << 5, q1 = min(q0 + 31, n_r - 1);
+          const int s_lo = find_cell(ro, 1, Wr, q0), s_hi = find_cell(ro, 1, Wr, q1);
+          rb = ro[max(0, s_lo - kx)] & ~1;      // whole row pairs
+          re = min(ro[min(Sx, s_hi + 1)], q1);  // a row pairs with the columns after it
+          masked = 1;
+        } else {
+          const int q0 = (u - U_own) << 5, q1 = min(q0 + 31, n_a - 1);
+          const int s_lo = find_cell(E, Pn, Wa, q0), s_hi = find_cell(E, Pn, Wa, q1);
+          rb = ro[max(0, s_lo - 2 * kx)] & ~1;
+          re = ro[min(Sx, s_hi + 1)];
+          // Row cell x' and slab c' (x cell x' + c' - kx - x') are partners when 0 <= c' - x' <= 2 kx;
+          // any other combination in the range is tested in vain — harmless unless the offset
+          // c' - kx - x' reaches a periodic image of a partner cell, |c' - kx - x'| >= nx - kx.
+          // The extreme rows (incl. the ones that complete a pair) against the extreme slabs:
+          masked = 0;
+          if (re > rb) {
+            const int last = min(((re - rb + 1) & ~1) + rb, n_rows) - 1;  // last real row touched
+            const int xr_lo = find_cell(ro, 1, Sx, rb), xr_hi = find_cell(ro, 1, Sx, last);
+            masked = (s_hi - kx - xr_lo >= nx - kx || xr_hi + kx - s_lo >= nx - kx) ? 1 : 0;
           }
         }
-        // same species: columns q <= row are masked, so the stream starts at the pass's own block
-        // and only that block needs the mask
-        const int qs = same ? rp : 0;
-        // sub-ranges keep the evaluation counter of the histogram-flush logic fine-grained even
-        // for absurdly crowded neighbourhoods (normally one range = the whole stream)
-        for (int qa = qs; qa < total; qa += (1 << 20)) {
-          const int qe = min(total, qa + (1 << 20));
-          int q1 = qa;
-          if (same && qa == qs) {
-            // the pass's own block of the own cell: the only columns that need the col > row
-            // mask.  One masked body for every R (idle row slots hold NaN) keeps the code small —
-            // the kernel is sensitive to instruction-cache footprint.
-            q1 = min(qe, qa + RG * RMAX);
-            if (fast) cell_stream<RMAX, true, true, HIST_SMEM>(ws, qa, q1, xi, yi, zi, il);
-            else      cell_stream<RMAX, false, true, HIST_SMEM>(ws, qa, q1, xi, yi, zi, il);
-          }
-          if (q1 < qe) {
-            if (fast) {
-              switch (R) {
-#define MDS_STREAM(RV) cell_stream<RV, true, false, HIST_SMEM>(ws, q1, qe, xi, yi, zi, il)
-                case 1: MDS_STREAM(1); break;
-                case 2: MDS_STREAM(RMAX >= 2 ? 2 : RMAX); break;
-                case 3: MDS_STREAM(RMAX >= 3 ? 3 : RMAX); break;
-                case 4: MDS_STREAM(RMAX >= 4 ? 4 : RMAX); break;
-                case 5: MDS_STREAM(RMAX >= 5 ? 5 : RMAX); break;
-                case 6: MDS_STREAM(RMAX >= 6 ? 6 : RMAX); break;
-                case 7: MDS_STREAM(RMAX >= 7 ? 7 : RMAX); break;
-                default: MDS_STREAM(RMAX); break;
-#undef MDS_STREAM
-              }
+        s_unit[u] = make_int2(rb, (re > rb ? (re - rb + 1) >> 1 : 0) | (masked << 30));
+      }
+      // candidate pairs of this segment (statistics): pairs whose cells are within the stencil
+      for (int c = tid; c < Sx; c += CELL_THREADS) {
+        const int n = ro[c + 1] - ro[c];
+        const int a0 = E[c * Pn], a1 = (c + 2 * kx + 1 < Wa) ? E[(c + 2 * kx + 1) * Pn] : n_a;
+        long long ev = (long long)n * (a1 - a0);
+        if (with_own) ev += (long long)n * (n - 1) / 2 + (long long)n * (ro[c + kx + 1] - ro[c + 1]);
+        evaluated += (unsigned long long)ev;
+      }
+      cp_async_wait_all();
+      __syncthreads();
+      // the row atoms once more as structure-of-arrays (+ a NaN pad so that pairs are whole)
+      for (int i = tid; i <= (n_rows | 1); i += CELL_THREADS) {
+        float4 v = nan4;
+        if (i < n_rows) v = S[i];
+        RX[i] = v.x; RY[i] = v.y; RZ[i] = v.z;
+      }
+      __syncthreads();
+
+      // ---- compute: one chunk per warp at a time ---------------------------------------------
+      for (;;) {
+        int u = 0;
+        if (lane == 0) u = (int)atomicAdd(s_misc + M_NEXT_CELL, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= U) break;
+        const int2 un = s_unit[u];
+        const int rb = un.x, n2 = un.y & 0x3fffffff;
+        if (n2 == 0) continue;
+        const bool masked = (un.y >> 30) != 0;
+        const bool own = u < U_own;
+        const int q = ((own ? u : u - U_own) << 5) + lane;
+        const int lim = own ? n_r : n_a;
+        float4 c = nan4;  // slots past the end hold NaN atoms (never inside the cutoff)
+        if (q < lim) c = lds128(s_addr + ((uint32_t)((own ? 0 : n_r) + q) << 4));
+        if (!masked && fast) {
+          rows_vs_column<true, false, HIST_SMEM>(RX + rb, RY + rb, RZ + rb, n2, c, 0, 0u, bc, issued);
+        } else {
+          // rows [lo, lo + len) of this chunk's row range are the ones column q may pair with
+          int lo = 0;
+          uint32_t len = 0x7fffffffu;
+          if (masked) {
+            if (own) {
+              const int cell = find_cell(ro, 1, Wr, min(q, n_r - 1));
+              lo = ro[max(0, cell - kx)] - rb;
+              len = (uint32_t)max(0, q - rb - lo);
             } else {
-              cell_stream<RMAX, false, false, HIST_SMEM>(ws, q1, qe, xi, yi, zi, il);
+              const int cell = find_cell(E, Pn, Wa, min(q, n_a - 1));
+              lo = ro[max(0, cell - 2 * kx)] - rb;
+              len = (uint32_t)max(0, ro[min(Sx, cell + 1)] - rb - lo);
             }
           }
-          if (HIST_SMEM) {
-            unpublished += (uint32_t)(qe - qa) * (uint32_t)nr;
-            if (unpublished >= publish_every) {
-              uint32_t old = 0;
-              if (lane == 0) old = atomicAdd(s_evals, unpublished);
-              old = __shfl_sync(0xffffffffu, old, 0);
-              // the warp whose contribution crosses the threshold empties the histogram
-              if (old < p.flush_threshold && old + unpublished >= p.flush_threshold) {
-                if (lane == 0) atomicSub(s_evals, p.flush_threshold);
-                flush_hist_warp(s_hist, p, lane MDS_CHK(, s_chk));
-              }
-              unpublished = 0;
+          if (fast) rows_vs_column<true, true, HIST_SMEM>(RX + rb, RY + rb, RZ + rb, n2, c, lo, len, bc,
+                                                         issued);
+          else rows_vs_column<false, true, HIST_SMEM>(RX + rb, RY + rb, RZ + rb, n2, c, lo, len, bc,
+                                                      issued);
+        }
+        tested += (uint32_t)n2 * 64u;
+        if (HIST_SMEM) {
+          unpublished += (uint32_t)n2 * 64u;
+          if (unpublished >= publish_every) {
+            uint32_t old = 0;
+            if (lane == 0) old = atomicAdd(s_misc + M_EVALS, unpublished);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            // the warp whose contribution crosses the threshold empties the histogram
+            if (old < p.flush_threshold && old + unpublished >= p.flush_threshold) {
+              if (lane == 0) atomicSub(s_misc + M_EVALS, p.flush_threshold);
+              flush_hist_warp(s_hist, p, lane MDS_CHK(, s_chk));
             }
+            unpublished = 0;
           }
         }
       }
-      // pairs distance-tested and not masked by the diagonal
-      evaluated += same ? (unsigned long long)n * (unsigned long long)(n - 1) / 2ull +
-                              (unsigned long long)n * (unsigned long long)(total - n)
-                        : (unsigned long long)n * (unsigned long long)total;
-    } while (0);
-    idx = __shfl_sync(0xffffffffu, nxt_raw, 0) * p.shard_count + p.shard_index;
+      __syncthreads();  // the staged segment is consumed
+      if (p_hi < P) p_lo = p_hi;
+      else { p_lo = 0; x0 += Sx; }
+    }
   }
 
+  evaluated = __reduce_add_sync(0xffffffffu, (unsigned)(evaluated & 0xffffffffull)) +
+              ((unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)(evaluated >> 32)) << 32);
   if (lane == 0 && evaluated) atomicAdd(p.evaluated, evaluated);
+  if (lane == 0 && tested) atomicAdd(p.evaluated + 1, tested);
   if (HIST_SMEM) {
     __syncthreads();
     MDS_CHK(checked_conservation(s_chk, issued, s_hist, p.pair_cnt * hist_stride, tid, CELL_THREADS,
@@ -472,9 +615,12 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsP
 
 // ---- host-side launchers ------------------------------------------------------------------
 
-size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem) {
-  size_t b = (size_t)CELL_WARPS * 2 * CH * 3 * sizeof(float) +
-             (size_t)CELL_WARPS * 2 * MAX_SPANS * sizeof(int) + 8 * sizeof(uint32_t);
+int cells_max_seg() { return MAXW - 2 * 4; }
+int cells_max_cap() { return MAX_CAP; }
+
+size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem, int cap_atoms) {
+  size_t b = (size_t)CELLS_FIXED_BYTES + 3 * (size_t)ROWS_CAP * sizeof(float) +
+             (size_t)cap_atoms * sizeof(float4);
   if (hist_in_smem) {
     b += (size_t)((nbins + 2 + 3) & ~3) * sizeof(float);
     b += (size_t)pair_cnt * (size_t)(nbins + 1) * sizeof(uint32_t);
@@ -483,25 +629,25 @@ size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem) {
 }
 
 cudaError_t launch_cell_build(const PackParams& pp, int n_species, float4* sorted,
-                              cudaStream_t stream) {
+                              uint32_t crowded_limit, int sm_count, cudaStream_t stream) {
   const long long total = (long long)pp.n_frames * pp.n_packed;
   if (total <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(pp.cell_off, 0,
                                   sizeof(uint32_t) * (size_t)pp.off_stride * (size_t)pp.n_frames,
                                   stream);
   if (e != cudaSuccess) return e;
-  e = launch_pack(pp, stream);  // quad-block positions + per-cell counts and ranks + frame flags
+  e = launch_pack(pp, sm_count, stream);  // quad-block positions + per-cell counts and ranks + frame flags
   if (e != cudaSuccess) return e;
-  rdf_cell_scan_kernel<<<(unsigned)pp.n_frames, 1024, 0, stream>>>(pp.cell_off, pp.off_stride,
-                                                                   n_species * pp.grid.nc);
+  rdf_cell_scan_kernel<<<(unsigned)pp.n_frames, 1024, 0, stream>>>(
+      pp.cell_off, pp.off_stride, n_species * pp.grid.nc, pp.frame_flags, crowded_limit);
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 64) blocks = 148 * 64;
+  if (blocks > (long long)sm_count * 64) blocks = (long long)sm_count * 64;
   rdf_cell_scatter_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pp, sorted);
   return cudaGetLastError();
 }
 
 cudaError_t launch_cells(const CellsParams& p, int sm_count, cudaStream_t stream, int* grid_out) {
-  const size_t smem = cells_smem_bytes(p.nbins, p.pair_cnt, p.hist_in_smem != 0);
+  const size_t smem = cells_smem_bytes(p.nbins, p.pair_cnt, p.hist_in_smem != 0, p.cap_atoms);
   auto kern = p.hist_in_smem ? rdf_cells_kernel<true> : rdf_cells_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -509,12 +655,11 @@ cudaError_t launch_cells(const CellsParams& p, int sm_count, cudaStream_t stream
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CELL_THREADS, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-  unsigned long long items =
-      (unsigned long long)p.n_frames * (unsigned long long)p.pair_cnt * (unsigned long long)p.nc;
+  unsigned long long items = (unsigned long long)p.n_frames * (unsigned long long)p.pair_cnt *
+                             (unsigned long long)p.ny * (unsigned long long)p.nz;
   items = (items + p.shard_count - 1) / p.shard_count;
   unsigned long long grid = (unsigned long long)per_sm * sm_count;  // persistent
-  const unsigned long long need = (items + CELL_WARPS - 1) / CELL_WARPS;
-  if (grid > need) grid = need;
+  if (grid > items) grid = items;
   if (grid < 1) grid = 1;
   if (grid_out) *grid_out = (int)grid;
   kern<<<(unsigned)grid, CELL_THREADS, smem, stream>>>(p);

@@ -162,14 +162,19 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 // Squared minimum-image distances of ONE row atom (xi, yi, zi) against TWO column atoms, every
 // op rounded exactly as in the scalar building blocks above.  Per pair: 1.5 FADD2 (differences)
 // + 1.5 FADD2 (box - |d|, abs/neg are operand modifiers) + 3 FMNMX + 1.5 FMUL2 + 2 FADD.
+// The row atom comes as register pairs (xi0, xi1) etc.: pair2_s passes the same register twice
+// (rows held in registers), pair2_sd two registers that hold the same value (rows broadcast
+// from a shared-memory layout that stores every coordinate twice, so that one LDS.128 yields
+// the aligned pairs the packed instructions want; rdf_cells.cu).
 template <bool FAST>
-__device__ __forceinline__ void pair2_s(float xj0, float xj1, float yj0, float yj1, float zj0,
-                                        float zj1, float xi, float yi, float zi, float bx, float by,
-                                        float bz, float& s0, float& s1) {
+__device__ __forceinline__ void pair2_sd(float xj0, float xj1, float yj0, float yj1, float zj0,
+                                         float zj1, float xi0, float xi1, float yi0, float yi1,
+                                         float zi0, float zi1, float bx, float by, float bz,
+                                         float& s0, float& s1) {
   float dx0, dx1, dy0, dy1, dz0, dz1;
-  unpack2(sub2(pack2(xj0, xj1), pack2(xi, xi)), dx0, dx1);
-  unpack2(sub2(pack2(yj0, yj1), pack2(yi, yi)), dy0, dy1);
-  unpack2(sub2(pack2(zj0, zj1), pack2(zi, zi)), dz0, dz1);
+  unpack2(sub2(pack2(xj0, xj1), pack2(xi0, xi1)), dx0, dx1);
+  unpack2(sub2(pack2(yj0, yj1), pack2(yi0, yi1)), dy0, dy1);
+  unpack2(sub2(pack2(zj0, zj1), pack2(zi0, zi1)), dz0, dz1);
   float mx0, mx1, my0, my1, mz0, mz1;
   if (FAST) {
     float tx0, tx1, ty0, ty1, tz0, tz1;
@@ -191,6 +196,37 @@ __device__ __forceinline__ void pair2_s(float xj0, float xj1, float yj0, float y
   unpack2(mul2(mz, mz), zz0, zz1);
   s0 = __fadd_rn(__fadd_rn(xx0, yy0), zz0);
   s1 = __fadd_rn(__fadd_rn(xx1, yy1), zz1);
+}
+
+// Same with everything already in packed registers: columns (xj, yj, zj) = two atoms, row
+// (xi, yi, zi) = one atom stored twice.  Keeps ptxas from re-assembling the pairs per iteration.
+__device__ __forceinline__ void pair2_fast_packed(f32x2 xj, f32x2 yj, f32x2 zj, f32x2 xi, f32x2 yi,
+                                                  f32x2 zi, float bx, float by, float bz, float& s0,
+                                                  float& s1) {
+  float dx0, dx1, dy0, dy1, dz0, dz1;
+  unpack2(sub2(xj, xi), dx0, dx1);
+  unpack2(sub2(yj, yi), dy0, dy1);
+  unpack2(sub2(zj, zi), dz0, dz1);
+  float tx0, tx1, ty0, ty1, tz0, tz1;
+  unpack2(sub2(pack2(bx, bx), pack2(fabsf(dx0), fabsf(dx1))), tx0, tx1);
+  unpack2(sub2(pack2(by, by), pack2(fabsf(dy0), fabsf(dy1))), ty0, ty1);
+  unpack2(sub2(pack2(bz, bz), pack2(fabsf(dz0), fabsf(dz1))), tz0, tz1);
+  const f32x2 mx = pack2(fminf(fabsf(dx0), tx0), fminf(fabsf(dx1), tx1));
+  const f32x2 my = pack2(fminf(fabsf(dy0), ty0), fminf(fabsf(dy1), ty1));
+  const f32x2 mz = pack2(fminf(fabsf(dz0), tz0), fminf(fabsf(dz1), tz1));
+  float xx0, xx1, yy0, yy1, zz0, zz1;
+  unpack2(mul2(mx, mx), xx0, xx1);
+  unpack2(mul2(my, my), yy0, yy1);
+  unpack2(mul2(mz, mz), zz0, zz1);
+  s0 = __fadd_rn(__fadd_rn(xx0, yy0), zz0);
+  s1 = __fadd_rn(__fadd_rn(xx1, yy1), zz1);
+}
+
+template <bool FAST>
+__device__ __forceinline__ void pair2_s(float xj0, float xj1, float yj0, float yj1, float zj0,
+                                        float zj1, float xi, float yi, float zi, float bx, float by,
+                                        float bz, float& s0, float& s1) {
+  pair2_sd<FAST>(xj0, xj1, yj0, yj1, zj0, zj1, xi, xi, yi, yi, zi, zi, bx, by, bz, s0, s1);
 }
 
 __device__ __forceinline__ float sqrt_approx(float s) {

@@ -42,7 +42,7 @@ struct PackParams {
   uint32_t* frame_flags;   // [n_frames], zeroed by the kernel's caller
   float box[3];
 };
-cudaError_t launch_pack(const PackParams& p, cudaStream_t stream);
+cudaError_t launch_pack(const PackParams& p, int sm_count, cudaStream_t stream);
 // out[0] += frames on the general minimum-image path, out[1] += frames flagged MDS_FRAME_FAR,
 // *batch_far (nullable) = frames flagged MDS_FRAME_FAR in this batch
 cudaError_t launch_count_general(const uint32_t* flags, int n, unsigned long long* out,
@@ -62,10 +62,12 @@ struct CellsParams {
   int64_t off_stride;         // >= n_species * nc + 1
   const uint32_t* frame_flags;
   int32_t nx, ny, nz, nc;
-  const int2* pair_ab;        // [n_pairs_total] species (a, b) of every pair, a <= b
+  int32_t kx, ky, kz;         // stencil half-widths: partners lie at most k cells away (1 or 2)
+  int32_t cap_atoms;          // staged positions per CTA (shared memory), see rdf_cells.cu
+  const int4* pair_ab;        // [n_pairs_total] (row species, column species, x cells per segment, 0)
   const float* edges;
   unsigned long long* counts;     // [n_pairs_total][nbins]
-  unsigned long long* evaluated;  // += candidate pairs distance-tested
+  unsigned long long* evaluated;  // [0] += candidate pairs (cells within the stencil), [1] += pairs distance-tested
   unsigned long long* work_counter;  // zeroed before launch
   int32_t nbins, pair_lo, pair_cnt, hist_in_smem;
   float s_cut, inv_step;
@@ -73,10 +75,13 @@ struct CellsParams {
   uint32_t flush_threshold;   // candidate pairs per CTA between histogram flushes (<= 2^30)
   uint32_t shard_index, shard_count;  // item sharding: units u with u % shard_count == shard_index
 };
-size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem);
-// pp must have cell_off / rank / grid set: pack + count, scan, scatter into `sorted`
+size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem, int cap_atoms);
+int cells_max_seg();   // longest segment (x cells) the kernel's tables can hold
+int cells_max_cap();   // largest cap_atoms the kernel's tables can hold
+// pp must have cell_off / rank / grid set: pack + count, scan, scatter into `sorted`; frames with
+// a cell of more than crowded_limit atoms are flagged MDS_FRAME_FAR
 cudaError_t launch_cell_build(const PackParams& pp, int n_species, float4* sorted,
-                              cudaStream_t stream);
+                              uint32_t crowded_limit, int sm_count, cudaStream_t stream);
 cudaError_t launch_cells(const CellsParams& p, int sm_count, cudaStream_t stream, int* grid_out);
 
 // ---- microbench.cu ----

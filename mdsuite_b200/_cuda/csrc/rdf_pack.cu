@@ -71,15 +71,16 @@ __global__ void __launch_bounds__(256, 8) rdf_pack_kernel(const PackParams p) {
   }
 }
 
-cudaError_t launch_pack(const PackParams& p, cudaStream_t stream) {
+cudaError_t launch_pack(const PackParams& p, int sm_count, cudaStream_t stream) {
   const bool atom_major = p.layout == MDS_LAYOUT_ATOM_MAJOR_XYZ;
   const long long inner_n = atom_major ? p.n_frames : (long long)p.n_packed;
   const long long outer_n = atom_major ? (long long)p.n_packed : p.n_frames;
   if (inner_n <= 0 || outer_n <= 0) return cudaSuccess;
   long long bx = (inner_n + 255) / 256;
-  if (bx > 148 * 64) bx = 148 * 64;
+  const long long fill = (long long)sm_count * 64;  // 8 resident CTAs per SM, 8 waves
+  if (bx > fill) bx = fill;
   // enough CTAs to fill the machine, at most 65535 in y
-  long long by = (148LL * 64 + bx - 1) / bx;
+  long long by = (fill + bx - 1) / bx;
   if (by > outer_n) by = outer_n;
   if (by > 65535) by = 65535;
   rdf_pack_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, stream>>>(p);

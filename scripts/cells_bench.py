@@ -24,10 +24,10 @@ def bench(name, sysm, cutoff, nbins, frames, path="celllist", reps=4):
             best_k = min(best_k, st.pair_kernel_ms)
             best_s = min(best_s, st.submit_ms)
         cand = st.pairs_evaluated / (best_k * 1e-3)
-        print(f"{name:28s} path={st.path_name} cells={st.cells} frames={frames} "
+        print(f"{name:28s} path={st.path_name} cells={st.cells} K={st.cell_stencil} frames={frames} "
               f"pair_kernel_ms={best_k:9.3f} submit_ms={best_s:9.3f} cand/s={cand:.3e} "
               f"frac22={cand / PEAK:.3f} binned/cand={st.pairs_binned / st.pairs_evaluated:.3f} "
-              f"allpairs_equiv/s={st.pairs_allpairs_equiv / (best_s * 1e-3):.3e} "
+              f"allpairs_equiv/s={st.pairs_allpairs_equiv / (best_s * 1e-3):.3e} tested/cand={st.pairs_tested / max(st.pairs_evaluated, 1):.2f} "
               f"us/frame={best_s * 1e3 / frames:.1f}", flush=True)
 
 

@@ -42,7 +42,7 @@ def test_struct_sizes_match_the_header_layout():
         subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), src, "-o", exe])
         cfg, st, ver = map(int, subprocess.check_output([exe]).split())
     assert ctypes.sizeof(_cuda._Config) == cfg == 48
-    assert ctypes.sizeof(_cuda._Stats) == st == 112
+    assert ctypes.sizeof(_cuda._Stats) == st == 136
     assert ver == _cuda.ABI_VERSION
 
 

@@ -17,6 +17,23 @@ from oracle import c_oracle
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["1", "2", "2,1,2"], ids=["K1", "K2", "K212"])
+def cell_k(request, monkeypatch):
+    """Stencil half-widths of the cell kernel (cells per cutoff length), forced through the
+    library's tuning variable so that every case runs on the classical grid, on the half-width
+    grid and on a mixed one."""
+    monkeypatch.setenv("MDS_RDF_CELL_K", request.param)
+    k = [int(v) for v in request.param.split(",")]
+    return tuple(k * 3 if len(k) == 1 else k)
+
+
+def expected_grid(box, cutoff, k):
+    """Cells per dimension as mds_rdf_create picks them: k cells span >= 1.001 x cutoff."""
+    return tuple(int(min(128 * k[d], np.floor(float(np.float32(box[d])) /
+                                               (float(np.float32(cutoff)) * 1.001 / k[d]))))
+                 for d in range(3))
+
+
 def run(pos, counts, box, cutoff, nbins, path, parity=True, layout=_cuda.LAYOUT_FRAME_MAJOR,
         device_input=False, max_frames=0):
     import torch
@@ -57,9 +74,9 @@ def cell_index(pos, box, n):
     return (out[2] * n[1] + out[1]) * n[0] + out[0]
 
 
-def expected_candidates(pos, counts, box, n, parity=True):
+def expected_candidates(pos, counts, box, n, parity=True, k=(1, 1, 1)):
     """Pairs the cell kernel distance-tests: same-species pairs inside a cell + all pairs of
-    atoms in distinct adjacent cells (27-stencil), per species pair, summed over frames."""
+    atoms in distinct cells at most k cells apart, per species pair, summed over frames."""
     nx, ny, nz = n
     nc = nx * ny * nz
     first = 1 if parity else 0
@@ -74,9 +91,9 @@ def expected_candidates(pos, counts, box, n, parity=True):
         for a in range(len(counts)):
             for b in range(a, len(counts)):
                 neigh = np.zeros_like(occ[b])
-                for dz in (-1, 0, 1):
-                    for dy in (-1, 0, 1):
-                        for dx in (-1, 0, 1):
+                for dz in range(-k[2], k[2] + 1):
+                    for dy in range(-k[1], k[1] + 1):
+                        for dx in range(-k[0], k[0] + 1):
                             neigh += np.roll(occ[b], (dz, dy, dx), axis=(0, 1, 2))
                 if a == b:
                     # ordered neighbours incl. self: (sum n_c * neigh_c - sum n_c) / 2
@@ -87,44 +104,48 @@ def expected_candidates(pos, counts, box, n, parity=True):
 
 
 @pytest.mark.parametrize("parity", [True, False])
-def test_lj_4096_vs_oracle(parity):
-    sysm = synthetic.lj_fluid(16, 3, seed=3)  # L = 16.93, cutoff 3 -> 5 cells per dimension
+def test_lj_4096_vs_oracle(parity, cell_k):
+    sysm = synthetic.lj_fluid(16, 3, seed=3)  # L = 16.93, cutoff 3 -> 5 (K = 1) / 11 (K = 2) cells
     got, st = run(sysm.positions, sysm.counts, sysm.box, 3.0, 300, "celllist", parity=parity)
     want, _ = oracle(sysm.positions, sysm.counts, sysm.box, 3.0, 300, parity=parity)
-    assert st.path == _cuda.PATH_CELLLIST and st.cells == (5, 5, 5)
+    assert st.path == _cuda.PATH_CELLLIST and st.cell_stencil == cell_k
+    assert st.cells == expected_grid(sysm.box, 3.0, cell_k)
+    assert st.cells == tuple(5 if k == 1 else 11 for k in cell_k)
     assert_same(got, want)
     assert st.pairs_binned == float(want.sum())
     assert st.pairs_evaluated == expected_candidates(sysm.positions, sysm.counts, sysm.box,
-                                                     st.cells, parity)
+                                                     st.cells, parity, cell_k)
     assert st.pairs_allpairs_equiv == sysm.pairs_per_frame(parity) * 3
     assert st.frames_general_minimage == 0 and st.frames_far == 0
 
 
-def test_water_three_pairs_vs_oracle():
-    sysm = synthetic.spc_water(12, 2, seed=4)  # 5184 atoms, L = 37.26, cutoff 8 -> 4 cells
+def test_water_three_pairs_vs_oracle(cell_k):
+    sysm = synthetic.spc_water(12, 2, seed=4)  # 5184 atoms, L = 37.26, cutoff 8 -> 4 / 9 cells
     got, st = run(sysm.positions, sysm.counts, sysm.box, 8.0, 800, "celllist")
     want, _ = oracle(sysm.positions, sysm.counts, sysm.box, 8.0, 800)
-    assert st.cells == (4, 4, 4)
+    assert st.cells == expected_grid(sysm.box, 8.0, cell_k)
+    assert st.cells == tuple(4 if k == 1 else 9 for k in cell_k)
     assert_same(got, want)
     assert st.pairs_evaluated == expected_candidates(sysm.positions, sysm.counts, sysm.box,
-                                                     st.cells)
+                                                     st.cells, True, cell_k)
 
 
-def test_noncubic_three_species_minimum_grid():
-    """3 x 4 x 5 cells (3 is the minimum: the x window always wraps), a species with one atom
-    (no pairs in parity mode) and uneven species sizes."""
+def test_noncubic_three_species_minimum_grid(cell_k):
+    """3 x 4 x 5 cutoff lengths (3 is the minimum: 3 or 6 cells, the stencil covers every cell of
+    the dimension and the x window always wraps), a species with one atom (no pairs in parity
+    mode) and uneven species sizes."""
     rng = np.random.default_rng(31)
     counts, box = [1500, 1, 900], np.array([9.1, 12.2, 15.3])
     pos = (rng.random((4, sum(counts), 3)) * box).astype(np.float32)
     for parity in (True, False):
         got, st = run(pos, counts, box, 3.0, 250, "celllist", parity=parity)
         want, _ = oracle(pos, counts, box, 3.0, 250, parity=parity)
-        assert st.cells == (3, 4, 5)
+        assert st.cells == tuple(n * k for n, k in zip((3, 4, 5), cell_k))
         assert_same(got, want)
-        assert st.pairs_evaluated == expected_candidates(pos, counts, box, st.cells, parity)
+        assert st.pairs_evaluated == expected_candidates(pos, counts, box, st.cells, parity, cell_k)
 
 
-def test_unwrapped_centered_and_far_frames():
+def test_unwrapped_centered_and_far_frames(cell_k):
     rng = np.random.default_rng(32)
     counts, box = [1300, 1100], np.array([14.0, 14.0, 14.0])
     n = sum(counts)
@@ -142,7 +163,7 @@ def test_unwrapped_centered_and_far_frames():
     assert st.frames_general_minimage == 3  # frames 1, 3, 4 leave both windows
 
 
-def test_nan_inf_coordinates():
+def test_nan_inf_coordinates(cell_k):
     rng = np.random.default_rng(33)
     counts, box = [1200, 1200], np.array([12.0, 12.0, 12.0])
     pos = (rng.random((3, 2400, 3)) * 12).astype(np.float32)
@@ -154,9 +175,10 @@ def test_nan_inf_coordinates():
     assert_same(got, want)
 
 
-def test_clustered_atoms_row_passes_and_histogram_flush(monkeypatch):
-    """Everything in a few cells: cells with hundreds of atoms (many row passes of 32), most cells
-    empty; a tiny flush threshold makes warps empty the shared histogram while others count."""
+def test_clustered_atoms_row_passes_and_histogram_flush(monkeypatch, cell_k):
+    """Everything in a few cells: cells with dozens to hundreds of atoms (segments that have to be
+    cut down to single cells and pencil subsets to fit the staging buffers), most cells empty; a
+    tiny flush threshold makes warps empty the shared histogram while others count."""
     monkeypatch.setenv("MDS_RDF_FLUSH_THRESHOLD", "4096")
     rng = np.random.default_rng(34)
     counts, box = [700, 500], np.array([30.0, 30.0, 30.0])
@@ -165,12 +187,28 @@ def test_clustered_atoms_row_passes_and_histogram_flush(monkeypatch):
     pos = np.where(pos >= 30.0, 0.0, pos).astype(np.float32)
     got, st = run(pos, counts, box, 2.9, 290, "celllist")
     want, _ = oracle(pos, counts, box, 2.9, 290)
-    assert st.cells == (10, 10, 10)
+    assert st.cells == tuple(10 if k == 1 else 20 for k in cell_k)
     assert_same(got, want)
-    assert st.pairs_evaluated == expected_candidates(pos, counts, box, st.cells)
+    assert st.pairs_evaluated == expected_candidates(pos, counts, box, st.cells, True, cell_k)
+    assert st.frames_far == 0
 
 
-def test_layouts_residency_and_batching_agree():
+@pytest.mark.parametrize("cap", [256, 1536])
+def test_crowded_frames_fall_back_to_all_pairs(monkeypatch, cap):
+    """A frame with more atoms in one cell than the pencil kernel can stage goes to the all-pairs
+    kernel as a whole (counted in frames_far); its neighbours in the batch stay on the cell path."""
+    monkeypatch.setenv("MDS_RDF_CELL_CAP", str(cap))
+    rng = np.random.default_rng(38)
+    counts, box = [1500, 900], np.array([24.0, 24.0, 24.0])
+    pos = (rng.random((3, 2400, 3)) * 24.0).astype(np.float32)
+    pos[1, :1500] = (12.0 + rng.random((1500, 3)) * 0.5).astype(np.float32)  # one tiny blob
+    got, st = run(pos, counts, box, 3.0, 150, "celllist")
+    want, _ = oracle(pos, counts, box, 3.0, 150)
+    assert_same(got, want)
+    assert st.frames_far == 1
+
+
+def test_layouts_residency_and_batching_agree(cell_k):
     sysm = synthetic.lj_fluid(12, 7, seed=35)  # 1728 atoms, L = 12.7
     want, _ = oracle(sysm.positions, sysm.counts, sysm.box, 2.5, 125)
     for layout in (_cuda.LAYOUT_FRAME_MAJOR, _cuda.LAYOUT_ATOM_MAJOR):
@@ -182,7 +220,7 @@ def test_layouts_residency_and_batching_agree():
                 assert_same(got, want)
 
 
-def test_many_species_pair_groups_and_global_histogram():
+def test_many_species_pair_groups_and_global_histogram(cell_k):
     rng = np.random.default_rng(36)
     counts, box = [500, 400, 300, 200, 600], np.array([20.0, 20.0, 20.0])
     pos = (rng.random((2, 2000, 3)) * 20).astype(np.float32)
@@ -197,11 +235,12 @@ def test_path_selection_and_forced_path_errors():
     box = np.array([40.0, 40.0, 40.0])
     pos = (rng.random((1, 3000, 3)) * 40).astype(np.float32)
     _, st = run(pos, [3000], box, 5.0, 50, None)      # 7^3 cells: auto picks the cell list
-    assert st.path == _cuda.PATH_CELLLIST and st.cells == (7, 7, 7)
+    # 3000 atoms in 7^3 cutoff cells: 1.1 per half-width cell -> the classical grid
+    assert st.path == _cuda.PATH_CELLLIST and st.cells == (7, 7, 7) and st.cell_stencil == (1, 1, 1)
     _, st = run(pos, [3000], box, 12.0, 50, None)     # 3^3 cells: not worth it
     assert st.path == _cuda.PATH_ALLPAIRS and st.cells == (0, 0, 0)
     _, st = run(pos, [3000], box, 12.0, 50, "celllist")
-    assert st.path == _cuda.PATH_CELLLIST and st.cells == (3, 3, 3)
+    assert st.path == _cuda.PATH_CELLLIST and st.cells == (6, 6, 6) and st.cell_stencil == (2, 2, 2)
     with pytest.raises(_cuda.MdsCudaError, match="cell-list path needs"):
         run(pos, [3000], box, 14.0, 50, "celllist")   # 40 / 14 < 3 cells
     a, _ = run(pos, [3000], box, 12.0, 120, "celllist")
@@ -214,7 +253,7 @@ def test_cfg5_ideal_gas_bins_sweep_cells_equals_allpairs():
     for nbins in (100, 1000, 5000):
         a, sa = run(sysm.positions, sysm.counts, sysm.box, 10.0, nbins, "celllist")
         b, sb = run(sysm.positions, sysm.counts, sysm.box, 10.0, nbins, "allpairs")
-        assert sa.cells == (9, 9, 9)
+        assert sa.cells == (19, 19, 19) and sa.cell_stencil == (2, 2, 2)
         assert_same(a, b)
         assert sa.pairs_binned == sb.pairs_binned
     want, _ = oracle(sysm.positions[:1], sysm.counts, sysm.box, 10.0, 1000)
@@ -225,7 +264,7 @@ def test_cfg5_ideal_gas_bins_sweep_cells_equals_allpairs():
 def test_cfg3_lj_100k_one_frame_vs_oracle_and_allpairs():
     sysm = synthetic.lj_fluid(46, 3, seed=3)  # 97 336 atoms (46^3), cfg3's density and cutoff
     got, st = run(sysm.positions, sysm.counts, sysm.box, 3.0, 300, None)
-    assert st.path == _cuda.PATH_CELLLIST and st.cells == (16, 16, 16)
+    assert st.path == _cuda.PATH_CELLLIST and st.cells == (32, 32, 32)
     ap, _ = run(sysm.positions, sysm.counts, sysm.box, 3.0, 300, "allpairs")
     assert_same(got, ap)
     want, _ = oracle(sysm.positions[:1], sysm.counts, sysm.box, 3.0, 300)
@@ -236,7 +275,7 @@ def test_cfg3_lj_100k_one_frame_vs_oracle_and_allpairs():
 def test_cfg4_water_1m_atoms_cells_equals_allpairs():
     sysm = synthetic.spc_water(69, 1, seed=4)  # 985 527 atoms, L = 214.3
     got, st = run(sysm.positions, sysm.counts, sysm.box, 8.0, 800, None)
-    assert st.path == _cuda.PATH_CELLLIST and st.cells == (26, 26, 26)
+    assert st.path == _cuda.PATH_CELLLIST and st.cells == (53, 53, 53)
     ap, sa = run(sysm.positions, sysm.counts, sysm.box, 8.0, 800, "allpairs")
     assert_same(got, ap)
     assert st.pairs_allpairs_equiv == sa.pairs_evaluated == sysm.pairs_per_frame(True)
