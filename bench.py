@@ -7,7 +7,7 @@ bench.py — RDF pair-distance evaluations per second (BASELINE.json metric).
 
 A "step" is one pass of the hot path over one batch of synthetic frames: the RDF histogram of
 the workload's configurations for every species pair.  Default workload (configs[1] of
-BASELINE.json): 13,824-atom NaCl melt, 1,000 configurations per GPU, 3 species pairs, with the
+BASELINE.json): 13,824-atom NaCl melt, 1,000 configurations IN TOTAL, 3 species pairs, with the
 reference's default cutoff (box/2 - 0.1 = 37.7) and default bins (int(cutoff / 0.01)), parity mode.
 
 value  : pair evaluations / s with the frames already resident in HBM (raw float32 xyz), timed
@@ -17,8 +17,12 @@ e2e    : same metric through the public host-buffer call (RDFHandle.submit of pi
          -> H2D on a side stream -> kernels -> D2H of the histogram), wall clock, max over ranks.
 roofline / cpu_baseline / clocks: see DESIGN.md §6.
 
-Under torchrun (N > 1) every rank processes its own 1,000 frames (weak scaling; frames are the
-shard unit) and the per-GPU histograms are summed with one NCCL allreduce per step.
+Under torchrun (N > 1) the SAME fixed workload is split over the ranks (strong scaling): rank g
+takes block g of np.array_split(configurations, N) — the primitive the reference splits batches
+with (calculators/radial_distribution_function.py:594) — and the per-GPU histograms are summed
+with one NCCL allreduce per step.  Every line also carries `target_config`: BASELINE.json's
+north-star target (configs[2]: 100,000-atom LJ fluid, 10,000 configurations, cell-list path) at
+full size, sharded the same way, with its own parity block.
 """
 from __future__ import annotations
 
@@ -45,42 +49,43 @@ FLOP_PER_PAIR = 22  # 3 sub 3 div 3 rint 3 mul 3 sub 3 mul 2 add
 # ----------------------------------------------------------------------------------------------
 # workloads
 # ----------------------------------------------------------------------------------------------
-def make_workload(name: str, rank: int, frames: int):
+def make_workload(name: str, frames: int):
+    """The whole workload (every rank builds the same trajectory and takes its block of it)."""
     from mdsuite_b200 import synthetic
     if name == "cfg2":
-        sysm = synthetic.nacl_melt(12, frames, seed=2 + 1000 * rank)
+        sysm = synthetic.nacl_melt(12, frames, seed=2)
         cutoff = float(sysm.box[0] / 2 - 0.1)  # check_input default, reference :226-229
         nbins = int(cutoff / 0.01)  #            reference :239-242
-        desc = (f"cfg2: {sysm.n_atoms}-atom NaCl melt, {frames} configurations per GPU, 3 species "
+        desc = (f"cfg2: {sysm.n_atoms}-atom NaCl melt, {frames} configurations, 3 species "
                 f"pairs, default cutoff {cutoff:.1f} A and default {nbins} bins, parity mode")
     elif name == "cfg2_rc10":
-        sysm = synthetic.nacl_melt(12, frames, seed=2 + 1000 * rank)
+        sysm = synthetic.nacl_melt(12, frames, seed=2)
         cutoff, nbins = 10.0, 500
-        desc = (f"cfg2 variant: {sysm.n_atoms}-atom NaCl melt, {frames} configurations per GPU, "
+        desc = (f"cfg2 variant: {sysm.n_atoms}-atom NaCl melt, {frames} configurations, "
                 f"cutoff 10 A, 500 bins, parity mode")
     elif name == "cfg1":
-        sysm = synthetic.nacl_melt(5, frames, seed=1 + 1000 * rank)
+        sysm = synthetic.nacl_melt(5, frames, seed=1)
         cutoff, nbins = 10.0, 500
         desc = f"cfg1: 1000-atom NaCl melt, {frames} configurations, cutoff 10 A, 500 bins"
     elif name == "cfg5":
-        sysm = synthetic.ideal_gas(50000, frames, seed=5 + 1000 * rank)
+        sysm = synthetic.ideal_gas(50000, frames, seed=5)
         cutoff, nbins = 49.9, 1000
         desc = f"cfg5: 50k-atom ideal gas, {frames} configurations, cutoff 49.9, 1000 bins"
     elif name == "cfg5_rc10":
-        sysm = synthetic.ideal_gas(50000, frames, seed=5 + 1000 * rank)
+        sysm = synthetic.ideal_gas(50000, frames, seed=5)
         cutoff, nbins = 10.0, 1000
         desc = (f"cfg5: 50k-atom ideal gas, {frames} configurations, cutoff 10, 1000 bins "
                 f"(cell-list path)")
     elif name == "cfg3":
-        sysm = synthetic.lj_fluid(47, frames, seed=3 + 1000 * rank, n_atoms=100_000)
+        sysm = synthetic.lj_fluid(47, frames, seed=3, n_atoms=100_000)
         cutoff, nbins = 3.0, 300
         desc = (f"cfg3: {sysm.n_atoms}-atom LJ fluid (rho*=0.8442, L=49.1 sigma), {frames} "
-                f"configurations per GPU, cutoff 3.0 sigma, 300 bins, cell-list path, parity mode")
+                f"configurations, cutoff 3.0 sigma, 300 bins, cell-list path, parity mode")
     elif name == "cfg4":
-        sysm = synthetic.spc_water(70, frames, seed=4 + 1000 * rank, n_molecules=333_333)
+        sysm = synthetic.spc_water(70, frames, seed=4, n_molecules=333_333)
         cutoff, nbins = 8.0, 800
         desc = (f"cfg4: {sysm.n_atoms}-atom SPC water (333,333 molecules, L=215.3 A), {frames} "
-                f"configurations per GPU, cutoff 8 A, 800 bins, 3 species pairs, cell-list path, "
+                f"configurations, cutoff 8 A, 800 bins, 3 species pairs, cell-list path, "
                 f"parity mode")
     else:
         raise SystemExit(f"unknown workload {name}")
@@ -206,7 +211,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     per_step = max(1, min(8, int(60.0 / (4.5 * (args.steps + args.warmup)))))
-    sysm, cutoff, nbins, desc = make_workload(args.workload, 0, per_step)
+    sysm, cutoff, nbins, desc = make_workload(args.workload, per_step)
     # same workload as the GPU arm; a step of this arm is a bounded sample of it (see "sample")
     desc = desc.replace(f" {per_step} configurations", f" {args.frames} configurations", 1)
     for _ in range(args.warmup):
@@ -223,9 +228,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": desc, "frames_per_gpu": args.frames, "atoms": sysm.n_atoms,
+        "config": {"workload": desc, "frames_total": args.frames, "atoms": sysm.n_atoms,
                    "nbins": nbins, "cutoff": cutoff,
                    "species_pairs": len(sysm.counts) * (len(sysm.counts) + 1) // 2,
                    "sample": f"each step times {per_step} configuration(s) of the workload; the "
@@ -266,40 +271,63 @@ def user_api_probe(sysm, cutoff, nbins, pairs_per_step):
                     "normalisation; results not saved"}
 
 
-def cell_list_probe(device: int, fp32_peak: float, frames: int = 160):
-    """cfg3-shaped (100k-atom LJ fluid, cutoff 3 sigma, 300 bins) frames resident in HBM through the
-    cell-list kernel: candidate-pair rate against the same FP32 roofline, the all-pairs-equivalent
-    rate, and a parity gate against the all-pairs kernel on the same frames."""
-    import torch
-    from mdsuite_b200 import _cuda, synthetic
-    sysm = synthetic.lj_fluid(47, 4, seed=3, n_atoms=100_000)
-    base = torch.from_numpy(sysm.positions).cuda(device)
-    pos = base.repeat((frames + 3) // 4, 1, 1)[:frames].contiguous()
-    best = None
-    with _cuda.RDFHandle(sysm.counts, 300, 3.0, sysm.box, device=device) as h:
-        for _ in range(4):
-            h.reset()
-            h.submit_device(pos)
-            st = h.stats()
-            if best is None or st.pair_kernel_ms < best[0]:
-                best = (st.pair_kernel_ms, st.submit_ms)
-        h.reset()
-        h.submit_device(base)
-        cells = h.counts()
-    with _cuda.RDFHandle(sysm.counts, 300, 3.0, sysm.box, device=device, path="allpairs") as h:
-        h.submit_device(base)
-        allp = h.counts()
-    cand = st.pairs_evaluated / (best[0] * 1e-3)
-    return {
-        "workload": f"cfg3-shaped: {sysm.n_atoms}-atom LJ fluid, cutoff 3.0, 300 bins, {frames} frames "
-                    f"resident in HBM, best of 4",
-        "kernel": "rdf_cells_kernel", "cells": list(st.cells),
-        "candidate_pair_evals_per_s": cand, "frac_of_fp32_roofline": cand * FLOP_PER_PAIR / fp32_peak,
-        "binned_over_candidates": st.pairs_binned / st.pairs_evaluated,
-        "allpairs_equivalent_per_s": st.pairs_allpairs_equiv / (best[1] * 1e-3),
-        "us_per_frame": best[1] * 1e3 / frames,
-        "bins_differing_vs_allpairs_kernel": int((cells != allp).sum()),
-    }
+def load_integration_stub():
+    """The reference-side binding exactly as INTEGRATION.md §2 prints it (the first python block of
+    that section), executed with the library name resolved to the in-tree build."""
+    from mdsuite_b200 import _cuda
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as fh:
+        text = fh.read()
+    section = text[text.index("## 2."):]
+    code = section[section.index("```python") + len("```python"):]
+    code = code[:code.index("```")]
+    code = code.replace('ctypes.CDLL("libmds_rdf.so")', "ctypes.CDLL(%r)" % _cuda.LIB_PATH)
+    namespace = {}
+    exec(compile(code, "INTEGRATION.md#2", "exec"), namespace)  # noqa: S102 - our own document
+    return namespace["RDFHandle"]
+
+
+def reference_binding_probe(sysm, cutoff, nbins, device, e2e_value):
+    """The call a reference maintainer would make: the literal ctypes stub,
+    PAGEABLE NumPy batches in the reference's (N, C, 3) layout, one submit per batch as in the loop
+    it replaces (reference calculators/radial_distribution_function.py:846-885) — with C = 1 (what
+    the reference's memory manager picks at this size) and C = 64."""
+    RDFHandle = load_integration_stub()
+    n_frames = sysm.n_frames
+    pairs = sysm.pairs_per_frame(parity=True) * n_frames
+    out = {"stub": "INTEGRATION.md section 2, executed as printed", "host_memory": "pageable numpy",
+           "layout": "(N, C, 3) atom-major", "e2e_value_pinned_frame_major": e2e_value}
+    want = None
+    for C in (1, 64):
+        batches = [np.ascontiguousarray(sysm.positions[f0:f0 + C].transpose(1, 0, 2))
+                   for f0 in range(0, n_frames, C)]
+        # one handle per calculator run, as in the patched loop; the first pass over the batches
+        # pays for the handle's lazily allocated staging buffers (reported separately), the timed
+        # passes add to the same accumulator (the stub has no reset): k passes = k x the histogram
+        handle = RDFHandle(sysm.counts, nbins, cutoff, sysm.box, device=device)
+        t0 = time.perf_counter()
+        for b in batches:
+            handle.submit(b)
+        first = handle.counts()
+        first_s = time.perf_counter() - t0
+        best = None
+        for k in range(2, 5):
+            t0 = time.perf_counter()
+            for b in batches:
+                handle.submit(b)
+            counts = handle.counts()
+            dt = time.perf_counter() - t0
+            best = dt if best is None or dt < best else best
+            if not np.array_equal(counts, first * np.uint64(k)):
+                raise RuntimeError("reference binding: accumulated histogram is not k x the first pass")
+        handle.close()
+        counts = first
+        if want is None:
+            want = counts
+        out[f"C{C}"] = {"batches": len(batches), "seconds": best, "first_pass_seconds": first_s,
+                        "value": pairs / best, "unit": UNIT,
+                        "ratio_to_e2e": pairs / best / e2e_value,
+                        "same_histogram": bool(np.array_equal(counts, want))}
+    return out
 
 
 def adf_probe(device: int, frames: int = 64, check: bool = True):
@@ -341,6 +369,147 @@ def adf_probe(device: int, frames: int = 64, check: bool = True):
     }
 
 
+def target_config_probe(args, world, rank, local_rank, dist, fp32_peak):
+    """BASELINE.json's north-star target at FULL size: RDF of the 100,000-atom LJ fluid over 10,000
+    configurations (cell-list path, cutoff 3 sigma, 300 bins, parity mode), the configurations
+    split over the ranks with np.array_split, one NCCL allreduce per step.
+
+    The trajectory is 40 distinct seeded frames used 250 times each (frame i of the 10,000 is base
+    frame i % 40): generating 12 GB of Gaussian displacements would take longer than every
+    measurement here, and the kernels do the same work on a repeated frame.  That also gives the
+    parity gate: the allreduced histogram must equal 250 x the single-handle histogram of the 40
+    base frames, and one base frame is checked against the fused-C oracle.
+
+    resident: this rank's frames in HBM as raw xyz.  e2e: pinned host frames through
+    RDFHandle.submit (a block of at most 1,200 frames submitted repeatedly: every byte crosses
+    PCIe every step)."""
+    import torch
+    from mdsuite_b200 import _cuda, synthetic
+    n_total, n_base = 10_000, 40
+    steps = max(1, min(args.steps, args.target_steps))
+    sysm = synthetic.lj_fluid(47, n_base, seed=3, n_atoms=100_000)
+    cutoff, nbins = 3.0, 300
+    mine = np.array_split(np.arange(n_total), world)[rank]
+    base_dev = torch.from_numpy(sysm.positions).cuda(local_rank)
+    idx = torch.from_numpy(mine % n_base).cuda(local_rank)
+    dev = base_dev[idx].contiguous() if len(mine) else base_dev[:0]
+    block = min(len(mine), 1200)  # a multiple of the 40 base frames: every block is the same sequence
+    host = torch.from_numpy(sysm.positions[mine[:block] % n_base]).pin_memory() if block else None
+    handle = _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, parity=True, device=local_rank)
+    counts_dev = counts_tensor(handle, handle.n_pairs, nbins) if dist is not None else None
+    pairs_total = sysm.pairs_per_frame(parity=True) * n_total
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        if dist is not None:
+            handle.wait()
+        handle.reset()
+        if len(mine):
+            handle.submit_device(dev)
+        handle.join()
+        if dist is not None:
+            dist.all_reduce(counts_dev)
+
+    def step_e2e():
+        if dist is not None:
+            handle.wait()
+        handle.reset()
+        done = 0
+        while done < len(mine):
+            n = min(block, len(mine) - done)
+            # frames done .. done + n of this rank are base frames (mine[done + k] % 40): the pinned
+            # block holds exactly that sequence when `done` is a multiple of the block
+            handle.submit(host[:n], pinned=True)
+            done += n
+        if dist is not None:
+            handle.join()
+            dist.all_reduce(counts_dev)
+            handle.wait()
+        return handle.counts()
+
+    def timed(fn):
+        fn()
+        handle.stats()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(steps):
+            out = fn()
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = ev0.elapsed_time(ev1)
+        if dist is not None:
+            t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0].item()), float(t[1].item())
+        return ms / steps, wall / steps, out
+
+    res_ms, _w, _ = timed(step_resident)
+    st = handle.stats()
+    result = handle.counts()
+    _ms, e2e_s, result_e2e = timed(step_e2e)
+
+    # local statistics of one un-reduced pass (the accumulator holds the global sum after a step)
+    handle.reset()
+    if len(mine):
+        handle.submit_device(dev)
+    st_local = handle.stats()
+    parity = None
+    if rank == 0:
+        with _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, parity=True, device=local_rank) as h:
+            h.submit_device(base_dev)
+            h40 = h.counts()
+            h.reset()
+            h.submit_device(base_dev[:1].contiguous())
+            h1 = h.counts()
+        parity = {
+            "frames_total": n_total,
+            "expected": "250 x the single-handle histogram of the 40 base frames (rank 0)",
+            "bins_differing_resident": int((result != h40 * np.uint64(n_total // n_base)).sum()),
+            "bins_differing_e2e": int((result_e2e != h40 * np.uint64(n_total // n_base)).sum()),
+        }
+        if not args.no_cpu_baseline:
+            from oracle import c_oracle  # the checker
+            want, _ev = c_oracle.rdf_counts_c(sysm.positions[:1], sysm.counts, sysm.box, cutoff, nbins,
+                                              skip_first=True, layout=c_oracle.FRAME_MAJOR)
+            parity["frames_checked_fused_c"] = 1
+            parity["bins_differing_fused_c"] = int((h1.astype(np.int64) != want).sum())
+    handle.close()
+    if rank != 0:
+        return None
+    launches = max(1, st.pair_kernel_launches)
+    kernel_s = st.pair_kernel_ms * 1e-3
+    cand_rate = st_local.pairs_evaluated * steps / max(kernel_s, 1e-12)
+    tested_rate = st_local.pairs_tested * steps / max(kernel_s, 1e-12)
+    return {
+        "workload": "cfg3 (BASELINE.json configs[2], the north-star target) at full size: 100,000-atom "
+                    "LJ fluid (rho*=0.8442, L=49.1 sigma), 10,000 configurations in total, cutoff 3.0 "
+                    "sigma, 300 bins, cell-list path, parity mode",
+        "frames_total": n_total, "frames_rank0": int(len(mine)), "distinct_frames": n_base,
+        "steps": steps, "n_gpus": world,
+        "ms_per_step_resident": res_ms, "ms_per_step_e2e": 1e3 * e2e_s,
+        "allpairs_equivalent_per_s_resident": pairs_total / (res_ms * 1e-3),
+        "allpairs_equivalent_per_s_e2e": pairs_total / e2e_s,
+        "h2d_bytes_per_step": int(12 * sysm.n_atoms * n_total), "d2h_bytes_per_step": int(8 * nbins),
+        "kernel": "rdf_cells_kernel", "cells": list(st.cells), "cell_stencil": list(st.cell_stencil),
+        "rank0_pair_kernel_ms_per_step": st.pair_kernel_ms / steps,
+        "rank0_pair_kernel_launches_per_step": launches / steps,
+        "rank0_kernel_share_of_resident_step": st.pair_kernel_ms / steps / res_ms,
+        "candidate_pair_evals_per_s_per_gpu": cand_rate,
+        "frac_of_fp32_roofline_candidates": cand_rate * FLOP_PER_PAIR / fp32_peak,
+        "tested_pair_evals_per_s_per_gpu": tested_rate,
+        "frac_of_fp32_roofline_tested": tested_rate * FLOP_PER_PAIR / fp32_peak,
+        "binned_over_candidates": st_local.pairs_binned / max(st_local.pairs_evaluated, 1.0),
+        "parity": parity,
+    }
+
+
 def run_ours(args):
     import torch
     from mdsuite_b200 import _cuda
@@ -356,22 +525,22 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout; the
-        # contract is ONE JSON line there
-        if "BENCH_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        # NCCL's log (NCCL_DEBUG) stays as the environment sets it: fd 1 already points at stderr
+        # (claim_stdout), so nothing but the JSON line reaches stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    sysm, cutoff, nbins, desc = make_workload(args.workload, rank, args.frames)
-    n_frames, n_atoms = sysm.n_frames, sysm.n_atoms
-    host = torch.from_numpy(sysm.positions).pin_memory()
+    # the same fixed workload on every rank; rank g takes block g of np.array_split (strong scaling)
+    sysm, cutoff, nbins, desc = make_workload(args.workload, args.frames)
+    n_total, n_atoms = sysm.n_frames, sysm.n_atoms
+    mine = np.array_split(np.arange(n_total), world)[rank]
+    n_frames = len(mine)
+    host = torch.from_numpy(sysm.positions[mine[0]:mine[-1] + 1] if n_frames else
+                            sysm.positions[:0]).pin_memory()
     dev = host.cuda(non_blocking=False)
     handle = _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, parity=True, device=local_rank)
     n_pairs = handle.n_pairs
     counts_dev = counts_tensor(handle, n_pairs, nbins) if world > 1 else None
-    pairs_per_step = sysm.pairs_per_frame(parity=True) * n_frames
+    pairs_per_step = sysm.pairs_per_frame(parity=True) * n_total  # the whole job, all ranks
 
     def barrier():
         if dist is not None:
@@ -382,7 +551,8 @@ def run_ours(args):
         if dist is not None:
             handle.wait()  # the previous step's allreduce reads the accumulator
         handle.reset()
-        handle.submit_device(dev)
+        if n_frames:
+            handle.submit_device(dev)
         handle.join()
         if dist is not None:
             dist.all_reduce(counts_dev)
@@ -391,12 +561,20 @@ def run_ours(args):
         if dist is not None:
             handle.wait()
         handle.reset()
-        handle.submit(host, pinned=True)
+        if n_frames:
+            handle.submit(host, pinned=True)
         if dist is not None:
             handle.join()
             dist.all_reduce(counts_dev)
             handle.wait()
         return handle.counts()
+
+    # ---- this rank's own statistics: one un-reduced pass (after a step the accumulator holds
+    # the sum over all ranks) --------------------------------------------------------------------
+    handle.reset()
+    if n_frames:
+        handle.submit_device(dev)
+    st_local = handle.stats()
 
     # ---- HBM-resident timing (value) -------------------------------------------------------
     for _ in range(max(args.warmup, 0)):
@@ -426,7 +604,7 @@ def run_ours(args):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * pairs_per_step * args.steps / (ms * 1e-3)
+    value = pairs_per_step * args.steps / (ms * 1e-3)
 
     # ---- end to end through host buffers (e2e) ---------------------------------------------
     for _ in range(max(1, min(args.warmup, 3))):
@@ -441,33 +619,66 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * pairs_per_step * args.steps / e2e_s
+    e2e_value = pairs_per_step * args.steps / e2e_s
     if not np.array_equal(result, result_e2e):
         raise SystemExit("bench.py: HBM-resident and end-to-end histograms differ")
 
+    peaks, peaks_src = measured_peaks()
+    f_max = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    fp32_peak = st.sm_count * 128 * f_max  # non-FMA FP32 issue, op/s
+
+    # ---- the north-star target configuration at full size (every rank takes part) -----------
+    target = None
+    if not args.no_target_config:
+        try:
+            target = target_config_probe(args, world, rank, local_rank, dist, fp32_peak)
+        except Exception as exc:  # noqa: BLE001
+            if dist is not None:
+                raise  # a rank that drops out would leave the others in the collective
+            target = {"error": str(exc)}
+
+    # ---- multi-rank parity: the sharded + allreduced histogram against ONE handle on rank 0 over
+    # all the frames, and the first frames against the fused-C oracle ---------------------------
+    parity_multi = None
+    if world > 1 and rank == 0:
+        with _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, parity=True, device=local_rank) as h:
+            h.submit(sysm.positions)
+            single = h.counts()
+        parity_multi = {"frames_total": n_total, "ranks": world,
+                        "bins_differing_vs_single_handle": int((single != result).sum()),
+                        "bins_differing_e2e_vs_single_handle": int((single != result_e2e).sum())}
+        if not args.no_cpu_baseline:
+            n_c = max(1, min(n_total, args.cpu_frames))
+            _r, _dt, c_fused, _th = cpu_fused_c_rate(sysm, cutoff, nbins, n_c)
+            with _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, parity=True,
+                                 device=local_rank) as h:
+                h.submit(sysm.positions[:n_c])
+                got = h.counts().astype(np.int64)
+            parity_multi["frames_checked_fused_c"] = n_c
+            parity_multi["bins_differing_fused_c"] = int((got != c_fused).sum())
+
     if rank != 0:
+        handle.close()
         if dist is not None:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (the all-pairs pair kernel) -----------------------
-    peaks, peaks_src = measured_peaks()
+    # ---- roofline of the dominant kernel (the all-pairs pair kernel), rank 0's launches -------
     sm_count = st.sm_count
-    f_max = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
-    fp32_peak = sm_count * 128 * f_max  # non-FMA FP32 issue, op/s
     launches = max(1, st.pair_kernel_launches)
     avg_launch_s = st.pair_kernel_ms * 1e-3 / launches
     # pairs the pair kernel distance-tested per launch: every reference pair on the all-pairs
-    # path, the candidates of adjacent cells on the cell-list path
-    pairs_per_launch = st.pairs_evaluated * args.steps / launches
+    # path, the candidates of nearby cells on the cell-list path — this rank's own
+    pairs_per_launch = st_local.pairs_evaluated * args.steps / launches
     kernel_rate = pairs_per_launch / avg_launch_s
     kernel_name = "rdf_cells_kernel" if st.path == _cuda.PATH_CELLLIST else "rdf_allpairs_kernel"
     achieved = kernel_rate * FLOP_PER_PAIR
-    kernel_share = st.pair_kernel_ms / ms if world == 1 else None
+    kernel_share = st.pair_kernel_ms / ms
     atom = {}
     try:
         spread, rnd, mhz = _cuda.bench_shared_atomics(local_rank, max(64, n_pairs * (nbins + 1)), 4096)
-        binned_frac = st.pairs_binned / max(st.pairs_evaluated, 1.0)
+        binned_frac = st_local.pairs_binned / max(st_local.pairs_evaluated, 1.0)
         # dense binning issues one shared atomic per evaluated pair (out-of-cutoff lanes hit the
         # sink slot); the sparse path only for binned pairs
         atomics_per_pair = 1.0 if st.dense else binned_frac
@@ -499,7 +710,7 @@ def run_ours(args):
         "peak": fp32_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
         "traffic": traffic, "pair_evals_per_s": kernel_rate,
         "pair_evals_per_s_peak": fp32_peak / FLOP_PER_PAIR, "flop_per_pair": FLOP_PER_PAIR,
-        "allpairs_equivalent_per_s": pairs_per_step * args.steps / launches / avg_launch_s,
+        "measured_on": "rank 0's launches (per GPU)",
         "launches_timed": st.pair_kernel_launches, "avg_launch_ms": avg_launch_s * 1e3,
         "kernel_share_of_step": kernel_share,
         "peak_source": f"{sm_count} SMs x 128 lanes x sm_max_mhz from {peaks_src} (non-FMA issue rate)",
@@ -510,14 +721,6 @@ def run_ours(args):
                 "achieved_gbs": 12.0 * n_atoms * n_frames * args.steps / launches / avg_launch_s / 1e9,
                 "peak_gbs": peaks.get("hbm_gbs")},
     }
-
-    # ---- the other kernel of the path: a short cell-list measurement (rank 0, N = 1 only) ----
-    cell_list = None
-    if world == 1 and st.path != _cuda.PATH_CELLLIST and not args.no_cell_probe:
-        try:
-            cell_list = cell_list_probe(local_rank, fp32_peak)
-        except Exception as exc:  # noqa: BLE001
-            cell_list = {"error": str(exc)}
 
     # ---- the sibling structural path, the ADF (rank 0, N = 1 only) ---------------------------
     adf = None
@@ -535,9 +738,17 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             user_api = {"error": str(exc)}
 
+    # ---- the literal reference-side binding of INTEGRATION.md §2 (rank 0, N = 1 only) --------
+    binding = None
+    if world == 1 and not args.no_binding_probe:
+        try:
+            binding = reference_binding_probe(sysm, cutoff, nbins, local_rank, e2e_value)
+        except Exception as exc:  # noqa: BLE001
+            binding = {"error": str(exc)}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------
     cpu_baseline = None
-    parity = None
+    parity = parity_multi
     if world == 1 and not args.no_cpu_baseline:
         n_ref = max(1, min(n_frames, args.cpu_frames))
         rate, dt, c_ref, threads = cpu_reference_rate(sysm, cutoff, nbins, n_ref)
@@ -563,19 +774,23 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "frames_per_gpu": n_frames, "atoms": n_atoms, "nbins": nbins,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "frames_total": n_total, "frames_rank0": n_frames,
+                   "atoms": n_atoms, "nbins": nbins,
                    "cutoff": cutoff, "species_pairs": n_pairs,
-                   "l2": f"inputs larger than L2: {12 * n_atoms * n_frames / 1e6:.0f} MB raw xyz + "
-                         f"{12 * n_atoms * n_frames / 1e6:.0f} MB packed per step vs 126 MB L2",
-                   "parallelism": f"frames sharded over {world} GPU(s), 1 NCCL allreduce/step"
-                   if world > 1 else "1 GPU"},
-        "roofline": roofline, "cell_list_path": cell_list, "adf_path": adf, "user_api": user_api,
+                   "l2": f"inputs larger than L2 at N=1: {12 * n_atoms * n_total / 1e6:.0f} MB raw xyz + "
+                         f"{12 * n_atoms * n_total / 1e6:.0f} MB packed per step vs 126 MB L2 "
+                         f"(rank 0 here: {12 * n_atoms * n_frames / 1e6:.0f} MB raw)",
+                   "parallelism": f"the {n_total} configurations split over {world} GPU(s) with "
+                                  f"np.array_split, 1 NCCL allreduce/step" if world > 1 else "1 GPU"},
+        "roofline": roofline, "target_config": target, "adf_path": adf, "user_api": user_api,
+        "e2e_reference_binding": binding,
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
-                "h2d_bytes_per_step": int(12 * n_atoms * n_frames),
-                "d2h_bytes_per_step": int(8 * n_pairs * nbins)},
+                "h2d_bytes_per_step": int(12 * n_atoms * n_total),
+                "d2h_bytes_per_step": int(8 * n_pairs * nbins) * world},
         "gpu_launches": int(st.kernel_launches * args.steps),
+        "gpu_launches_note": "rank 0's kernels in the timed region" if world > 1 else None,
         "clocks": clocks, "parity": parity,
         "kernel_variant": {"path": st.path_name, "variant": st.variant, "dense": st.dense,
                            "cells": list(st.cells)},
@@ -583,6 +798,7 @@ def run_ours(args):
     emit(line)
     handle.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -618,7 +834,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
-    ap.add_argument("--frames", type=int, default=1000, help="configurations per GPU per step")
+    ap.add_argument("--frames", type=int, default=1000, help="configurations per step")
     ap.add_argument("--cpu-frames", type=int, default=12,
                     help="configurations timed by the op-by-op CPU baseline (x8 for the C port)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -626,8 +842,12 @@ def main():
                     help="skip the Project -> Experiment -> run.RadialDistributionFunction timing")
     ap.add_argument("--no-adf-probe", action="store_true",
                     help="skip the short angular-distribution measurement added at N=1")
-    ap.add_argument("--no-cell-probe", action="store_true",
-                    help="skip the short cfg3-shaped cell-list measurement added at N=1")
+    ap.add_argument("--no-target-config", action="store_true",
+                    help="skip the full-size north-star block (100k atoms x 10k configurations)")
+    ap.add_argument("--target-steps", type=int, default=3,
+                    help="timed steps of the full-size north-star block (at most --steps)")
+    ap.add_argument("--no-binding-probe", action="store_true",
+                    help="skip the INTEGRATION.md reference-side binding measurement added at N=1")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

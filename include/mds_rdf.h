@@ -122,9 +122,16 @@ MDS_API int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg);
 MDS_API void mds_rdf_destroy(mds_rdf_t* h);
 
 /* Accumulate the histograms of n_frames configurations held in HOST memory (replaces one or more
- * iterations of the batch loop :846-885).  Asynchronous: copies go on a side stream in
- * max_frames_in_flight chunks, double buffered against the kernels.  host_is_pinned != 0 promises
- * page-locked memory (true async copies); otherwise the copy is staged by the driver. */
+ * iterations of the batch loop :846-885).  Asynchronous.
+ *   host_is_pinned != 0  promises page-locked memory: the frames are copied straight out of the
+ *     caller's buffer on a side stream in max_frames_in_flight chunks, double buffered against the
+ *     kernels; the buffer must stay untouched until mds_rdf_wait_host_copies / a synchronising call.
+ *   host_is_pinned == 0  (pageable memory, e.g. a NumPy array per batch): the calling thread copies
+ *     the frames into the library's own ring of pinned buffers (transposing the atom-major layout
+ *     to frame-major on the way); a buffer travels to the device when it is full or when results
+ *     are asked for.  The caller's buffer may be reused as soon as the call returns, and many
+ *     small calls (one configuration each, as the reference batches at default memory settings)
+ *     cost one memcpy each instead of one transfer + four kernel launches each. */
 MDS_API int mds_rdf_submit(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
                    int host_is_pinned);
 

@@ -137,6 +137,13 @@ struct mds_rdf {
   unsigned long long* d_evaluated = nullptr; // [2] pairs evaluated (candidates on the cell path) / tested
   unsigned long long* d_batch_far = nullptr; // [2] far frames of the batch in each buffer
   size_t raw_bytes = 0;
+  // pageable host submits: frames are copied (and, for the atom-major layout, transposed to frame
+  // major) into a ring of pinned buffers by the calling thread and sent on when a buffer is full
+  float* stage[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_stage_done[3] = {nullptr, nullptr, nullptr};  // H2D out of the buffer finished
+  int stage_slot = 0;
+  int64_t stage_frames = 0;     // frames waiting in stage[stage_slot]
+  int64_t stage_capacity = 0;   // frames per buffer
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   cudaEvent_t ev_raw_ready[2] = {nullptr, nullptr};  // H2D of staging buffer done
   cudaEvent_t ev_raw_free[2] = {nullptr, nullptr};   // pack consumed staging buffer
@@ -324,7 +331,12 @@ int next_work_slot(mds_rdf* h) {
   return h->work_slot++;
 }
 
+// At most PK_MAX launches are timed between two mds_rdf_stats_get calls: a long-lived handle whose
+// owner never asks for statistics must not pile up events without bound.
+constexpr int PK_MAX = 16384;
+
 int timed_launch_begin(mds_rdf* h) {
+  if (h->pk_used >= PK_MAX) return MDS_OK;
   if ((int)h->pk_events.size() < 2 * (h->pk_used + 1)) {
     cudaEvent_t a = nullptr, b = nullptr;
     CUDA_TRY(cudaEventCreate(&a));
@@ -337,9 +349,10 @@ int timed_launch_begin(mds_rdf* h) {
 }
 
 int timed_launch_end(mds_rdf* h) {
+  h->launches += 1;
+  if (h->pk_used >= PK_MAX) return MDS_OK;
   CUDA_TRY(cudaEventRecord(h->pk_events[2 * h->pk_used + 1], h->s_compute));
   h->pk_used += 1;
-  h->launches += 1;
   return MDS_OK;
 }
 
@@ -602,18 +615,25 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
     h->path = (forced_cells || (!forced_all && auto_cells)) ? MDS_RDF_PATH_CELLLIST
                                                             : MDS_RDF_PATH_ALLPAIRS;
     if (h->path == MDS_RDF_PATH_CELLLIST) {
-      // Half-width cells test 15.6 instead of 27 cutoff-cell volumes per atom, but every row cell
-      // costs a fixed amount; below ~1.5 atoms of the most populous species per fine cell the
-      // classical grid wins (MDS_RDF_CELL_K = 1 | 2 | "kx,ky,kz" overrides).
+      // Finer cells along x (the direction the kernel sweeps): with kx cells per cutoff length the
+      // partners of an atom lie in 2 + 1/kx cutoff lengths of x instead of 3, at the price of
+      // fewer rows per cell.  Measured on the BASELINE shapes: about 8 atoms of the
+      // most populous species per cell is the sweet spot; y and z stay cutoff-sized — halving them
+      // too cuts the candidates further (15.6 instead of 22.5 cutoff-cell volumes) but quadruples
+      // the staging work per row atom, which costs more than it saves unless the cells are full.
+      // MDS_RDF_CELL_K = k | "kx,ky,kz" overrides (kx <= 4, ky, kz <= 2).
       int max_pcnt = 0;
       for (int c : h->pcnt) max_pcnt = std::max(max_pcnt, c);
-      int K[3] = {2, 2, 2};
-      if ((double)max_pcnt / ((double)nc1 * 8.0) < 1.5) K[0] = K[1] = K[2] = 1;
+      const double per_cutoff_cell = (double)max_pcnt / (double)nc1;
+      int K[3] = {std::min(4, std::max(1, (int)std::floor(per_cutoff_cell / 8.0 + 0.5))), 1, 1};
+      // dense systems (>= 6 atoms per half-width cell, e.g. the 50k-atom gas with cutoff 10): there
+      // the half-width grid in all three dimensions is ahead
+      if (per_cutoff_cell >= 48.0) K[0] = K[1] = K[2] = 2;
       if (const char* env = getenv("MDS_RDF_CELL_K")) {
         int a = 0, b = 0, c = 0;
         const int got = sscanf(env, "%d,%d,%d", &a, &b, &c);
         if (got == 1) b = c = a;
-        if ((got == 1 || got == 3) && a >= 1 && a <= 2 && b >= 1 && b <= 2 && c >= 1 && c <= 2) {
+        if ((got == 1 || got == 3) && a >= 1 && a <= 4 && b >= 1 && b <= 2 && c >= 1 && c <= 2) {
           K[0] = a; K[1] = b; K[2] = c;
         }
       }
@@ -744,7 +764,7 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
         int seg = 1;
         for (int sg = 1; sg <= seg_max; ++sg) {
           const double staged = P * (sg + 2 * K0) * rho_c + (sg + K0) * rho_r;
-          if (staged <= 0.75 * h->cap_atoms && (sg + 2 * K0) * P <= 1024) seg = sg;
+          if (staged <= 0.75 * h->cap_atoms && (sg + 2 * K0) * P <= mds::cells_max_entries()) seg = sg;
         }
         const int pieces = (h->grid.nx + seg - 1) / seg;  // even pieces
         seg = (h->grid.nx + pieces - 1) / pieces;
@@ -813,6 +833,10 @@ void mds_rdf_destroy(mds_rdf_t* h) {
     if (h->ev_raw_ready[b]) cudaEventDestroy(h->ev_raw_ready[b]);
     if (h->ev_raw_free[b]) cudaEventDestroy(h->ev_raw_free[b]);
   }
+  for (int k = 0; k < 3; ++k) {
+    if (h->stage[k]) cudaFreeHost(h->stage[k]);
+    if (h->ev_stage_done[k]) cudaEventDestroy(h->ev_stage_done[k]);
+  }
   if (h->ev_ext) cudaEventDestroy(h->ev_ext);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (cudaEvent_t e : h->pk_events) cudaEventDestroy(e);
@@ -824,6 +848,8 @@ void mds_rdf_destroy(mds_rdf_t* h) {
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   delete h;
 }
+
+static int flush_stage(mds_rdf_t* h);
 
 static int check_submit_args(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
                              const char* who) {
@@ -842,6 +868,8 @@ int mds_rdf_submit_device(mds_rdf_t* h, const float* d_xyz, int64_t n_frames, in
   if (n_frames == 0) return MDS_OK;
   NvtxRange range("mds_rdf_submit_device");
   DeviceGuard guard(h->device);
+  rc = flush_stage(h);  // frames submitted earlier go first
+  if (rc != MDS_OK) return rc;
   CUDA_TRY(cudaEventRecord(h->ev_ext, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_ext, 0));
   CUDA_TRY(cudaEventRecord(h->ev_t0, h->s_compute));
@@ -859,14 +887,10 @@ int mds_rdf_submit_device(mds_rdf_t* h, const float* d_xyz, int64_t n_frames, in
   return MDS_OK;
 }
 
-int mds_rdf_submit(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
-                   int host_is_pinned) {
-  int rc = check_submit_args(h, xyz, n_frames, layout, "mds_rdf_submit");
-  if (rc != MDS_OK) return rc;
-  if (n_frames == 0) return MDS_OK;
+// Host frames in page-locked memory: H2D on the side stream in batches, double buffered against
+// the kernels.
+static int submit_pinned(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout) {
   NvtxRange range("mds_rdf_submit (host frames)");
-  (void)host_is_pinned;  // cudaMemcpyAsync stages pageable memory itself
-  DeviceGuard guard(h->device);
   const size_t frame_bytes = (size_t)h->n_atoms * 3 * sizeof(float);
   const size_t need = std::max<size_t>(16, frame_bytes * (size_t)h->batch_frames);
   if (h->raw_bytes < need) {
@@ -896,6 +920,10 @@ int mds_rdf_submit(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
     if (layout == MDS_LAYOUT_FRAME_MAJOR_XYZ) {
       CUDA_TRY(cudaMemcpyAsync(h->d_raw[b], xyz + (size_t)f0 * h->n_atoms * 3, frame_bytes * nf,
                                cudaMemcpyHostToDevice, h->s_copy));
+    } else if (nf == n_frames) {
+      // atom-major and the whole call in one batch (the reference's (N, C, 3) positions_tensor
+      // with a modest C): the block is contiguous, one plain copy
+      CUDA_TRY(cudaMemcpyAsync(h->d_raw[b], xyz, frame_bytes * nf, cudaMemcpyHostToDevice, h->s_copy));
     } else {
       // atom-major: one strided 2-D copy gathers frames [f0, f0+nf) of every atom
       CUDA_TRY(cudaMemcpy2DAsync(h->d_raw[b], (size_t)nf * 12, xyz + (size_t)f0 * 3,
@@ -909,7 +937,7 @@ int mds_rdf_submit(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
       first_kernel = false;
     }
     // inside the staging buffer the batch starts at frame 0 and holds nf frames
-    rc = process_batch(h, h->d_raw[b], layout, 0, nf, nf, b);
+    const int rc = process_batch(h, h->d_raw[b], layout, 0, nf, nf, b);
     if (rc != MDS_OK) return rc;
     CUDA_TRY(cudaEventRecord(h->ev_raw_free[b], h->s_compute));
     h->buf ^= 1;
@@ -922,9 +950,105 @@ int mds_rdf_submit(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
   return MDS_OK;
 }
 
+// Send the frames waiting in the current pinned ring buffer (pageable submits) on their way.
+static int flush_stage(mds_rdf_t* h) {
+  if (h->stage_frames == 0) return MDS_OK;
+  const int slot = h->stage_slot;
+  const int64_t nf = h->stage_frames;
+  h->stage_frames = 0;
+  h->stage_slot = (slot + 1) % 3;
+  const int rc = submit_pinned(h, h->stage[slot], nf, MDS_LAYOUT_FRAME_MAJOR_XYZ);
+  if (rc != MDS_OK) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev_stage_done[slot], h->s_copy));  // every H2D out of the slot is queued
+  return MDS_OK;
+}
+
+// Host frames in PAGEABLE memory (the reference-side binding passes plain NumPy arrays, one batch
+// of C configurations per call).  A cudaMemcpyAsync from pageable memory is
+// staged by the driver call by call and an atom-major batch would go as N rows of C x 12 bytes;
+// instead the calling thread copies the frames into a ring of pinned buffers — transposing the
+// (N, C, 3) layout to frame-major on the way — and a buffer is sent when it is full or when the
+// caller asks for results.  The caller's array may be reused as soon as the call returns.
+static int submit_pageable(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout) {
+  NvtxRange range("mds_rdf_submit (pageable host frames)");
+  const size_t frame_floats = (size_t)h->n_atoms * 3;
+  if (frame_floats == 0) { h->frames_done += n_frames; return MDS_OK; }
+  if (!h->stage[0]) {
+    const size_t frame_bytes = frame_floats * sizeof(float);
+    h->stage_capacity = std::max<int64_t>(1, std::min<int64_t>(h->batch_frames,
+                                                               (int64_t)((16u << 20) / frame_bytes)));
+    for (int k = 0; k < 3; ++k) {
+      CUDA_TRY(cudaHostAlloc((void**)&h->stage[k], frame_bytes * (size_t)h->stage_capacity,
+                             cudaHostAllocDefault));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_stage_done[k], cudaEventDisableTiming));
+    }
+  }
+  if (layout == MDS_LAYOUT_ATOM_MAJOR_XYZ && n_frames == 1) layout = MDS_LAYOUT_FRAME_MAJOR_XYZ;  // same bytes
+  if (layout == MDS_LAYOUT_ATOM_MAJOR_XYZ && n_frames <= h->stage_capacity) {
+    // a (N, C, 3) block that fits one buffer: copy it as it is — the pack kernel reads the
+    // atom-major layout directly — and send it as a batch of its own
+    int rc = flush_stage(h);
+    if (rc != MDS_OK) return rc;
+    const int slot = h->stage_slot;
+    CUDA_TRY(cudaEventSynchronize(h->ev_stage_done[slot]));
+    memcpy(h->stage[slot], xyz, (size_t)n_frames * frame_floats * sizeof(float));
+    h->stage_slot = (slot + 1) % 3;
+    rc = submit_pinned(h, h->stage[slot], n_frames, MDS_LAYOUT_ATOM_MAJOR_XYZ);
+    if (rc != MDS_OK) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_stage_done[slot], h->s_copy));
+    return MDS_OK;
+  }
+  for (int64_t f0 = 0; f0 < n_frames;) {
+    if (h->stage_frames == 0)  // first write into this buffer: its previous copies must be done
+      CUDA_TRY(cudaEventSynchronize(h->ev_stage_done[h->stage_slot]));
+    const int64_t nf = std::min<int64_t>(h->stage_capacity - h->stage_frames, n_frames - f0);
+    float* dst = h->stage[h->stage_slot] + (size_t)h->stage_frames * frame_floats;
+    if (layout == MDS_LAYOUT_FRAME_MAJOR_XYZ) {
+      memcpy(dst, xyz + (size_t)f0 * frame_floats, (size_t)nf * frame_floats * sizeof(float));
+    } else {
+      // (N, C, 3) with more configurations than a buffer holds -> (nf, N, 3), in blocks of atoms so
+      // that both sides stay in cache
+      const int64_t N = h->n_atoms;
+      for (int64_t a0 = 0; a0 < N; a0 += 256) {
+        const int64_t a1 = std::min<int64_t>(N, a0 + 256);
+        for (int64_t f = 0; f < nf; ++f) {
+          float* d = dst + ((size_t)f * N + a0) * 3;
+          const float* sp = xyz + ((size_t)a0 * n_frames + f0 + f) * 3;
+          for (int64_t a = a0; a < a1; ++a, d += 3, sp += (size_t)n_frames * 3) {
+            d[0] = sp[0]; d[1] = sp[1]; d[2] = sp[2];
+          }
+        }
+      }
+    }
+    h->stage_frames += nf;
+    f0 += nf;
+    if (h->stage_frames == h->stage_capacity) {
+      const int rc = flush_stage(h);
+      if (rc != MDS_OK) return rc;
+    }
+  }
+  return MDS_OK;
+}
+
+int mds_rdf_submit(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout,
+                   int host_is_pinned) {
+  int rc = check_submit_args(h, xyz, n_frames, layout, "mds_rdf_submit");
+  if (rc != MDS_OK) return rc;
+  if (n_frames == 0) return MDS_OK;
+  DeviceGuard guard(h->device);
+  if (!host_is_pinned) return submit_pageable(h, xyz, n_frames, layout);
+  rc = flush_stage(h);  // frames submitted earlier go first
+  if (rc != MDS_OK) return rc;
+  return submit_pinned(h, xyz, n_frames, layout);
+}
+
 int mds_rdf_join(mds_rdf_t* h, void* stream) {
   if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_join: handle is NULL");
   DeviceGuard guard(h->device);
+  {
+    const int rc = flush_stage(h);
+    if (rc != MDS_OK) return rc;
+  }
   CUDA_TRY(cudaEventRecord(h->ev_join, h->s_compute));
   CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_join, 0));
   return MDS_OK;
@@ -941,6 +1065,10 @@ int mds_rdf_wait(mds_rdf_t* h, void* stream) {
 int mds_rdf_wait_host_copies(mds_rdf_t* h) {
   if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_wait_host_copies: handle is NULL");
   DeviceGuard guard(h->device);
+  {
+    const int rc = flush_stage(h);
+    if (rc != MDS_OK) return rc;
+  }
   CUDA_TRY(cudaStreamSynchronize(h->s_copy));
   return MDS_OK;
 }
@@ -948,6 +1076,10 @@ int mds_rdf_wait_host_copies(mds_rdf_t* h) {
 int mds_rdf_synchronize(mds_rdf_t* h) {
   if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_synchronize: handle is NULL");
   DeviceGuard guard(h->device);
+  {
+    const int rc = flush_stage(h);
+    if (rc != MDS_OK) return rc;
+  }
   CUDA_TRY(cudaStreamSynchronize(h->s_copy));
   CUDA_TRY(cudaStreamSynchronize(h->s_compute));
   return MDS_OK;
@@ -956,6 +1088,10 @@ int mds_rdf_synchronize(mds_rdf_t* h) {
 int mds_rdf_counts(mds_rdf_t* h, uint64_t* out, int sync) {
   if (!h || !out) return fail(MDS_ERR_INVALID, "mds_rdf_counts: NULL argument");
   DeviceGuard guard(h->device);
+  {
+    const int rc = flush_stage(h);
+    if (rc != MDS_OK) return rc;
+  }
   const size_t bytes = (size_t)h->n_pairs * (size_t)h->nbins * sizeof(uint64_t);
   CUDA_TRY(cudaMemcpyAsync(out, h->d_counts, bytes, cudaMemcpyDeviceToHost, h->s_compute));
   if (sync) return mds_rdf_synchronize(h);
@@ -972,6 +1108,7 @@ int mds_rdf_device_counts(mds_rdf_t* h, void** d_counts, void** stream) {
 int mds_rdf_reset(mds_rdf_t* h) {
   if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_reset: handle is NULL");
   DeviceGuard guard(h->device);
+  h->stage_frames = 0;  // frames still waiting in the pinned ring belong to the run being discarded
   const size_t bytes = (size_t)h->n_pairs * (size_t)h->nbins * sizeof(uint64_t);
   CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, bytes, h->s_compute));
   CUDA_TRY(cudaMemsetAsync(h->d_general, 0, 2 * sizeof(unsigned long long), h->s_compute));

@@ -617,6 +617,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 4) rdf_cells_kernel(const CellsP
 
 int cells_max_seg() { return MAXW - 2 * 4; }
 int cells_max_cap() { return MAX_CAP; }
+int cells_max_entries() { return MAX_ENT; }
 
 size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem, int cap_atoms) {
   size_t b = (size_t)CELLS_FIXED_BYTES + 3 * (size_t)ROWS_CAP * sizeof(float) +

@@ -78,6 +78,7 @@ struct CellsParams {
 size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem, int cap_atoms);
 int cells_max_seg();   // longest segment (x cells) the kernel's tables can hold
 int cells_max_cap();   // largest cap_atoms the kernel's tables can hold
+int cells_max_entries();  // (x cell, neighbour pencil) entries of a staged segment, at most
 // pp must have cell_off / rank / grid set: pack + count, scan, scatter into `sorted`; frames with
 // a cell of more than crowded_limit atoms are flagged MDS_FRAME_FAR
 cudaError_t launch_cell_build(const PackParams& pp, int n_species, float4* sorted,
