@@ -153,7 +153,16 @@ class AngularDistributionFunction(Calculator):
 
     def prepare_computation(self):
         paths, selections = resolve_species_data(self.experiment, self.args, self.loaded_property)
-        split_arr = np.array_split(self.sample_configurations, self._number_of_batches(paths))
+        n_batches = self._number_of_batches(paths)
+        # the batch count follows from the host's free memory: under torch.distributed the ranks
+        # could round it differently, and every batch is normalised on its own — rank 0 decides
+        from mdsuite_b200.distributed import distributed_context
+        _rank, _world, dist = distributed_context()
+        if dist is not None:
+            box = [int(n_batches)]
+            dist.broadcast_object_list(box, src=0)
+            n_batches = int(box[0])
+        split_arr = np.array_split(self.sample_configurations, n_batches)
         return paths, selections, split_arr
 
     def _load(self, paths, selections, frames, counts, staging=None) -> np.ndarray:

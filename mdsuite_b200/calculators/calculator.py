@@ -23,20 +23,41 @@ def call(func):
 
     @functools.wraps(func)
     def inner(self, *args, **kwargs) -> Union[Computation, Dict[str, Computation]]:
+        from mdsuite_b200.distributed import distributed_context
         return_dict = self.experiment is None
         out = {}
+        # Under torch.distributed every rank runs the analysis (its share of the configurations)
+        # but ONE rank owns the project database: rank 0 looks the computation up and tells the
+        # others whether it is a hit, rank 0 alone writes the result, and the others work with the
+        # in-memory copy — no double rows, no sqlite lock contention, and no rank that skips
+        # run_analysis (a late cache hit) while the others wait in the allreduce.
+        rank, world, dist = distributed_context()
         for experiment in self.experiments:
             cls = self.__class__(experiment=experiment)
             func(cls, *args, **kwargs)
-            data = cls.get_computation_data()
-            if data is None:
+            data = cls.get_computation_data() if rank == 0 else None
+            hit = data is not None
+            if dist is not None:
+                box = [hit]
+                dist.broadcast_object_list(box, src=0)
+                hit = bool(box[0])
+            if not hit:
                 cls.prepare_db_entry()
                 cls.save_computation_args()
                 cls.run_analysis()
-                cls.save_db_data()
+                if rank == 0:
+                    cls.save_db_data()
+                else:
+                    cls.keep_computation_in_memory()
+                if dist is not None:
+                    dist.barrier()  # the row is written before any rank goes on
                 func(cls, *args, **kwargs)  # defaults filled in by check_input must not leak
-                data = cls.get_computation_data() or cls.last_computation
-            if cls.plot and data is not None:
+                data = (cls.get_computation_data() if rank == 0 else None) or cls.last_computation
+            elif dist is not None:
+                box = [data]
+                dist.broadcast_object_list(box, src=0)  # the cached result, for every rank
+                data = box[0]
+            if cls.plot and data is not None and rank == 0:
                 cls.plotter = DataVisualizer2D(title=cls.analysis_name, path=experiment.figures_path)
                 cls.plot_data(data.data_dict)
                 cls.plotter.grid_show(cls.plot_array)
@@ -91,12 +112,17 @@ class Calculator:
         """calculator_database.py:236-248."""
         self._queued_data.append((data, list(subjects)))
 
+    def keep_computation_in_memory(self):
+        """The finished run as a Computation that is not written to the project database
+        (``save=False``, and every rank but 0 of a distributed run)."""
+        attrs = [(k, {"serialized_value": v}) for k, v in self._db_attributes.items()]
+        results = [(d, [(s, c) for s, c in _count_subjects(subj)]) for d, subj in self._queued_data]
+        self.last_computation = Computation(-1, self.analysis_name, -1, attrs, results)
+
     def save_db_data(self):
         """calculator_database.py:196-234 — only reached when the run completed."""
         if not self.save_to_db:
-            attrs = [(k, {"serialized_value": v}) for k, v in self._db_attributes.items()]
-            results = [(d, [(s, c) for s, c in _count_subjects(subj)]) for d, subj in self._queued_data]
-            self.last_computation = Computation(-1, self.analysis_name, -1, attrs, results)
+            self.keep_computation_in_memory()
             return
         self.experiment.project.database.save_computation(
             self.experiment.name, self.analysis_name, self._db_attributes, self._queued_data)

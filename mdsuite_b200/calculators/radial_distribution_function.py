@@ -279,8 +279,16 @@ class RadialDistributionFunction(Calculator):
                 b = FrameBatcher(self.experiment.database, paths, particles, h, fpb, selections,
                                  pin=torch.cuda.is_available())
                 batchers.append(b)
-            for b, shard in zip(batchers, shards):
-                b.run(shard)
+            # one batch per device in turn: every GPU of an in-process run is fed from the start
+            feeds = [b.batches(shard) for b, shard in zip(batchers, shards)]
+            while feeds:
+                feeds = [f for f in feeds if next(f, None) is not None]
+            if dist is not None:
+                # the per-handle allreduce below pairs handle k of every rank
+                n_dev = [None] * world
+                dist.all_gather_object(n_dev, len(devices))
+                if len(set(n_dev)) != 1:
+                    raise ValueError(f"every rank must use the same number of devices, got {n_dev}")
             total = None
             for h in handles:
                 if dist is not None and hasattr(h, "device_counts"):
@@ -290,16 +298,30 @@ class RadialDistributionFunction(Calculator):
                     c = allreduce_host_counts(c)  # process groups without a CUDA backend
                 total = c if total is None else total + c
             stats = [h.stats() for h in handles]
+            failed = False
+        except BaseException:
+            failed = True
+            raise
         finally:
             for h in handles:
-                # synchronises the handle's streams (the staging buffers are idle afterwards) and
-                # keeps the handle for the next run with the same configuration
-                if injected is None:
-                    _cuda.park_handle(h)
-                else:
-                    h.close()
+                # a finished run synchronises the handle's streams (the staging buffers are idle
+                # afterwards) and keeps the handle for the next run with the same configuration;
+                # after an error the handle is destroyed instead, and nothing raised here may hide
+                # the original exception or skip the remaining handles and rings
+                try:
+                    if injected is None and not failed:
+                        _cuda.park_handle(h)
+                    else:
+                        h.close()
+                except Exception:  # noqa: BLE001
+                    log.exception("RDF: releasing a device handle failed")
+                    if not failed:
+                        raise
             for b in batchers:
-                b.close()
+                try:
+                    b.close()
+                except Exception:  # noqa: BLE001
+                    log.exception("RDF: releasing a staging ring failed")
         elapsed = time.perf_counter() - t0
         self.counts = total
         scale = world if dist is not None else 1

@@ -256,6 +256,13 @@ class ProjectDatabase:
                     return self._load_computation(con, cid)
         return None
 
+    def count_computations(self, experiment: str, analysis_name: str) -> int:
+        """Stored computations of one calculator for an experiment (rows of ``computations``)."""
+        eid = self.experiment_id(experiment)
+        with self.session() as con:
+            return int(con.execute("SELECT COUNT(*) FROM computations WHERE experiment_id = ? AND "
+                                   "name = ?", (eid, analysis_name)).fetchone()[0])
+
     def save_computation(self, experiment: str, analysis_name: str, attributes: Dict[str, Any],
                          results: Sequence[tuple]) -> int:
         """results: [(data_dict, [subject, ...]), ...] — one computation_results row per entry plus

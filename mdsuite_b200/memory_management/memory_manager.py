@@ -125,8 +125,11 @@ class FrameBatcher:
             _release_ring(self._ring_key, self._ring)
             self._ring = None
 
-    def run(self, sample_configurations: Sequence[int]) -> int:
-        """Submit the given configuration indices (in order); returns the number of frames."""
+    def batches(self, sample_configurations: Sequence[int]):
+        """Generator: every step loads and submits one batch of the given configuration indices
+        (in order) and yields the number of frames submitted so far.  Several batchers — one per
+        device of an in-process multi-GPU run — are fed in turn by stepping their generators
+        round-robin, so that no device waits for another device's whole shard."""
         frames = np.asarray(sample_configurations, dtype=np.int64)
         for k, lo in enumerate(range(0, len(frames), self.frames_per_batch)):
             idx = frames[lo:lo + self.frames_per_batch]
@@ -142,4 +145,10 @@ class FrameBatcher:
             self.handle.submit(buf[:len(idx)], pinned=self.pinned)
             self.frames_submitted += len(idx)
             self.bytes_staged += len(idx) * off * 12
+            yield self.frames_submitted
+
+    def run(self, sample_configurations: Sequence[int]) -> int:
+        """Submit the given configuration indices (in order); returns the number of frames."""
+        for _ in self.batches(sample_configurations):
+            pass
         return self.frames_submitted

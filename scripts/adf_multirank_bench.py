@@ -30,7 +30,6 @@ def main():
     rank, local = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(local)
-    os.environ.pop("NCCL_DEBUG", None)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sysm = synthetic.nacl_melt(args.cells, 8, seed=2)

@@ -116,6 +116,51 @@ def test_adf_calculator_shards_every_batch_over_ranks(tmp_path):
         assert np.max(np.abs(row - want[key]["adf"])) <= 2e-6 * want[key]["adf"].max()
 
 
+def _worker_shared_project(rank, world, port, out_dir):
+    """Both ranks open the SAME project (the normal torchrun case).  Rank 0 creates it first."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mdsuite_b200 as mds
+    from mdsuite_b200.calculators.radial_distribution_function import RadialDistributionFunction
+    from tests.test_calculator_cpu import OracleHandle
+    RadialDistributionFunction.handle_factory = OracleHandle
+    sysm = synthetic.nacl_melt(2, 6, seed=14)
+    if rank == 0:
+        p = mds.Project("shared", storage_path=out_dir)
+        e = p.add_experiment("NaCl")
+        e.add_positions(sysm.positions, sysm.species, sysm.box)
+    dist.barrier()
+    if rank != 0:
+        p = mds.Project("shared", storage_path=out_dir)
+        e = p.experiments["NaCl"]
+    runs = []
+    for _ in range(2):  # second call: a cache hit, decided by rank 0 for everybody
+        before = len(OracleHandle.instances)
+        comp = e.run.RadialDistributionFunction(number_of_configurations=6, cutoff=6.0,
+                                                number_of_bins=30, plot=False)
+        runs.append((len(OracleHandle.instances) - before, np.array(comp["Na_Cl"]["y"])))
+    np.save(os.path.join(out_dir, f"shared_y{rank}.npy"), np.stack([r[1] for r in runs]))
+    np.save(os.path.join(out_dir, f"shared_ran{rank}.npy"), np.array([r[0] for r in runs]))
+    dist.barrier()
+    if rank == 0:
+        rows = p.database.count_computations("NaCl", "Radial_Distribution_Function")
+        np.save(os.path.join(out_dir, "shared_rows.npy"), np.array([rows]))
+    dist.destroy_process_group()
+
+
+def test_ranks_sharing_one_project_write_one_row_and_agree_on_the_cache(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker_shared_project, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    y0, y1 = np.load(tmp_path / "shared_y0.npy"), np.load(tmp_path / "shared_y1.npy")
+    assert np.array_equal(y0[0][1:], y1[0][1:]) and np.array_equal(y0[1][1:], y1[1][1:])
+    assert np.array_equal(y0[0][1:], y0[1][1:])
+    # both ranks ran the analysis once (first call), neither on the cache hit
+    assert np.load(tmp_path / "shared_ran0.npy").tolist() == [1, 0]
+    assert np.load(tmp_path / "shared_ran1.npy").tolist() == [1, 0]
+    assert np.load(tmp_path / "shared_rows.npy").tolist() == [1]
+
+
 def test_shard_configurations_edge_cases():
     assert shard_configurations(np.arange(3), 8, 5).size == 0  # more ranks than frames
     parts = [shard_configurations(np.arange(10), 4, r) for r in range(4)]

@@ -25,7 +25,6 @@ from mdsuite_b200 import synthetic
 
 rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
-os.environ.pop("NCCL_DEBUG", None)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 out = os.environ["MDS_OUT"]
 for name, sysm, cutoff, nbins in (
