@@ -698,7 +698,9 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   int bf = cfg->max_frames_in_flight;
   if (bf <= 0) {
     const int64_t per_frame = h->frame_stride * (cells ? 12 + 4 + 16 : 12) + h->off_stride * 4;
-    bf = (int)std::min<int64_t>(4096, std::max<int64_t>(1, (128LL << 20) / per_frame));
+    // 128 MB of internal buffers per batch; 512 MB on the cell path, whose pair kernel spreads
+    // (frame, pencil) items over persistent CTAs and loses ~3 % to ramp and tail on short batches
+    bf = (int)std::min<int64_t>(4096, std::max<int64_t>(1, ((cells ? 512LL : 128LL) << 20) / per_frame));
   }
   h->batch_frames = bf;
   build_items(h, mds::allpairs_variant_tile(h->variant), bf);

@@ -15,7 +15,8 @@ PEAK = 148 * 128 * 1.965e9 / 22
 def bench(name, sysm, cutoff, nbins, frames, path="celllist", reps=4):
     base = torch.from_numpy(sysm.positions).cuda()
     pos = base.repeat((frames + base.shape[0] - 1) // base.shape[0], 1, 1)[:frames].contiguous()
-    with _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, path=path) as h:
+    with _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, path=path,
+                         max_frames_in_flight=int(os.environ.get("CB_MAXF", "0"))) as h:
         best_k, best_s = 1e30, 1e30
         for _ in range(reps):
             h.reset()
