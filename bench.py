@@ -369,7 +369,7 @@ def adf_probe(device: int, frames: int = 64, check: bool = True):
     }
 
 
-def target_config_probe(args, world, rank, local_rank, dist, fp32_peak):
+def target_config_probe(args, world, rank, local_rank, dist, comm, fp32_peak):
     """BASELINE.json's north-star target at FULL size: RDF of the 100,000-atom LJ fluid over 10,000
     configurations (cell-list path, cutoff 3 sigma, 300 bins, parity mode), the configurations
     split over the ranks with np.array_split, one NCCL allreduce per step.
@@ -404,18 +404,28 @@ def target_config_probe(args, world, rank, local_rank, dist, fp32_peak):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def collective():
+        """ONE allreduce of the [n_pairs][nbins] uint64 accumulator, ordered after the kernels."""
+        if dist is None:
+            return
+        if comm is not None:
+            handle.allreduce(comm)  # on the library's stream
+        else:
+            handle.join()
+            dist.all_reduce(counts_dev)
+            handle.wait()
+
     def step_resident():
-        if dist is not None:
+        if dist is not None and comm is None:
             handle.wait()
         handle.reset()
         if len(mine):
             handle.submit_device(dev)
+        collective()
         handle.join()
-        if dist is not None:
-            dist.all_reduce(counts_dev)
 
     def step_e2e():
-        if dist is not None:
+        if dist is not None and comm is None:
             handle.wait()
         handle.reset()
         done = 0
@@ -425,10 +435,7 @@ def target_config_probe(args, world, rank, local_rank, dist, fp32_peak):
             # block holds exactly that sequence when `done` is a multiple of the block
             handle.submit(host[:n], pinned=True)
             done += n
-        if dist is not None:
-            handle.join()
-            dist.all_reduce(counts_dev)
-            handle.wait()
+        collective()
         return handle.counts()
 
     def timed(fn):
@@ -528,6 +535,12 @@ def run_ours(args):
         # NCCL's log (NCCL_DEBUG) stays as the environment sets it: fd 1 already points at stderr
         # (claim_stdout), so nothing but the JSON line reaches stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # the collective goes through the C ABI (mds_rdf_allreduce over a raw ncclComm_t, on the
+    # library's stream) unless --torch-collective asks for torch's process group
+    comm = None
+    if dist is not None and not args.torch_collective:
+        from mdsuite_b200.distributed import raw_communicator
+        comm = raw_communicator(local_rank)
 
     # the same fixed workload on every rank; rank g takes block g of np.array_split (strong scaling)
     sysm, cutoff, nbins, desc = make_workload(args.workload, args.frames)
@@ -547,26 +560,33 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def collective():
+        """ONE allreduce of the [n_pairs][nbins] uint64 accumulator, ordered after the kernels."""
+        if dist is None:
+            return
+        if comm is not None:
+            handle.allreduce(comm)  # on the library's stream
+        else:
+            handle.join()
+            dist.all_reduce(counts_dev)
+            handle.wait()
+
     def step_resident():
-        if dist is not None:
+        if dist is not None and comm is None:
             handle.wait()  # the previous step's allreduce reads the accumulator
         handle.reset()
         if n_frames:
             handle.submit_device(dev)
+        collective()
         handle.join()
-        if dist is not None:
-            dist.all_reduce(counts_dev)
 
     def step_e2e():
-        if dist is not None:
+        if dist is not None and comm is None:
             handle.wait()
         handle.reset()
         if n_frames:
             handle.submit(host, pinned=True)
-        if dist is not None:
-            handle.join()
-            dist.all_reduce(counts_dev)
-            handle.wait()
+        collective()
         return handle.counts()
 
     # ---- this rank's own statistics: one un-reduced pass (after a step the accumulator holds
@@ -631,7 +651,7 @@ def run_ours(args):
     target = None
     if not args.no_target_config:
         try:
-            target = target_config_probe(args, world, rank, local_rank, dist, fp32_peak)
+            target = target_config_probe(args, world, rank, local_rank, dist, comm, fp32_peak)
         except Exception as exc:  # noqa: BLE001
             if dist is not None:
                 raise  # a rank that drops out would leave the others in the collective
@@ -661,6 +681,8 @@ def run_ours(args):
         handle.close()
         if dist is not None:
             dist.barrier()
+            from mdsuite_b200.distributed import close_raw_communicators
+            close_raw_communicators()
             dist.destroy_process_group()
         return 0
 
@@ -782,7 +804,9 @@ def run_ours(args):
                          f"{12 * n_atoms * n_total / 1e6:.0f} MB packed per step vs 126 MB L2 "
                          f"(rank 0 here: {12 * n_atoms * n_frames / 1e6:.0f} MB raw)",
                    "parallelism": f"the {n_total} configurations split over {world} GPU(s) with "
-                                  f"np.array_split, 1 NCCL allreduce/step" if world > 1 else "1 GPU"},
+                                  f"np.array_split, 1 NCCL allreduce/step "
+                                  f"({'torch.distributed' if comm is None else 'mds_rdf_allreduce(ncclComm_t)'})"
+                   if world > 1 else "1 GPU"},
         "roofline": roofline, "target_config": target, "adf_path": adf, "user_api": user_api,
         "e2e_reference_binding": binding,
         "cpu_baseline": cpu_baseline,
@@ -799,6 +823,8 @@ def run_ours(args):
     handle.close()
     if dist is not None:
         dist.barrier()
+        from mdsuite_b200.distributed import close_raw_communicators
+        close_raw_communicators()
         dist.destroy_process_group()
     return 0
 
@@ -842,6 +868,8 @@ def main():
                     help="skip the Project -> Experiment -> run.RadialDistributionFunction timing")
     ap.add_argument("--no-adf-probe", action="store_true",
                     help="skip the short angular-distribution measurement added at N=1")
+    ap.add_argument("--torch-collective", action="store_true",
+                    help="allreduce with torch.distributed instead of mds_rdf_allreduce(ncclComm_t)")
     ap.add_argument("--no-target-config", action="store_true",
                     help="skip the full-size north-star block (100k atoms x 10k configurations)")
     ap.add_argument("--target-steps", type=int, default=3,

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MDS_RDF_ABI_VERSION 4
+#define MDS_RDF_ABI_VERSION 5
 
 #if defined(MDS_BUILD) && defined(__GNUC__)
 #define MDS_API __attribute__((visibility("default")))
@@ -150,6 +150,16 @@ MDS_API int mds_rdf_counts(mds_rdf_t* h, uint64_t* out, int sync);
  * produced on, for a collective over per-GPU handles (the host layer allreduces this buffer in
  * place with NCCL, one ncclAllReduce(sum, uint64) — SURVEY.md §8e). */
 MDS_API int mds_rdf_device_counts(mds_rdf_t* h, void** d_counts, void** stream);
+
+/* The one collective of the path: sum the accumulated counts over the ranks of
+ * `comm` (an ncclComm_t of NCCL 2.x; every rank calls this with its own handle of the same
+ * configuration), in place, as ONE ncclAllReduce(sum, ncclUint64, n_pairs * nbins) on the library's
+ * stream — ordered after everything submitted so far and before anything submitted or reset
+ * afterwards, without blocking the host.  Afterwards mds_rdf_counts returns the global histogram
+ * on every rank.  NCCL is resolved at run time (no link-time dependency): MDS_ERR_UNSUPPORTED if
+ * ncclAllReduce is neither loaded in the process nor found as libnccl.so.2. */
+struct ncclComm;
+MDS_API int mds_rdf_allreduce(mds_rdf_t* h, struct ncclComm* comm);
 
 /* Make `stream` (a cudaStream_t as void*, NULL = default stream) wait for everything submitted so
  * far, without blocking the host — so that events recorded on the caller's stream bracket the

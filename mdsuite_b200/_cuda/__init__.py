@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # (make -C csrc checked; see rdf_common.cuh MDS_CHECKED)
 LIB_PATH = os.environ.get("MDS_RDF_LIB") or os.path.join(_HERE, "libmds_rdf.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MDS_OK = 0
 PARITY_SKIP_FIRST = 0x1
 PATH_ALLPAIRS = 0x2
@@ -32,7 +32,7 @@ LAYOUT_ATOM_MAJOR = 1  # (n_atoms, n_frames, 3) — the reference's positions_te
 
 EXPORTED_SYMBOLS = (
     "mds_rdf_create", "mds_rdf_destroy", "mds_rdf_submit", "mds_rdf_submit_device",
-    "mds_rdf_counts", "mds_rdf_device_counts", "mds_rdf_join", "mds_rdf_wait", "mds_rdf_wait_host_copies", "mds_rdf_synchronize",
+    "mds_rdf_counts", "mds_rdf_device_counts", "mds_rdf_allreduce", "mds_rdf_join", "mds_rdf_wait", "mds_rdf_wait_host_copies", "mds_rdf_synchronize",
     "mds_rdf_reset", "mds_rdf_set_item_shard",
     "mds_rdf_stats_get", "mds_rdf_threshold_table", "mds_rdf_build_threshold_table",
     "mds_bench_shared_atomics",
@@ -136,6 +136,7 @@ def load() -> ctypes.CDLL:
     lib.mds_rdf_submit_device.argtypes = [vp, vp, i64, i32, vp]
     lib.mds_rdf_counts.argtypes = [vp, vp, i32]
     lib.mds_rdf_device_counts.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    lib.mds_rdf_allreduce.argtypes = [vp, vp]
     lib.mds_rdf_join.argtypes = [vp, vp]
     lib.mds_rdf_wait.argtypes = [vp, vp]
     lib.mds_rdf_wait_host_copies.argtypes = [vp]
@@ -321,6 +322,13 @@ class RDFHandle:
         _check(self._lib.mds_rdf_device_counts(self._h, ctypes.byref(ptr), ctypes.byref(stream)),
                "mds_rdf_device_counts")
         return ptr.value, (stream.value or 0)
+
+    def allreduce(self, comm):
+        """Sum the accumulated counts over the ranks of a raw NCCL communicator (an ``ncclComm_t``
+        as an integer / ``c_void_p``, or a :class:`mdsuite_b200._cuda.nccl.Communicator`): one
+        in-place ncclAllReduce on the library's stream, ordered with the kernels."""
+        ptr = getattr(comm, "handle", comm)
+        _check(self._lib.mds_rdf_allreduce(self._h, ctypes.c_void_p(ptr)), "mds_rdf_allreduce")
 
     def reset(self):
         _check(self._lib.mds_rdf_reset(self._h), "mds_rdf_reset")

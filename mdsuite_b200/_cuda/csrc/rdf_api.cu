@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in Nsight Systems, no-ops otherwise
 
 #include "mds_rdf.h"
@@ -1061,6 +1063,50 @@ int mds_rdf_wait(mds_rdf_t* h, void* stream) {
   DeviceGuard guard(h->device);
   CUDA_TRY(cudaEventRecord(h->ev_ext, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_ext, 0));
+  return MDS_OK;
+}
+
+// ncclAllReduce, resolved at run time: the library has no link-time dependency on NCCL, a caller
+// that shards over GPUs already has it loaded (or libnccl.so.2 is on the loader path).
+namespace {
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_fn)(int);
+nccl_allreduce_fn g_nccl_allreduce = nullptr;
+nccl_errstr_fn g_nccl_errstr = nullptr;
+bool resolve_nccl() {
+  if (g_nccl_allreduce) return true;
+  void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+  void* err = dlsym(RTLD_DEFAULT, "ncclGetErrorString");
+  if (!sym) {
+    if (void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL)) {
+      sym = dlsym(lib, "ncclAllReduce");
+      err = dlsym(lib, "ncclGetErrorString");
+    }
+  }
+  g_nccl_allreduce = reinterpret_cast<nccl_allreduce_fn>(sym);
+  g_nccl_errstr = reinterpret_cast<nccl_errstr_fn>(err);
+  return g_nccl_allreduce != nullptr;
+}
+}  // namespace
+
+int mds_rdf_allreduce(mds_rdf_t* h, struct ncclComm* comm) {
+  if (!h || !comm) return fail(MDS_ERR_INVALID, "mds_rdf_allreduce: NULL argument");
+  if (!resolve_nccl())
+    return fail(MDS_ERR_UNSUPPORTED, "mds_rdf_allreduce: ncclAllReduce not found (load NCCL first or "
+                                     "put libnccl.so.2 on the loader path)");
+  DeviceGuard guard(h->device);
+  {
+    const int rc = flush_stage(h);
+    if (rc != MDS_OK) return rc;
+  }
+  NvtxRange range("mds_rdf_allreduce");
+  const size_t n = (size_t)h->n_pairs * (size_t)h->nbins;
+  // in place, on the library's own stream: ordered after every kernel submitted so far and before
+  // anything submitted or reset afterwards — no join / wait needed around it
+  const int rc = g_nccl_allreduce(h->d_counts, h->d_counts, n, /*ncclUint64*/ 5, /*ncclSum*/ 0, comm,
+                                  h->s_compute);
+  if (rc != 0)
+    return fail(MDS_ERR_CUDA, "ncclAllReduce failed: %s", g_nccl_errstr ? g_nccl_errstr(rc) : "?");
   return MDS_OK;
 }
 

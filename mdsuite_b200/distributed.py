@@ -31,11 +31,38 @@ def counts_as_tensor(handle):
     return torch.as_tensor(_Wrap(), device=f"cuda:{handle.device}")
 
 
-def allreduce_counts(handle, group=None):
-    """In-place sum of the per-GPU histograms over the process group (one NCCL allreduce), ordered
-    after the handle's kernels and before any later work on the handle."""
+_RAW_COMMS = {}  # device -> mdsuite_b200._cuda.nccl.Communicator over the default group
+
+
+def raw_communicator(device: int):
+    """The process's raw NCCL communicator for ``device`` over the ranks of the default
+    torch.distributed group (created on first use; every rank must ask for it at the same point)."""
+    from mdsuite_b200._cuda import nccl
+    comm = _RAW_COMMS.get(device)
+    if comm is None:
+        comm = nccl.Communicator.from_torch(device=device)
+        _RAW_COMMS[device] = comm
+    return comm
+
+
+def close_raw_communicators():
+    for comm in _RAW_COMMS.values():
+        comm.close()
+    _RAW_COMMS.clear()
+
+
+def allreduce_counts(handle, group=None, raw: bool = True):
+    """In-place sum of the per-GPU histograms over the process group — ONE ncclAllReduce.
+
+    raw=True (default): through the C ABI, ``mds_rdf_allreduce(handle, ncclComm_t)``, on the
+    library's own stream; ordering with the kernels is the library's business.  raw=False: torch's
+    process group reduces a tensor view of the accumulator, bracketed by join / wait."""
     import torch
     import torch.distributed as dist
+    if raw and group is None and hasattr(handle, "allreduce"):
+        with torch.cuda.device(handle.device):
+            handle.allreduce(raw_communicator(handle.device))
+        return None
     t = counts_as_tensor(handle)
     with torch.cuda.device(handle.device):
         handle.join()  # torch's stream waits for the kernels

@@ -46,6 +46,23 @@ exp.add_positions(melt.positions, melt.species, melt.box)
 adf = exp.run.AngularDistributionFunction(number_of_configurations=8, cutoff=4.0, start=0,
                                           number_of_bins=60, norm_power=4, batches=3, plot=False)
 np.save(os.path.join(out, f"adf{rank}.npy"), np.array([adf[k]["adf"] for k in adf.keys()], dtype=float))
+# the collective of the C ABI (mds_rdf_allreduce over a raw ncclComm_t) against torch's process group
+from mdsuite_b200 import _cuda
+from mdsuite_b200.distributed import allreduce_counts, close_raw_communicators
+sysm = synthetic.nacl_melt(3, 6, seed=25)
+mine = np.array_split(np.arange(6), dist.get_world_size())[rank]
+got = {}
+for raw in (True, False):
+    with _cuda.RDFHandle(sysm.counts, 80, 8.0, sysm.box, device=local) as h:
+        h.submit(sysm.positions[mine])
+        allreduce_counts(h, raw=raw)
+        got[raw] = h.counts()
+        h.reset()                      # work submitted after the collective is ordered behind it
+        h.submit(sysm.positions[mine])
+        allreduce_counts(h, raw=raw)
+        assert np.array_equal(h.counts(), got[raw])
+np.save(os.path.join(out, f"raw{rank}.npy"), np.stack([got[True], got[False]]))
+close_raw_communicators()
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -83,6 +100,15 @@ def test_two_ranks_nccl_calculator(tmp_path):
         want = rdf_oracle.normalise(counts, names, sysm.counts, sysm.box, cutoff, sysm.n_frames)
         for row, key in zip(y0, want):
             assert np.allclose(row[1:], np.array(want[key]["y"])[1:], rtol=1e-12, atol=0)
+
+    # mds_rdf_allreduce(ncclComm_t) == torch's all_reduce == the oracle on all six frames
+    sysm = synthetic.nacl_melt(3, 6, seed=25)
+    want, _ = c_oracle.rdf_counts_c(sysm.positions, sysm.counts, sysm.box, 8.0, 80,
+                                    layout=c_oracle.FRAME_MAJOR)
+    for r in range(2):
+        both = np.load(tmp_path / f"raw{r}.npy")
+        assert np.array_equal(both[0], want.astype(np.uint64))
+        assert np.array_equal(both[1], want.astype(np.uint64))
 
     # ADF: both ranks hold the same curves, equal to the single-process oracle's
     from oracle import adf_oracle
