@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MDS_IO_ABI_VERSION 2
+#define MDS_IO_ABI_VERSION 3
 
 #if defined(MDS_BUILD) && defined(__GNUC__)
 #define MDS_IO_API __attribute__((visibility("default")))
@@ -93,6 +93,46 @@ MDS_IO_API int mds_dump_read_columns_mapped(mds_dump_t* h, int64_t frame0, int64
 /* The string -> float32 conversion on its own (for parity tests): n NUL-terminated tokens at
  * stride `stride` bytes -> out[n]. */
 MDS_IO_API int mds_parse_float32(const char* tokens, int64_t n, int32_t stride, float* out);
+
+/* ---- HDF5 chunk decoding: the feed out of a reference project's database.hdf5 -------------------
+ * The reference stores <species>/Positions as (n_atoms, n_configurations, 3) float32, chunked and
+ * gzip-compressed (mdsuite/database/simulation_database.py:449-499) and reads it with h5py fancy
+ * indexing (:594-639): libhdf5 inflates chunk after chunk on one thread.  The host language walks
+ * the file's metadata (mdsuite_b200/database/hdf5_reader.py) and hands the chunks of a request to
+ * mds_h5_read_chunks, which decodes them on all cores and writes the requested box with the
+ * caller's strides — e.g. frame-major for the GPU feed. */
+typedef struct mds_h5_chunk {
+  int64_t address;        /* file offset of the stored (filtered) chunk */
+  int64_t nbytes;         /* its stored size */
+  int64_t offsets[4];     /* dataset coordinates of the chunk's first element (rank entries used) */
+  uint32_t filter_mask;   /* bit i set: filter i of the pipeline was skipped for this chunk */
+  uint32_t reserved;
+} mds_h5_chunk;
+
+typedef struct mds_h5_layout {
+  uint32_t struct_size;   /* sizeof(mds_h5_layout) */
+  int32_t rank;           /* 1..4 */
+  int32_t elem_size;      /* bytes per element */
+  int32_t n_filters;      /* filter pipeline in write order: 1 deflate, 2 shuffle, 3 fletcher32 */
+  int32_t filter_ids[8];
+  int32_t filter_cd0[8];  /* first client-data value of each filter (shuffle: element size) */
+  int32_t verify_checksums; /* != 0: check the adler32 of every deflate stream */
+  int32_t reserved;
+  int64_t chunk_dims[4];
+  int64_t box_lo[4];      /* requested box [lo, hi) in dataset coordinates */
+  int64_t box_hi[4];
+  int64_t out_strides[4]; /* element strides of the output: index = sum (i_d - lo_d) * stride_d */
+} mds_h5_layout;
+
+/* Decode `n_chunks` chunks read from file descriptor `fd` (pread; the descriptor's offset is not
+ * used) with n_threads threads (<= 0: hardware concurrency) and copy their intersection with the
+ * box into `out`.  Elements of the box that no chunk covers are left untouched (the caller
+ * pre-fills the HDF5 fill value). */
+MDS_IO_API int mds_h5_read_chunks(int fd, const mds_h5_layout* layout, const mds_h5_chunk* chunks,
+                                  int64_t n_chunks, void* out, int n_threads);
+/* The library's own inflate on one zlib stream (RFC 1950 / 1951), for tests and audits. */
+MDS_IO_API int mds_inflate(const void* src, int64_t src_len, void* dst, int64_t dst_capacity,
+                           int64_t* dst_len, int verify_checksum);
 
 MDS_IO_API const char* mds_io_last_error(void);
 MDS_IO_API int mds_io_abi_version(void);

@@ -17,12 +17,12 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmds_io.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTED_SYMBOLS = (
     "mds_dump_open", "mds_xyz_open", "mds_dump_header_line", "mds_dump_close", "mds_dump_info_get", "mds_dump_column_name",
     "mds_dump_first_frame_labels", "mds_dump_read_columns", "mds_dump_read_columns_mapped",
-    "mds_parse_float32",
+    "mds_parse_float32", "mds_h5_read_chunks", "mds_inflate",
     "mds_io_last_error", "mds_io_abi_version",
 )
 
@@ -47,6 +47,23 @@ class _DumpInfo(ctypes.Structure):
     ]
 
 
+class H5Chunk(ctypes.Structure):
+    """mds_h5_chunk (include/mds_io.h)."""
+    _fields_ = [("address", ctypes.c_int64), ("nbytes", ctypes.c_int64),
+                ("offsets", ctypes.c_int64 * 4), ("filter_mask", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32)]
+
+
+class H5Layout(ctypes.Structure):
+    """mds_h5_layout (include/mds_io.h)."""
+    _fields_ = [("struct_size", ctypes.c_uint32), ("rank", ctypes.c_int32),
+                ("elem_size", ctypes.c_int32), ("n_filters", ctypes.c_int32),
+                ("filter_ids", ctypes.c_int32 * 8), ("filter_cd0", ctypes.c_int32 * 8),
+                ("verify_checksums", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("chunk_dims", ctypes.c_int64 * 4), ("box_lo", ctypes.c_int64 * 4),
+                ("box_hi", ctypes.c_int64 * 4), ("out_strides", ctypes.c_int64 * 4)]
+
+
 def build(force: bool = False) -> str:
     cmd = ["make", "-s", "-C", os.path.join(_HERE, "csrc")]
     if force:
@@ -64,9 +81,10 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    src = os.path.join(_HERE, "csrc", "lammps_reader.cpp")
-    if not os.path.exists(LIB_PATH) or (os.path.exists(src)
-                                        and os.path.getmtime(LIB_PATH) < os.path.getmtime(src)):
+    srcs = [os.path.join(_HERE, "csrc", f) for f in ("lammps_reader.cpp", "h5_chunks.cpp")]
+    if not os.path.exists(LIB_PATH) or any(os.path.exists(src) and
+                                           os.path.getmtime(LIB_PATH) < os.path.getmtime(src)
+                                           for src in srcs):
         build()
     lib = ctypes.CDLL(LIB_PATH)
     vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
@@ -82,6 +100,8 @@ def load() -> ctypes.CDLL:
     lib.mds_dump_read_columns.argtypes = [vp, i64, i64, vp, i32, ctypes.c_int, vp]
     lib.mds_dump_read_columns_mapped.argtypes = [vp, i64, i64, vp, i32, ctypes.c_int, vp, vp]
     lib.mds_parse_float32.argtypes = [vp, i64, i32, vp]
+    lib.mds_h5_read_chunks.argtypes = [ctypes.c_int, ctypes.POINTER(H5Layout), vp, i64, vp, ctypes.c_int]
+    lib.mds_inflate.argtypes = [vp, i64, vp, i64, ctypes.POINTER(i64), ctypes.c_int]
     lib.mds_io_last_error.restype = ctypes.c_char_p
     lib.mds_io_abi_version.restype = ctypes.c_int
     if lib.mds_io_abi_version() != ABI_VERSION:
@@ -210,4 +230,40 @@ def parse_float32(tokens: Sequence[str]) -> np.ndarray:
     buf = b"".join(t.ljust(stride, b"\0") for t in enc)
     out = np.empty(len(enc), dtype=np.float32)
     _check(load().mds_parse_float32(buf, len(enc), stride, out.ctypes.data), "mds_parse_float32")
+    return out
+
+
+def inflate(data: bytes, size: int, verify: bool = True) -> bytes:
+    """The library's own inflate on one zlib stream of known decompressed size (tests, audits)."""
+    out = ctypes.create_string_buffer(max(1, size))
+    n = ctypes.c_int64()
+    _check(load().mds_inflate(data, len(data), out, size, ctypes.byref(n), int(verify)), "mds_inflate")
+    return out.raw[:n.value]
+
+
+def h5_read_chunks(fd: int, chunks, chunk_dims, elem_size: int, filters, box_lo, box_hi,
+                   out: np.ndarray, out_strides, n_threads: int = 0, verify: bool = True):
+    """Decode HDF5 chunks and place their part of the box [box_lo, box_hi) into ``out``.
+
+    chunks: iterable of (address, nbytes, filter_mask, offsets); filters: [(id, first client value
+    or 0), ...] in pipeline order; out_strides: element strides of ``out`` per dataset dimension."""
+    lib = load()
+    rank = len(chunk_dims)
+    lay = H5Layout()
+    lay.struct_size = ctypes.sizeof(H5Layout)
+    lay.rank, lay.elem_size, lay.n_filters = rank, int(elem_size), len(filters)
+    for i, (fid, cd0) in enumerate(filters):
+        lay.filter_ids[i], lay.filter_cd0[i] = int(fid), int(cd0)
+    lay.verify_checksums = int(verify)
+    for d in range(rank):
+        lay.chunk_dims[d], lay.box_lo[d], lay.box_hi[d] = int(chunk_dims[d]), int(box_lo[d]), int(box_hi[d])
+        lay.out_strides[d] = int(out_strides[d])
+    chunks = list(chunks)
+    arr = (H5Chunk * max(1, len(chunks)))()
+    for k, (address, nbytes, mask, offsets) in enumerate(chunks):
+        arr[k].address, arr[k].nbytes, arr[k].filter_mask = int(address), int(nbytes), int(mask)
+        for d in range(rank):
+            arr[k].offsets[d] = int(offsets[d])
+    _check(lib.mds_h5_read_chunks(int(fd), ctypes.byref(lay), arr, len(chunks), out.ctypes.data,
+                                  int(n_threads)), "mds_h5_read_chunks")
     return out

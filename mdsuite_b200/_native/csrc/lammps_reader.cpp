@@ -45,6 +45,15 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+}  // namespace
+
+namespace mds_io {
+// the library's thread-local error message, for the other translation units (h5_chunks.cpp)
+void set_error(const std::string& msg) { g_err = msg; }
+}  // namespace mds_io
+
+namespace {
+
 constexpr int N_HEADER_LAMMPS = 9;
 constexpr int N_HEADER_XYZ = 2;
 

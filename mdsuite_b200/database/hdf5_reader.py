@@ -106,6 +106,31 @@ class Dataset:
         """The whole dataset as a NumPy array."""
         return self.read_hyperslab(tuple(slice(0, n) for n in self.shape))
 
+    def read_box_into(self, lo: Sequence[int], hi: Sequence[int], out: np.ndarray,
+                      out_strides: Sequence[int], threads: int = 0, verify: bool = True) -> bool:
+        """The box [lo, hi) of a chunked dataset decoded by the native library on all host cores
+        (include/mds_io.h, mds_h5_read_chunks: pread + hand-written inflate + strided placement)
+        straight into ``out``: the element at dataset index i lands at flat position
+        sum_d (i_d - lo_d) * out_strides[d].  ``out`` must be pre-filled with the fill value.
+        Returns False when the dataset is outside what the native path takes (not chunked, rank
+        above 4, a filter it does not know) — the caller then uses read_hyperslab."""
+        if self.layout != "chunked" or len(self.shape) > 4 or len(self.filters) > 8:
+            return False
+        if any(fid not in (1, 2, 3) for fid, _ in self.filters):
+            return False
+        from mdsuite_b200 import _native
+        index = self.chunk_index()
+        ranges = [range(l // c * c, h, c) for l, h, c in zip(lo, hi, self.chunks)]
+        wanted = [ref for offs in np.ndindex(*[len(r) for r in ranges])
+                  if (ref := index.get(tuple(r[i] for r, i in zip(ranges, offs)))) is not None]
+        base = self.file._base
+        _native.h5_read_chunks(
+            self.file._fh.fileno(),
+            [(base + ref.address, ref.nbytes, ref.filter_mask, ref.offsets) for ref in wanted],
+            self.chunks, self.dtype.itemsize, [(fid, cd[0] if cd else 0) for fid, cd in self.filters],
+            lo, hi, out, out_strides, n_threads=threads, verify=verify)
+        return True
+
     def read_hyperslab(self, slices: Sequence[slice], threads: int = 8) -> np.ndarray:
         """Axis-aligned box [start, stop) per dimension (unit steps)."""
         lo = [s.start or 0 for s in slices]

@@ -220,8 +220,9 @@ class HDF5Database:
         self.file = H5File(path)
         self._datasets = {}
         self._n_configurations = n_configurations
-        self._cache = {}  # path -> (f0, f1, array (n_atoms, f1 - f0, dims))
+        self._cache = {}  # path -> (f0, f1, frame-major array (f1 - f0, n_atoms, dims))
         self._cache_bytes = cache_bytes
+        self.native = True  # chunks decoded by libmds_io (False: the pure-Python reader, for tests)
 
     def close(self):
         self.file.close()
@@ -244,21 +245,35 @@ class HDF5Database:
         return ds.shape[0], n_cfg, int(ds.shape[0] * n_cfg * np.prod(ds.shape[2:])) * ds.dtype.itemsize
 
     def _window(self, path: str, f0: int, f1: int) -> np.ndarray:
-        """(n_atoms, f1 - f0, dims) for configurations [f0, f1), widened to whole frame-chunks and
-        kept for the next call."""
+        """FRAME-MAJOR (f1 - f0, n_atoms, dims) for configurations [f0, f1), widened to whole
+        frame-chunks and kept for the next call.  The chunks are atom-major on disk
+        (simulation_database.py:449-499); the native decoder writes them transposed, so a batch is
+        a contiguous slice of the window."""
         ds = self._ds(path)
         hit = self._cache.get(path)
         if hit is not None and hit[0] <= f0 and f1 <= hit[1]:
-            return hit[2][:, f0 - hit[0]:f1 - hit[0]]
+            return hit[2][f0 - hit[0]:f1 - hit[0]]
         cf = ds.chunks[1] if ds.chunks else ds.shape[1]
         w0, w1 = f0 // cf * cf, min(ds.shape[1], -(-f1 // cf) * cf)
         per_frame = ds.shape[0] * int(np.prod(ds.shape[2:])) * ds.dtype.itemsize
         if (w1 - w0) * per_frame > self._cache_bytes:  # too wide to keep: read exactly what is asked
             w0, w1 = f0, f1
-        block = ds.read_hyperslab((slice(0, ds.shape[0]), slice(w0, w1)) +
-                                  tuple(slice(0, n) for n in ds.shape[2:]))
+        n_atoms, inner = ds.shape[0], tuple(ds.shape[2:])
+        block = np.zeros((w1 - w0, n_atoms) + inner, dtype=ds.dtype)  # missing chunks: fill value 0
+        n_inner = int(np.prod(inner)) if inner else 1
+        # element strides of the frame-major block per dataset dimension (atoms, frames, inner...)
+        strides = [n_inner, n_atoms * n_inner]
+        acc = n_inner
+        for n in inner:
+            acc //= n
+            strides.append(acc)
+        lo = [0, w0] + [0] * len(inner)
+        hi = [n_atoms, w1] + list(inner)
+        if not (self.native and ds.read_box_into(lo, hi, block, strides)):
+            am = ds.read_hyperslab((slice(0, n_atoms), slice(w0, w1)) + tuple(slice(0, n) for n in inner))
+            block = np.ascontiguousarray(np.moveaxis(am, 0, 1))
         self._cache[path] = (w0, w1, block)
-        return block[:, f0 - w0:f1 - w0]
+        return block[f0 - w0:f1 - w0]
 
     def load_frames(self, path: str, frames: Sequence[int], out: np.ndarray = None,
                     atom_selection=None) -> np.ndarray:
@@ -269,11 +284,10 @@ class HDF5Database:
             lo, hi = int(frames.min()), int(frames.max()) + 1
             block = self._window(path, lo, hi)
             data = block if (len(frames) == hi - lo and np.all(np.diff(frames) == 1)) \
-                else block[:, frames - lo]
+                else block[frames - lo]
         if atom_selection is not None and not (isinstance(atom_selection, slice)
                                                and atom_selection == slice(None)):
-            data = data[atom_selection]
-        data = data.transpose(1, 0, 2)  # atom-major on disk -> frame-major for the GPU feed
+            data = data[:, atom_selection]
         if out is None:
             return np.ascontiguousarray(data, dtype=np.float32)
         np.copyto(out, data, casting="same_kind")

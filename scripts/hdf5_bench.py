@@ -17,8 +17,10 @@ from mdsuite_b200 import synthetic  # noqa: E402
 from mdsuite_b200.database.simulation_database import Database, HDF5Database, import_hdf5  # noqa: E402
 
 n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-sysm = synthetic.nacl_melt(12, 8, seed=2)
-pos = np.tile(sysm.positions, ((n_frames + 7) // 8, 1, 1))[:n_frames]
+# every frame its own Gaussian displacements: float32 positions barely compress (ratio ~0.9), as
+# in a real trajectory — repeated frames would flatter the inflate rate
+sysm = synthetic.nacl_melt(12, n_frames, seed=2)
+pos = sysm.positions
 am = np.ascontiguousarray(pos.transpose(1, 0, 2))
 n = sysm.counts[0]
 with tempfile.TemporaryDirectory() as tmp:
@@ -31,8 +33,11 @@ with tempfile.TemporaryDirectory() as tmp:
     w.save(path)
     raw_mb = pos.nbytes / 1e6
     out = {"atoms": sysm.n_atoms, "frames": n_frames, "raw_mb": raw_mb,
-           "file_mb": os.path.getsize(path) / 1e6, "cores": os.cpu_count()}
+           "file_mb": os.path.getsize(path) / 1e6, "cores": os.cpu_count(),
+           "decoder": "libmds_io: pread + own inflate + strided placement, all cores"}
     db = HDF5Database(path)
+    db.load_frames("Na/Positions", np.arange(0, 1))  # chunk index, library load
+    db._cache.clear()
     t0 = time.perf_counter()
     batch = 32
     for f0 in range(0, n_frames, batch):
