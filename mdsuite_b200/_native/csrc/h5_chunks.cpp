@@ -336,39 +336,57 @@ struct Inflater {
       // longest match plus the 8-byte copy overshoot
       while (ie - ip >= 16 && oe - op >= 274) {
         MDS_REFILL_FAST();  // >= 56 bits
-        uint32_t e;
-        MDS_LOOKUP(lt, lmask, lbits, e);
-        if (e & KIND_LITERAL) {
-          // up to three literals per refill (3 x 15 bits <= 56)
-          bb >>= (e & 0xff); bc -= (int)(e & 0xff);
-          *op++ = (uint8_t)(e >> 16);
-          MDS_LOOKUP(lt, lmask, lbits, e);
+        uint32_t e = lt[bb & lmask];
+        // Literals straight out of the primary table are at most LIT_BITS = 11 bits long: five of
+        // them fit one refill.  (Positions barely compress — most of the stream is literals.)
+#define MDS_LITERAL_STEP()                 \
+  do {                                     \
+    bb >>= (e & 63);                       \
+    bc -= (int)(e & 63);                   \
+    *op++ = (uint8_t)(e >> 16);            \
+    e = lt[bb & lmask];                    \
+  } while (0)
+        if (__builtin_expect((e & KIND_LITERAL) != 0, 1)) {
+          MDS_LITERAL_STEP();
           if (e & KIND_LITERAL) {
-            bb >>= (e & 0xff); bc -= (int)(e & 0xff);
-            *op++ = (uint8_t)(e >> 16);
-            MDS_LOOKUP(lt, lmask, lbits, e);
+            MDS_LITERAL_STEP();
             if (e & KIND_LITERAL) {
-              bb >>= (e & 0xff); bc -= (int)(e & 0xff);
-              *op++ = (uint8_t)(e >> 16);
-              continue;
+              MDS_LITERAL_STEP();
+              if (e & KIND_LITERAL) {
+                MDS_LITERAL_STEP();
+                if (e & KIND_LITERAL) {
+                  bb >>= (e & 63); bc -= (int)(e & 63);
+                  *op++ = (uint8_t)(e >> 16);
+                  continue;
+                }
+              }
             }
           }
           MDS_REFILL_FAST();  // e was looked up in bits that are still the lowest ones
         }
+#undef MDS_LITERAL_STEP
+        if (e & KIND_SUB) {  // a code longer than the primary table
+          e = lt[(e >> 16) + ((bb >> lbits) & ((1u << (e & 0xffu)) - 1))];
+          if (e & KIND_LITERAL) {
+            bb >>= (e & 63); bc -= (int)(e & 63);
+            *op++ = (uint8_t)(e >> 16);
+            continue;
+          }
+        }
         if (e & (KIND_EOB | KIND_INVALID)) {
           if (e & KIND_INVALID) { err = "invalid literal/length code"; break; }
-          bb >>= (e & 0xff); bc -= (int)(e & 0xff);
+          bb >>= (e & 63); bc -= (int)(e & 63);
           done = true;
           break;
         }
-        bb >>= (e & 0xff); bc -= (int)(e & 0xff);
+        bb >>= (e & 63); bc -= (int)(e & 63);
         const int lx = (int)((e >> 8) & 0xff);
         const uint32_t len = (e >> 16) + (uint32_t)(bb & ((1ull << lx) - 1));  // <= 15 + 5 bits of >= 56
         bb >>= lx; bc -= lx;
         uint32_t d;
         MDS_LOOKUP(dt, dmask, dbits, d);
         if (d & KIND_INVALID) { err = "invalid distance code"; break; }
-        bb >>= (d & 0xff); bc -= (int)(d & 0xff);
+        bb >>= (d & 63); bc -= (int)(d & 63);
         const int dx = (int)((d >> 8) & 0xff);
         const uint32_t distance = (d >> 16) + (uint32_t)(bb & ((1ull << dx) - 1));  // 48 bits at most
         bb >>= dx; bc -= dx;

@@ -275,9 +275,47 @@ class HDF5Database:
         self._cache[path] = (w0, w1, block)
         return block[f0 - w0:f1 - w0]
 
+    def frames_per_chunk(self, path: str) -> int:
+        """Configurations per HDF5 chunk: batches that start on a multiple of this (and end on one,
+        or at the end of the dataset) are decoded straight into the caller's buffer."""
+        ds = self._ds(path)
+        return int(ds.chunks[1]) if ds.chunks else int(ds.shape[1])
+
+    def _decode_into(self, path: str, f0: int, f1: int, out: np.ndarray) -> bool:
+        """Chunk-aligned contiguous range [f0, f1) decoded by the native library directly into
+        ``out`` (frames, atoms, dims) — e.g. a slice of the batcher's pinned ring buffer; no window
+        cache, no intermediate copy.  False if the request does not qualify."""
+        ds = self._ds(path)
+        if not self.native or ds.layout != "chunked" or out.dtype != ds.dtype or out.ndim != len(ds.shape):
+            return False
+        cf = ds.chunks[1]
+        if f0 % cf or (f1 % cf and f1 != ds.shape[1]):
+            return False
+        inner = tuple(ds.shape[2:])
+        if out.shape != (f1 - f0, ds.shape[0]) + inner:
+            return False
+        item = out.itemsize
+        if any(st % item for st in out.strides):
+            return False
+        st = [x // item for x in out.strides]  # (frames, atoms, inner...) in elements
+        lo = [0, f0] + [0] * len(inner)
+        hi = [ds.shape[0], f1] + list(inner)
+        index = ds.chunk_index()
+        grid = [range(l // c * c, h, c) for l, h, c in zip(lo, hi, ds.chunks)]
+        if any(tuple(r[i] for r, i in zip(grid, offs)) not in index
+               for offs in np.ndindex(*[len(r) for r in grid])):
+            out[...] = 0  # chunks that were never written read as the fill value
+        return ds.read_box_into(lo, hi, out, [st[1], st[0]] + st[2:])
+
     def load_frames(self, path: str, frames: Sequence[int], out: np.ndarray = None,
                     atom_selection=None) -> np.ndarray:
         frames = np.asarray(frames, dtype=np.int64)
+        whole = atom_selection is None or (isinstance(atom_selection, slice)
+                                           and atom_selection == slice(None))
+        if (out is not None and whole and len(frames) and
+                len(frames) == int(frames[-1]) - int(frames[0]) + 1 and np.all(np.diff(frames) == 1)
+                and self._decode_into(path, int(frames[0]), int(frames[-1]) + 1, out)):
+            return out
         if len(frames) == 0:
             data = np.zeros((0,) + tuple(np.delete(self._ds(path).shape, 1)), dtype=np.float32)
         else:
