@@ -277,12 +277,33 @@ __device__ __forceinline__ int bin_of_s(float s, float inv_step_biased,
 // limiter (all-pairs kernel, most pairs inside the cutoff), not where it is idle (cell kernel).
 // `hi` is carried by the caller between calls: a lane that skips the load keeps a stale value,
 // which the AND with p makes irrelevant (declaring it inside the asm block makes ptxas spill it).
+// -DMDS_BIN_MATCHANY builds the variant the north star sketched — explicit warp aggregation with
+// __match_any_sync: lanes that hit the same bin elect a leader, which adds the population count
+// with one atomic.  Kept for measurement only (scripts/binning_variants.py): the
+// default, red.shared.add.u32 -> ATOMS.POPC.INC, lets the hardware merge same-address lanes, costs
+// one issue slot instead of MATCH + popc + elect + a predicated atomic, and needs no convergence.
 template <bool DIAG, bool COND>
 __device__ __forceinline__ void bin_count_dense(float s, float s_cut, float inv_lo, float inv_hi,
                                                 uint32_t c_edge, uint32_t c_hist, uint32_t four,
                                                 int jg, int ig, float& hi) {
   float t = fminf(s, s_cut);  // min.f32 returns the non-NaN operand
   if (DIAG) t = (jg > ig) ? t : s_cut;
+#ifdef MDS_BIN_MATCHANY
+  {
+    (void)inv_hi; (void)hi;
+    const float f = __fmaf_rz(sqrt_approx(t), inv_lo, 8388608.0f);
+    const uint32_t a = __float_as_uint(f);
+    const uint32_t e = a * four + c_edge;
+    uint32_t h = a * four + c_hist;
+    float edge;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(edge) : "r"(e));
+    h += (t >= edge) ? 4u : 0u;
+    const unsigned peers = __match_any_sync(0xffffffffu, h);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1)
+      asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(h), "r"((uint32_t)__popc(peers)) : "memory");
+    return;
+  }
+#endif
   if (COND) {
     asm volatile(
         "{\n"

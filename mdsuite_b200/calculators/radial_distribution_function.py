@@ -276,6 +276,14 @@ class RadialDistributionFunction(Calculator):
                               max(1, (32 << 20) // (12 * max(1, sum(particles)))))
                     if self.override_n_batches:
                         fpb = max(1, int(np.ceil(len(shard) / self.override_n_batches)))
+                    else:
+                        # a reference database.hdf5 read in place: whole HDF5 chunks per batch are
+                        # decoded straight into the pinned ring (HDF5Database._decode_into)
+                        per_chunk = getattr(self.experiment.database, "frames_per_chunk", None)
+                        if per_chunk is not None:
+                            cf = max(per_chunk(p) for p in paths)
+                            if fpb >= cf:
+                                fpb = fpb // cf * cf
                 b = FrameBatcher(self.experiment.database, paths, particles, h, fpb, selections,
                                  pin=torch.cuda.is_available())
                 batchers.append(b)

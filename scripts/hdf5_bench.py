@@ -16,7 +16,7 @@ from hdf5_writer import H5Writer  # noqa: E402  (no libhdf5 in the image: the te
 from mdsuite_b200 import synthetic  # noqa: E402
 from mdsuite_b200.database.simulation_database import Database, HDF5Database, import_hdf5  # noqa: E402
 
-n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 # every frame its own Gaussian displacements: float32 positions barely compress (ratio ~0.9), as
 # in a real trajectory — repeated frames would flatter the inflate rate
 sysm = synthetic.nacl_melt(12, n_frames, seed=2)
@@ -26,7 +26,7 @@ n = sysm.counts[0]
 with tempfile.TemporaryDirectory() as tmp:
     w = H5Writer()
     # h5py's guess_chunk on (6912, F, 3) float32 lands near (432, F/8, 3); use that shape
-    cf = max(1, n_frames // 8)
+    cf = 32
     w.create_dataset("Na/Positions", am[:n], chunks=(432, cf, 3), maxshape=(n, None, 3))
     w.create_dataset("Cl/Positions", am[n:], chunks=(432, cf, 3), maxshape=(n, None, 3))
     path = os.path.join(tmp, "database.hdf5")
@@ -39,7 +39,7 @@ with tempfile.TemporaryDirectory() as tmp:
     db.load_frames("Na/Positions", np.arange(0, 1))  # chunk index, library load
     db._cache.clear()
     t0 = time.perf_counter()
-    batch = 32
+    batch = 4 * cf  # whole HDF5 chunks per batch, as the calculator's frame batcher picks them
     # as the frame batcher calls it: both species into one (frames, atoms, 3) staging buffer
     stage = np.empty((batch, sysm.n_atoms, 3), dtype=np.float32)
     for f0 in range(0, n_frames, batch):
