@@ -457,7 +457,13 @@ def target_config_probe(args, world, rank, local_rank, dist, comm, fp32_peak):
             ms, wall = float(t[0].item()), float(t[1].item())
         return ms / steps, wall / steps, out
 
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ
+                           else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    if rank == 0:
+        sampler.start()
+    t_clk0 = time.perf_counter()
     res_ms, _w, _ = timed(step_resident)
+    clocks = sampler.stop(t_clk0, time.perf_counter()) if rank == 0 else None
     st = handle.stats()
     result = handle.counts()
     _ms, e2e_s, result_e2e = timed(step_e2e)
@@ -513,6 +519,10 @@ def target_config_probe(args, world, rank, local_rank, dist, comm, fp32_peak):
         "tested_pair_evals_per_s_per_gpu": tested_rate,
         "frac_of_fp32_roofline_tested": tested_rate * FLOP_PER_PAIR / fp32_peak,
         "binned_over_candidates": st_local.pairs_binned / max(st_local.pairs_evaluated, 1.0),
+        "clocks_resident": clocks,
+        "frac_of_fp32_roofline_candidates_at_sampled_clock":
+            (cand_rate * FLOP_PER_PAIR / (fp32_peak * clocks["sm_mhz"] / clocks["sm_max_mhz"])
+             if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") else None),
         "parity": parity,
     }
 
@@ -528,6 +538,10 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU path "
                          "(use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
+    # the feeding process next to its GPU: pinned buffers are first-touched on that NUMA node
+    from mdsuite_b200.utils import affinity
+    binding = affinity.bind_to_gpu(local_rank) if not args.no_numa_binding else {"bound": False,
+                                                                                 "reason": "--no-numa-binding"}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -815,7 +829,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(8 * n_pairs * nbins) * world},
         "gpu_launches": int(st.kernel_launches * args.steps),
         "gpu_launches_note": "rank 0's kernels in the timed region" if world > 1 else None,
-        "clocks": clocks, "parity": parity,
+        "clocks": clocks, "parity": parity, "host_binding_rank0": binding,
         "kernel_variant": {"path": st.path_name, "variant": st.variant, "dense": st.dense,
                            "cells": list(st.cells)},
     }
@@ -868,6 +882,8 @@ def main():
                     help="skip the Project -> Experiment -> run.RadialDistributionFunction timing")
     ap.add_argument("--no-adf-probe", action="store_true",
                     help="skip the short angular-distribution measurement added at N=1")
+    ap.add_argument("--no-numa-binding", action="store_true",
+                    help="leave the process on whatever CPUs it was started on")
     ap.add_argument("--torch-collective", action="store_true",
                     help="allreduce with torch.distributed instead of mds_rdf_allreduce(ncclComm_t)")
     ap.add_argument("--no-target-config", action="store_true",
