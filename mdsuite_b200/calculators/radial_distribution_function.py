@@ -286,6 +286,9 @@ class RadialDistributionFunction(Calculator):
                                 fpb = fpb // cf * cf
                 b = FrameBatcher(self.experiment.database, paths, particles, h, fpb, selections,
                                  pin=torch.cuda.is_available())
+                per_chunk = getattr(self.experiment.database, "frames_per_chunk", None)
+                if per_chunk is not None:
+                    b.align = max(per_chunk(p) for p in paths)  # whole HDF5 chunks per batch
                 batchers.append(b)
             # one batch per device in turn: every GPU of an in-process run is fed from the start
             feeds = [b.batches(shard) for b, shard in zip(batchers, shards)]

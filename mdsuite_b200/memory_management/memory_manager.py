@@ -131,8 +131,20 @@ class FrameBatcher:
         device of an in-process multi-GPU run — are fed in turn by stepping their generators
         round-robin, so that no device waits for another device's whole shard."""
         frames = np.asarray(sample_configurations, dtype=np.int64)
-        for k, lo in enumerate(range(0, len(frames), self.frames_per_batch)):
-            idx = frames[lo:lo + self.frames_per_batch]
+        # Ramp: nothing can overlap the first load, so the first two batches are small (1/8 and
+        # 1/3 of a full one) and the GPU starts within a fraction of a full batch's load time.
+        # Batches that must stay whole (``align``, e.g. HDF5 chunks decoded in place) are not cut.
+        fpb, align = self.frames_per_batch, max(1, int(getattr(self, "align", 1)))
+        starts, lo, k = [], 0, 0
+        while lo < len(frames):
+            size = fpb
+            if len(frames) > fpb and k < 2:
+                size = max(align, (fpb // (8 if k == 0 else 3)) // align * align)
+            starts.append((lo, min(len(frames), lo + size)))
+            lo += size
+            k += 1
+        for k, (lo, hi) in enumerate(starts):
+            idx = frames[lo:hi]
             buf = self._ring[k & 1]
             if k >= 2:
                 self.handle.wait_host_copies()  # the buffer's previous H2D copy has finished
