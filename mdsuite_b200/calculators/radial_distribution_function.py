@@ -286,6 +286,8 @@ class RadialDistributionFunction(Calculator):
                                 fpb = fpb // cf * cf
                 b = FrameBatcher(self.experiment.database, paths, particles, h, fpb, selections,
                                  pin=torch.cuda.is_available())
+                # batch sizes the user fixed stay as they are; the automatic ones start small
+                b.ramp = self.frames_per_batch is None and not self.override_n_batches
                 per_chunk = getattr(self.experiment.database, "frames_per_chunk", None)
                 if per_chunk is not None:
                     b.align = max(per_chunk(p) for p in paths)  # whole HDF5 chunks per batch

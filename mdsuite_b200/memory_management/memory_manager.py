@@ -138,7 +138,7 @@ class FrameBatcher:
         starts, lo, k = [], 0, 0
         while lo < len(frames):
             size = fpb
-            if len(frames) > fpb and k < 2:
+            if getattr(self, "ramp", False) and len(frames) > 2 * fpb and k < 2:
                 size = max(align, (fpb // (8 if k == 0 else 3)) // align * align)
             starts.append((lo, min(len(frames), lo + size)))
             lo += size
