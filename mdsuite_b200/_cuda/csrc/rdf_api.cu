@@ -111,9 +111,10 @@ struct mds_rdf {
   bool hist_in_smem = true;
   bool dense = true;  // expected in-cutoff fraction is high: predicated binning
   int path = MDS_RDF_PATH_ALLPAIRS;
-  mds::CellGrid grid = {0, 0, 0, 0, {0, 0, 0}};
+  mds::CellGrid grid = {0, 0, 0, 0, {0, 0, 0}, 0, 0};
   int kcell[3] = {0, 0, 0};       // stencil half-widths of the cell path (cells per cutoff)
   int cap_atoms = 0;              // positions a CTA of the cell kernel stages in shared memory
+  int cell_segments = 1;          // work items per pencil (x segments), see CellsParams.n_seg
   uint32_t crowded_limit = 0;     // atoms per cell above which a frame goes to the all-pairs kernel
   int64_t off_stride = 0;         // uint32 entries per frame of the cell-offset table
   uint32_t flush_threshold = 1u << 30;
@@ -378,6 +379,14 @@ mds::PackParams pack_params(mds_rdf* h, const float* d_xyz, int layout, int64_t 
   pp.off_stride = 0;
   pp.rank = nullptr;
   pp.grid = h->grid;
+  if (h->path == MDS_RDF_PATH_CELLLIST && h->shard_count > 1 && (uint32_t)h->grid.nz >= h->shard_count) {
+    // only the handle's slab of z layers and the layers its stencil reaches are sorted
+    const long long nz = h->grid.nz, z0 = nz * h->shard_index / h->shard_count,
+                    z1 = nz * (h->shard_index + 1) / h->shard_count;
+    const int kz = h->kcell[2];
+    pp.grid.z_len = (z1 > z0) ? (int)std::min<long long>(nz, (z1 - z0) + 2 * kz) : 0;
+    pp.grid.z_lo = (int)(((z0 - kz) % nz + nz) % nz);
+  }
   if (h->path == MDS_RDF_PATH_CELLLIST) {
     pp.cell_off = h->d_cell_off[buf];
     pp.off_stride = h->off_stride;
@@ -451,8 +460,21 @@ int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t fram
     cp.inv_step = h->inv_step;
     for (int k = 0; k < 3; ++k) cp.box[k] = h->box[k];
     cp.flush_threshold = h->flush_threshold;
+    // item shards: a slab of z layers per handle, [nz * index / count, nz * (index + 1) / count),
+    // if there are enough layers; else every count-th item
+    cp.pen_lo = 0;
+    cp.n_pen = h->grid.ny * h->grid.nz;
+    cp.n_seg = h->cell_segments;
     cp.shard_index = h->shard_index;
     cp.shard_count = h->shard_count;
+    if (h->shard_count > 1 && (uint32_t)h->grid.nz >= h->shard_count) {
+      const long long nz = h->grid.nz, z0 = nz * h->shard_index / h->shard_count,
+                      z1 = nz * (h->shard_index + 1) / h->shard_count;
+      cp.pen_lo = (int32_t)(z0 * h->grid.ny);
+      cp.n_pen = (int32_t)((z1 - z0) * h->grid.ny);
+      cp.shard_index = 0;
+      cp.shard_count = 1;
+    }
     const int slot = next_work_slot(h);
     if (slot < 0) return fail(MDS_ERR_CUDA, "work-counter reset failed");
     cp.work_counter = h->d_work64 + slot;
@@ -649,6 +671,8 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
       const long long nc = (long long)n[0] * n[1] * n[2];
       h->grid.nx = n[0]; h->grid.ny = n[1]; h->grid.nz = n[2];
       h->grid.nc = (int)nc;
+      h->grid.z_lo = 0;
+      h->grid.z_len = n[2];
       for (int k = 0; k < 3; ++k) h->grid.box[k] = h->box[k];
       h->off_stride = (((int64_t)h->n_species * nc + 1) + 3) & ~3LL;
       h->cap_atoms = 2048;
@@ -773,6 +797,7 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
         const int pieces = (h->grid.nx + seg - 1) / seg;  // even pieces
         seg = (h->grid.nx + pieces - 1) / pieces;
         ab.push_back(make_int4(row, col, seg, 0));
+        h->cell_segments = std::max(h->cell_segments, pieces);
       }
     CREATE_TRY(cudaMalloc(&h->d_pair_ab, ab.size() * sizeof(int4)));
     CREATE_TRY(cudaMemcpy(h->d_pair_ab, ab.data(), ab.size() * sizeof(int4), cudaMemcpyHostToDevice));

@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(256) rdf_cell_scatter_kernel(const PackParams 
     if (p.src_index[q] < 0) continue;  // padding slot
     const float* src = p.out + (f * p.frame_stride + (q & ~3)) * 3 + (q & 3);
     const float x = src[0], y = src[4], z = src[8];
-    const int key = p.species[q] * p.grid.nc + cell_of(x, y, z, p.grid);
+    const int cell = cell_of(x, y, z, p.grid);
+    if (!cell_in_slab(cell, p.grid)) continue;  // item shards: not in this handle's slab
+    const int key = p.species[q] * p.grid.nc + cell;
     const uint32_t pos = p.cell_off[f * p.off_stride + key] + p.rank[f * p.frame_stride + q];
     sorted[f * p.frame_stride + pos] = make_float4(x, y, z, __int_as_float(q));
   }
@@ -275,7 +277,7 @@ __device__ __forceinline__ void flush_hist_warp(uint32_t* s_hist, const CellsPar
 
 // misc slots of the CTA
 enum { M_EVALS = 0, M_CEDGE = 1, M_HIST0 = 2, M_FOUR = 4, M_FRAME = 6, M_PEN = 7, M_PR = 8,
-       M_NEXT_CELL = 9, M_WSUM = 16, M_MISC_WORDS = 24 };
+       M_NEXT_CELL = 9, M_SEG = 10, M_WSUM = 16, M_MISC_WORDS = 24 };
 
 // 128-bit load from a shared-memory byte address
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -310,23 +312,28 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) rdf_cells_kernel(cons
 
   const int nx = p.nx, ny = p.ny, nc = p.nc;
   const int kx = p.kx, ky = p.ky, kz = p.kz;
-  const int npen = ny * p.nz;
+  const int npen = p.n_pen;  // pencils of this handle per frame (all ny * nz without item shards)
   const int wy = 2 * ky + 1;
-  const unsigned long long total_items =
-      (unsigned long long)p.n_frames * (unsigned long long)p.pair_cnt * (unsigned long long)npen;
+  const unsigned long long total_items = (unsigned long long)p.n_frames *
+                                         (unsigned long long)p.pair_cnt *
+                                         (unsigned long long)npen * (unsigned long long)p.n_seg;
   // thread 0: take the next work item off the global counter and leave it decoded in the slots
   auto fetch_item = [&]() {
     const unsigned long long idx = atomicAdd(p.work_counter, 1ull) * p.shard_count + p.shard_index;
-    int frame = -1, pen = 0, pr = 0;
+    int frame = -1, pen = 0, pr = 0, seg = 0;
     if (idx < total_items) {
-      pen = (int)(idx % (unsigned long long)npen);
-      const unsigned long long t = idx / (unsigned long long)npen;
+      // consecutive items: the segments of a pencil, then the next pencil of the frame
+      seg = (int)(idx % (unsigned long long)p.n_seg);
+      const unsigned long long u = idx / (unsigned long long)p.n_seg;
+      pen = p.pen_lo + (int)(u % (unsigned long long)npen);
+      const unsigned long long t = u / (unsigned long long)npen;
       pr = (int)(t % (unsigned long long)p.pair_cnt);
       frame = (int)(t / (unsigned long long)p.pair_cnt);
     }
     s_misc[M_FRAME] = (uint32_t)frame;
     s_misc[M_PEN] = (uint32_t)pen;
     s_misc[M_PR] = (uint32_t)pr;
+    s_misc[M_SEG] = (uint32_t)seg;
   };
 
   if (HIST_SMEM) {
@@ -365,6 +372,7 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) rdf_cells_kernel(cons
     const int frame = (int)*reinterpret_cast<volatile uint32_t*>(s_misc + M_FRAME);
     const int pen = (int)*reinterpret_cast<volatile uint32_t*>(s_misc + M_PEN);
     const int pr = (int)*reinterpret_cast<volatile uint32_t*>(s_misc + M_PR);
+    const int seg_i = (int)*reinterpret_cast<volatile uint32_t*>(s_misc + M_SEG);
     int4 ab = make_int4(0, 0, 1, 0);
     if (frame >= 0) ab = p.pair_ab[p.pair_lo + pr];  // row species, column species, segment length
     const bool same = ab.x == ab.y;
@@ -398,12 +406,15 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) rdf_cells_kernel(cons
     bc.c_hist = hist0 + (uint32_t)(pr * hist_stride) * 4u;
     bc.hist_g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
 
-    int x0 = 0, p_lo = 0;
-    while (x0 < nx) {
+    // this item: x cells [seg_i * ab.z, (seg_i + 1) * ab.z) of the pencil (nothing if the pair's
+    // segments are longer than those of the pair that sets n_seg)
+    int x0 = seg_i * ab.z, p_lo = 0;
+    const int x_end = min(nx, x0 + ab.z);
+    while (x0 < x_end) {
       // ---- stage Sx row cells against neighbour pencils [p_lo, p_hi): count, scan, and make it
       // smaller while it does not fit (cells are given up first, so a pencil subset, p_lo > 0,
       // only ever follows a one-cell pass)
-      int Sx = p_lo > 0 ? 1 : min(ab.z, nx - x0), p_hi = P;
+      int Sx = p_lo > 0 ? 1 : x_end - x0, p_hi = P;
       const bool with_own = same && p_lo == 0;  // the pass that also takes the own pencil's +x half
       int Wa, Wr, Pn, n_r, n_a, n_ent;
       for (;;) {
@@ -664,8 +675,9 @@ cudaError_t launch_cells(const CellsParams& p, int sm_count, cudaStream_t stream
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
   unsigned long long items = (unsigned long long)p.n_frames * (unsigned long long)p.pair_cnt *
-                             (unsigned long long)p.ny * (unsigned long long)p.nz;
+                             (unsigned long long)p.n_pen * (unsigned long long)p.n_seg;
   items = (items + p.shard_count - 1) / p.shard_count;
+  if (items == 0) return cudaSuccess;
   unsigned long long grid = (unsigned long long)per_sm * sm_count;  // persistent
   if (grid > items) grid = items;
   if (grid < 1) grid = 1;

@@ -21,7 +21,17 @@ constexpr int ALLPAIRS_N_VARIANTS = 7;
 struct CellGrid {
   int nx, ny, nz, nc;  // cells per dimension, nc = nx * ny * nz (each >= 3)
   float box[3];
+  // item shards of the cell path (mds_rdf_set_item_shard): this handle only works on a slab of z
+  // layers, so only atoms in layers [z_lo, z_lo + z_len) (periodic; the slab plus its stencil)
+  // are counted, ranked and sorted.  z_len >= nz: every atom.
+  int z_lo, z_len;
 };
+__host__ __device__ inline bool cell_in_slab(int cell, const CellGrid& g) {
+  if (g.z_len >= g.nz) return true;
+  int dz = cell / (g.nx * g.ny) - g.z_lo;
+  dz += (dz < 0) ? g.nz : 0;
+  return dz < g.z_len;
+}
 struct PackParams {
   const float* xyz;        // raw input, layout below
   int layout;              // MDS_LAYOUT_*
@@ -73,7 +83,13 @@ struct CellsParams {
   float s_cut, inv_step;
   float box[3];
   uint32_t flush_threshold;   // candidate pairs per CTA between histogram flushes (<= 2^30)
-  uint32_t shard_index, shard_count;  // item sharding: units u with u % shard_count == shard_index
+  // item shards: with at least as many z layers as shards the handle takes the pencils [pen_lo,
+  // pen_lo + n_pen) of every frame (a slab of z layers: only that slab and its stencil have to be
+  // sorted); otherwise every shard_count-th (frame, pair, pencil, segment) item from shard_index
+  int32_t pen_lo, n_pen;
+  uint32_t shard_index, shard_count;
+  int32_t n_seg;              // x segments per pencil = work items per (frame, pair, pencil): the
+                              // largest ceil(nx / segment length) over the species pairs
 };
 size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem, int cap_atoms);
 int cells_max_seg();   // longest segment (x cells) the kernel's tables can hold

@@ -48,14 +48,19 @@ __global__ void __launch_bounds__(256, 8) rdf_pack_kernel(const PackParams p) {
         // cell-list path: rank of the atom inside its (frame, species, cell).  Lanes of a warp that
         // hit the same counter (neighbouring atoms of an ordered trajectory share a cell) are
         // merged with __match_any_sync: one global atomic per distinct counter and warp.
-        const int key = p.species[q] * p.grid.nc + cell_of(x, y, z, p.grid);
-        uint32_t* counter = p.cell_off + f * p.off_stride + key;
+        const int cell = cell_of(x, y, z, p.grid);
+        // (item shards: atoms outside this handle's slab of z layers are not part of its lists)
+        uint32_t* counter = cell_in_slab(cell, p.grid)
+                                ? p.cell_off + f * p.off_stride + p.species[q] * p.grid.nc + cell
+                                : nullptr;
         const unsigned peers = __match_any_sync(active, (unsigned long long)counter);
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        p.rank[f * p.frame_stride + q] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        if (counter) {
+          const int leader = __ffs(peers) - 1;
+          uint32_t base = 0;
+          if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(peers));
+          base = __shfl_sync(peers, base, leader);
+          p.rank[f * p.frame_stride + q] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        }
         // a coordinate further than 8 box lengths out (or infinite): the cell margin no longer
         // covers the float32 rounding of the reference's own arithmetic -> all-pairs for this frame
         if (fabsf(x) > 8.0f * p.box[0] || fabsf(y) > 8.0f * p.box[1] || fabsf(z) > 8.0f * p.box[2])
