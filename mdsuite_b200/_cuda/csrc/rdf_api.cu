@@ -137,6 +137,7 @@ struct mds_rdf {
   uint32_t* d_cell_off[2] = {nullptr, nullptr};
   int4* d_pair_ab = nullptr;
   unsigned long long* d_work64 = nullptr;    // ring of 64-bit work counters
+  uint32_t* d_scan_tmp = nullptr;            // scratch of the multi-CTA cell-offset scan
   unsigned long long* d_evaluated = nullptr; // [2] pairs evaluated (candidates on the cell path) / tested
   unsigned long long* d_batch_far = nullptr; // [2] far frames of the batch in each buffer
   size_t raw_bytes = 0;
@@ -430,8 +431,8 @@ int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t fram
                         int64_t n_frames, int64_t n_frames_total, int buf) {
   CUDA_TRY(cudaMemsetAsync(h->d_flags[buf], 0, sizeof(uint32_t) * (size_t)n_frames, h->s_compute));
   const mds::PackParams pp = pack_params(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf);
-  CUDA_TRY(mds::launch_cell_build(pp, h->n_species, h->d_sorted[buf], h->crowded_limit, h->sm_count,
-                                  h->s_compute));
+  CUDA_TRY(mds::launch_cell_build(pp, h->n_species, h->d_sorted[buf], h->crowded_limit, h->d_scan_tmp,
+                                  h->sm_count, h->s_compute));
   CUDA_TRY(mds::launch_count_general(h->d_flags[buf], (int)n_frames, h->d_general,
                                      h->d_batch_far + buf, h->s_compute));
   h->launches += 4;
@@ -803,6 +804,11 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
     CREATE_TRY(cudaMemcpy(h->d_pair_ab, ab.data(), ab.size() * sizeof(int4), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMalloc(&h->d_work64, sizeof(unsigned long long) * WORK_RING));
     CREATE_TRY(cudaMemset(h->d_work64, 0, sizeof(unsigned long long) * WORK_RING));
+    if (bf <= 4096) {
+      const size_t words = mds::cells_scan_tmp_words(bf, h->n_species * h->grid.nc);
+      CREATE_TRY(cudaMalloc(&h->d_scan_tmp, words * sizeof(uint32_t)));
+      CREATE_TRY(cudaMemset(h->d_scan_tmp, 0, words * sizeof(uint32_t)));
+    }
     CREATE_TRY(cudaMalloc(&h->d_batch_far, 2 * sizeof(unsigned long long)));
     CREATE_TRY(cudaMemset(h->d_batch_far, 0, 2 * sizeof(unsigned long long)));
     for (int b = 0; b < 2; ++b) {
@@ -850,6 +856,7 @@ void mds_rdf_destroy(mds_rdf_t* h) {
   cudaFree(h->d_work);
   cudaFree(h->d_pair_ab);
   cudaFree(h->d_work64);
+  cudaFree(h->d_scan_tmp);
   cudaFree(h->d_evaluated);
   cudaFree(h->d_batch_far);
   for (int b = 0; b < 2; ++b) {

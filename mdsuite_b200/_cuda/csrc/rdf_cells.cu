@@ -86,6 +86,85 @@ __global__ void __launch_bounds__(1024) rdf_cell_scan_kernel(uint32_t* cell_off,
   }
 }
 
+// The same scan for long key tables (a million-atom frame has > 10^5 keys, and a single frame —
+// item-sharded over the GPUs — has nothing else to hide one serial CTA behind): pass 1 scans
+// blocks of 4096 keys in place and leaves their totals, pass 2 adds the totals of the blocks
+// before it.  grid = (blocks per frame, frames).
+__global__ void __launch_bounds__(1024) rdf_cell_scan_blocks_kernel(uint32_t* cell_off,
+                                                                    int64_t off_stride, int n_keys,
+                                                                    uint32_t* block_sums,
+                                                                    uint32_t* frame_max) {
+  uint32_t* a = cell_off + (long long)blockIdx.y * off_stride;
+  __shared__ uint32_t warp_sums[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * 4096 + threadIdx.x * 4;
+  uint32_t v[4], mx = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[k] = (i0 + k < n_keys) ? a[i0 + k] : 0u;
+    mx = max(mx, v[k]);
+  }
+  const uint32_t t = v[0] + v[1] + v[2] + v[3];
+  uint32_t inc = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = warp_sums[lane];
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += n;
+    }
+    warp_sums[lane] = winc - w;
+    if (lane == 31) block_sums[(long long)blockIdx.y * gridDim.x + blockIdx.x] = winc;
+  }
+  __syncthreads();
+  uint32_t e = warp_sums[warp] + inc - t;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (i0 + k < n_keys) a[i0 + k] = e;
+    e += v[k];
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0 && mx) atomicMax(frame_max + blockIdx.y, mx);
+}
+
+__global__ void __launch_bounds__(1024) rdf_cell_scan_finish_kernel(uint32_t* cell_off,
+                                                                    int64_t off_stride, int n_keys,
+                                                                    const uint32_t* block_sums,
+                                                                    uint32_t* frame_max,
+                                                                    uint32_t* frame_flags,
+                                                                    uint32_t crowded_limit) {
+  uint32_t* a = cell_off + (long long)blockIdx.y * off_stride;
+  const uint32_t* sums = block_sums + (long long)blockIdx.y * gridDim.x;
+  __shared__ uint32_t s_before;
+  if (threadIdx.x < 32) {  // totals of the blocks before this one (and of all, for the last)
+    uint32_t acc = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += 32) acc += sums[b];
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    if (threadIdx.x == 0) s_before = acc;
+  }
+  __syncthreads();
+  const uint32_t before = s_before;
+  const int i0 = blockIdx.x * 4096 + threadIdx.x * 4;
+  if (before) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (i0 + k < n_keys) a[i0 + k] += before;
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    a[n_keys] = before + sums[blockIdx.x];
+    if (frame_max[blockIdx.y] > crowded_limit) atomicOr(frame_flags + blockIdx.y, MDS_FRAME_FAR);
+    frame_max[blockIdx.y] = 0u;  // ready for the next batch
+  }
+}
+
 __global__ void __launch_bounds__(256) rdf_cell_scatter_kernel(const PackParams p,
                                                                float4* __restrict__ sorted) {
   const long long total = (long long)p.n_frames * p.n_packed;
@@ -635,6 +714,12 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) rdf_cells_kernel(cons
 
 int cells_max_seg() { return MAXW - 2 * 4; }
 int cells_max_cap() { return MAX_CAP; }
+// words of launch_cell_build's scratch: a fixed region for the per-frame maxima (MAX_SCAN_FRAMES
+// frames), then the block totals
+constexpr int MAX_SCAN_FRAMES = 4096;
+size_t cells_scan_tmp_words(int n_frames, int n_keys) {
+  return (size_t)MAX_SCAN_FRAMES + (size_t)n_frames * (size_t)((n_keys + 4095) / 4096);
+}
 int cells_max_entries() { return MAX_ENT; }
 
 size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem, int cap_atoms) {
@@ -648,7 +733,8 @@ size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem, int cap_atom
 }
 
 cudaError_t launch_cell_build(const PackParams& pp, int n_species, float4* sorted,
-                              uint32_t crowded_limit, int sm_count, cudaStream_t stream) {
+                              uint32_t crowded_limit, uint32_t* scan_tmp, int sm_count,
+                              cudaStream_t stream) {
   const long long total = (long long)pp.n_frames * pp.n_packed;
   if (total <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(pp.cell_off, 0,
@@ -657,8 +743,22 @@ cudaError_t launch_cell_build(const PackParams& pp, int n_species, float4* sorte
   if (e != cudaSuccess) return e;
   e = launch_pack(pp, sm_count, stream);  // quad-block positions + per-cell counts and ranks + frame flags
   if (e != cudaSuccess) return e;
-  rdf_cell_scan_kernel<<<(unsigned)pp.n_frames, 1024, 0, stream>>>(
-      pp.cell_off, pp.off_stride, n_species * pp.grid.nc, pp.frame_flags, crowded_limit);
+  const int n_keys = n_species * pp.grid.nc;
+  const int n_blocks = (n_keys + 4095) / 4096;
+  if (n_blocks <= 2 || !scan_tmp) {
+    rdf_cell_scan_kernel<<<(unsigned)pp.n_frames, 1024, 0, stream>>>(
+        pp.cell_off, pp.off_stride, n_keys, pp.frame_flags, crowded_limit);
+  } else {
+    // scan_tmp: [frames] per-frame maxima (kept zero between batches), then [frames][n_blocks] totals
+    uint32_t* frame_max = scan_tmp;
+    uint32_t* block_sums = scan_tmp + cells_scan_tmp_words(1, 0);
+    const dim3 grid((unsigned)n_blocks, (unsigned)pp.n_frames);
+    rdf_cell_scan_blocks_kernel<<<grid, 1024, 0, stream>>>(pp.cell_off, pp.off_stride, n_keys,
+                                                           block_sums, frame_max);
+    rdf_cell_scan_finish_kernel<<<grid, 1024, 0, stream>>>(pp.cell_off, pp.off_stride, n_keys,
+                                                           block_sums, frame_max, pp.frame_flags,
+                                                           crowded_limit);
+  }
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)sm_count * 64) blocks = (long long)sm_count * 64;
   rdf_cell_scatter_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pp, sorted);

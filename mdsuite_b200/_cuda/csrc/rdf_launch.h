@@ -97,8 +97,12 @@ int cells_max_cap();   // largest cap_atoms the kernel's tables can hold
 int cells_max_entries();  // (x cell, neighbour pencil) entries of a staged segment, at most
 // pp must have cell_off / rank / grid set: pack + count, scan, scatter into `sorted`; frames with
 // a cell of more than crowded_limit atoms are flagged MDS_FRAME_FAR
+// scan_tmp: cells_scan_tmp_words(frames per batch, keys) zeroed uint32 words (nullptr: one CTA
+// scans a frame's keys on its own)
+size_t cells_scan_tmp_words(int n_frames, int n_keys);
 cudaError_t launch_cell_build(const PackParams& pp, int n_species, float4* sorted,
-                              uint32_t crowded_limit, int sm_count, cudaStream_t stream);
+                              uint32_t crowded_limit, uint32_t* scan_tmp, int sm_count,
+                              cudaStream_t stream);
 cudaError_t launch_cells(const CellsParams& p, int sm_count, cudaStream_t stream, int* grid_out);
 
 // ---- microbench.cu ----
