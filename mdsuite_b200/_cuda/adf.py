@@ -201,3 +201,44 @@ class ADFHandle:
                         float(raw.pair_tests), int(raw.kernel_launches), float(raw.kernel_ms),
                         float(raw.compute_ms), int(raw.max_neighbours), int(raw.sm_count),
                         tuple(int(c) for c in raw.cells), int(raw.frames_far))
+
+
+# ---- handle reuse (as for the RDF, mdsuite_b200._cuda.acquire_handle) ---------------------------
+# Creating a handle allocates device buffers that then grow to the batch size; a calculator call on
+# a few thousand configurations spends as long on that as on its kernels.  One parked handle per
+# device; the next call with the same configuration takes it back.
+_PARKED = {}
+
+
+def _key(counts, nbins, cutoff, box, norm_power, device):
+    return (tuple(int(c) for c in counts), int(nbins), float(np.float32(cutoff)),
+            tuple(float(np.float32(b)) for b in box), int(norm_power), int(device))
+
+
+def acquire_handle(counts, nbins, cutoff, box, norm_power=4, device=0) -> "ADFHandle":
+    key = _key(counts, nbins, cutoff, box, norm_power, device)
+    parked = _PARKED.pop(int(device), None)
+    if parked is not None:
+        if parked[0] == key:
+            return parked[1]
+        parked[1].close()
+    h = ADFHandle(counts, nbins, cutoff, box, norm_power=norm_power, device=device)
+    h._park_key = key
+    return h
+
+
+def park_handle(h: "ADFHandle"):
+    key = getattr(h, "_park_key", None)
+    if key is None or not h._h.value:
+        h.close()
+        return
+    old = _PARKED.pop(h.device, None)
+    if old is not None:
+        old[1].close()
+    _PARKED[h.device] = (key, h)
+
+
+def drop_parked_handles():
+    for _key_, h in list(_PARKED.values()):
+        h.close()
+    _PARKED.clear()

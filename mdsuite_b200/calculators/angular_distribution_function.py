@@ -193,7 +193,7 @@ class AngularDistributionFunction(Calculator):
                                    "CPU path")
             from mdsuite_b200._cuda import adf as cuda_adf
             device = self.device if self.device is not None else torch.cuda.current_device()
-            factory = lambda *a, **k: cuda_adf.ADFHandle(*a, device=device, **k)  # noqa: E731
+            factory = lambda *a, **k: cuda_adf.acquire_handle(*a, device=device, **k)  # noqa: E731
         else:
             factory = injected
         from mdsuite_b200.distributed import (allreduce_host_sums, distributed_context,
@@ -209,20 +209,24 @@ class AngularDistributionFunction(Calculator):
         t0 = time.perf_counter()
         handle = factory(counts, nbins, self.args.cutoff, self.experiment.box_array,
                          norm_power=self.args.norm_power)
+        # a handle taken back from the previous call keeps counting: statistics are differences
+        before = handle.stats() if hasattr(handle, "stats") else None
         # Two buffers for the largest batch (page-locked for long runs): the next batch is read from
         # the store by a worker thread while the GPU works on the current one, and no batch
         # allocates.
         my_batches = [(b, shard_configurations(frames, world, rank) if dist is not None else frames)
                       for b, frames in enumerate(split_arr)]
         my_batches = [(b, f) for b, f in my_batches if len(f)]
-        staging = [None, None]
+        staging, ring = [None, None], None
         if injected is None and my_batches:
-            import torch
+            from mdsuite_b200.memory_management.memory_manager import _acquire_ring
             largest = max(len(f) for _, f in my_batches)
-            # page-locking costs ~0.5 ms per MB: worth it from about eight batches on
-            pin = len(my_batches) >= 8 and largest * sum(counts) * 12 <= (1 << 30)
-            staging = [torch.empty((largest, sum(counts), 3), dtype=torch.float32,
-                                   pin_memory=pin).numpy() for _ in range(2)]
+            # two page-locked buffers from the per-process ring cache (page-locking costs ~0.5 ms
+            # per MB the first time; the next call of the process gets the same buffers back)
+            pin = largest * sum(counts) * 12 <= (1 << 30)
+            ring = _acquire_ring((largest, sum(counts), 3), pin)
+            staging = [t.numpy() for t in ring[1]]
+        failed = True
         try:
             from concurrent.futures import ThreadPoolExecutor
             with ThreadPoolExecutor(max_workers=1) as pool:
@@ -237,8 +241,15 @@ class AngularDistributionFunction(Calculator):
                     raw_all.append(raw)
                     batch_sums[b] = raw.sum(axis=0)
             stats = handle.stats() if hasattr(handle, "stats") else None
+            failed = False
         finally:
-            handle.close()
+            if injected is None and not failed:
+                cuda_adf.park_handle(handle)  # kept for the next call with this configuration
+            else:
+                handle.close()
+            if ring is not None:
+                from mdsuite_b200.memory_management.memory_manager import _release_ring
+                _release_ring(*ring)
         if dist is not None:
             batch_sums = allreduce_host_sums(batch_sums, device=getattr(handle, "device", None))
         angles = [None] * len(combos)
@@ -251,12 +262,14 @@ class AngularDistributionFunction(Calculator):
         self.raw = np.concatenate(raw_all, axis=0) if raw_all else None  # this rank's share
         elapsed = time.perf_counter() - t0
         if stats is not None:
-            self.run_stats = {"triples_this_rank": stats.triples,
-                              "pair_tests_this_rank": stats.pair_tests, "seconds": elapsed,
+            triples = stats.triples - (before.triples if before is not None else 0.0)
+            pair_tests = stats.pair_tests - (before.pair_tests if before is not None else 0.0)
+            self.run_stats = {"triples_this_rank": triples,
+                              "pair_tests_this_rank": pair_tests, "seconds": elapsed,
                               "max_neighbours": stats.max_neighbours,
                               "frames": int(len(self.sample_configurations)),
                               "batches": len(split_arr), "world_size": world}
-            log.info(f"ADF: {stats.triples:.3e} triples on this rank in {elapsed:.3f} s")
+            log.info(f"ADF: {triples:.3e} triples on this rank in {elapsed:.3f} s")
         self._compute_adfs(angles, combos)
 
     def _compute_adfs(self, angles, combos):
