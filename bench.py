@@ -369,31 +369,52 @@ def adf_probe(device: int, frames: int = 64, check: bool = True):
     }
 
 
-def target_config_probe(args, world, rank, local_rank, dist, comm, fp32_peak):
-    """BASELINE.json's north-star target at FULL size: RDF of the 100,000-atom LJ fluid over 10,000
-    configurations (cell-list path, cutoff 3 sigma, 300 bins, parity mode), the configurations
-    split over the ranks with np.array_split, one NCCL allreduce per step.
+FULL_CONFIGS = {
+    # BASELINE.json configs[2], the north-star target
+    "cfg3": dict(n_total=10_000, n_base=40, block=1200, cutoff=3.0, nbins=300, oracle="fused_c",
+                 system=lambda n: __import__("mdsuite_b200.synthetic", fromlist=["x"]).lj_fluid(
+                     47, n, seed=3, n_atoms=100_000),
+                 workload="cfg3 (BASELINE.json configs[2], the north-star target) at full size: "
+                          "100,000-atom LJ fluid (rho*=0.8442, L=49.1 sigma), 10,000 configurations in "
+                          "total, cutoff 3.0 sigma, 300 bins, cell-list path, parity mode"),
+    # BASELINE.json configs[3]
+    "cfg4": dict(n_total=1_000, n_base=2, block=100, cutoff=8.0, nbins=800, oracle="allpairs_kernel",
+                 system=lambda n: __import__("mdsuite_b200.synthetic", fromlist=["x"]).spc_water(
+                     70, n, seed=4, n_molecules=333_333),
+                 workload="cfg4 (BASELINE.json configs[3]) at full size: 999,999-atom SPC water (333,333 "
+                          "molecules, L=215.3 A), 1,000 configurations in total, cutoff 8 A, 800 bins, 3 "
+                          "species pairs (O-O, O-H, H-H), cell-list path, parity mode"),
+}
 
-    The trajectory is 40 distinct seeded frames used 250 times each (frame i of the 10,000 is base
-    frame i % 40): generating 12 GB of Gaussian displacements would take longer than every
+
+def target_config_probe(args, world, rank, local_rank, dist, comm, fp32_peak, name="cfg3"):
+    """A BASELINE.json multi-GPU configuration at FULL size (cfg3: the north-star target, the
+    100,000-atom LJ fluid over 10,000 configurations; cfg4: the 999,999-atom water over 1,000),
+    the configurations split over the ranks with np.array_split, one NCCL allreduce per step.
+
+    The trajectory is n_base distinct seeded frames used n_total / n_base times each (frame i is
+    base frame i % n_base): generating 12 GB of displacements would take longer than every
     measurement here, and the kernels do the same work on a repeated frame.  That also gives the
-    parity gate: the allreduced histogram must equal 250 x the single-handle histogram of the 40
-    base frames, and one base frame is checked against the fused-C oracle.
+    parity gate: the allreduced histogram must equal (n_total / n_base) x the single-handle
+    histogram of the base frames; one base frame is checked against the fused-C oracle (cfg3) or,
+    where the oracle's O(N^2) loop takes minutes (cfg4: scripts/run_configs.py does that once per
+    round), against the independently written all-pairs kernel.
 
     resident: this rank's frames in HBM as raw xyz.  e2e: pinned host frames through
-    RDFHandle.submit (a block of at most 1,200 frames submitted repeatedly: every byte crosses
-    PCIe every step)."""
+    RDFHandle.submit (a block of frames submitted repeatedly: every byte crosses PCIe every step)."""
     import torch
-    from mdsuite_b200 import _cuda, synthetic
-    n_total, n_base = 10_000, 40
+    from mdsuite_b200 import _cuda
+    spec = FULL_CONFIGS[name]
+    n_total, n_base = spec["n_total"], spec["n_base"]
     steps = max(1, min(args.steps, args.target_steps))
-    sysm = synthetic.lj_fluid(47, n_base, seed=3, n_atoms=100_000)
-    cutoff, nbins = 3.0, 300
+    sysm = spec["system"](n_base)
+    cutoff, nbins = spec["cutoff"], spec["nbins"]
     mine = np.array_split(np.arange(n_total), world)[rank]
     base_dev = torch.from_numpy(sysm.positions).cuda(local_rank)
     idx = torch.from_numpy(mine % n_base).cuda(local_rank)
     dev = base_dev[idx].contiguous() if len(mine) else base_dev[:0]
-    block = min(len(mine), 1200)  # a multiple of the 40 base frames: every block is the same sequence
+    # a multiple of the base frames: every block is the same sequence of frames
+    block = min(len(mine), spec["block"])
     host = torch.from_numpy(sysm.positions[mine[:block] % n_base]).pin_memory() if block else None
     handle = _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, parity=True, device=local_rank)
     counts_dev = counts_tensor(handle, handle.n_pairs, nbins) if dist is not None else None
@@ -483,17 +504,27 @@ def target_config_probe(args, world, rank, local_rank, dist, comm, fp32_peak):
             h1 = h.counts()
         parity = {
             "frames_total": n_total,
-            "expected": "250 x the single-handle histogram of the 40 base frames (rank 0)",
+            "expected": f"{n_total // n_base} x the single-handle histogram of the {n_base} base "
+                        f"frames (rank 0)",
             "bins_differing_resident": int((result != h40 * np.uint64(n_total // n_base)).sum()),
             "bins_differing_e2e": int((result_e2e != h40 * np.uint64(n_total // n_base)).sum()),
         }
-        if not args.no_cpu_baseline:
+        if spec["oracle"] == "allpairs_kernel":
+            with _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, parity=True, device=local_rank,
+                                 path="allpairs") as h:
+                h.submit_device(base_dev[:1].contiguous())
+                parity["frames_checked_allpairs_kernel"] = 1
+                parity["bins_differing_allpairs_kernel"] = int((h.counts() != h1).sum())
+        elif not args.no_cpu_baseline:
             from oracle import c_oracle  # the checker
             want, _ev = c_oracle.rdf_counts_c(sysm.positions[:1], sysm.counts, sysm.box, cutoff, nbins,
                                               skip_first=True, layout=c_oracle.FRAME_MAJOR)
             parity["frames_checked_fused_c"] = 1
             parity["bins_differing_fused_c"] = int((h1.astype(np.int64) != want).sum())
+    handle_pairs = handle.n_pairs
     handle.close()
+    del dev, host, base_dev
+    torch.cuda.empty_cache()
     if rank != 0:
         return None
     launches = max(1, st.pair_kernel_launches)
@@ -501,15 +532,13 @@ def target_config_probe(args, world, rank, local_rank, dist, comm, fp32_peak):
     cand_rate = st_local.pairs_evaluated * steps / max(kernel_s, 1e-12)
     tested_rate = st_local.pairs_tested * steps / max(kernel_s, 1e-12)
     return {
-        "workload": "cfg3 (BASELINE.json configs[2], the north-star target) at full size: 100,000-atom "
-                    "LJ fluid (rho*=0.8442, L=49.1 sigma), 10,000 configurations in total, cutoff 3.0 "
-                    "sigma, 300 bins, cell-list path, parity mode",
+        "workload": spec["workload"],
         "frames_total": n_total, "frames_rank0": int(len(mine)), "distinct_frames": n_base,
         "steps": steps, "n_gpus": world,
         "ms_per_step_resident": res_ms, "ms_per_step_e2e": 1e3 * e2e_s,
         "allpairs_equivalent_per_s_resident": pairs_total / (res_ms * 1e-3),
         "allpairs_equivalent_per_s_e2e": pairs_total / e2e_s,
-        "h2d_bytes_per_step": int(12 * sysm.n_atoms * n_total), "d2h_bytes_per_step": int(8 * nbins),
+        "h2d_bytes_per_step": int(12 * sysm.n_atoms * n_total), "d2h_bytes_per_step": int(8 * nbins * handle_pairs),
         "kernel": "rdf_cells_kernel", "cells": list(st.cells), "cell_stencil": list(st.cell_stencil),
         "rank0_pair_kernel_ms_per_step": st.pair_kernel_ms / steps,
         "rank0_pair_kernel_launches_per_step": launches / steps,
@@ -525,6 +554,84 @@ def target_config_probe(args, world, rank, local_rank, dist, comm, fp32_peak):
              if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") else None),
         "parity": parity,
     }
+
+
+def cfg5_sweep_probe(args, world, rank, local_rank, dist, comm, fp32_peak):
+    """BASELINE.json configs[4]: the uniform-random ideal gas (50,000 atoms, 64 configurations:
+    8 distinct x 8) over the bins / cutoff sweep, configurations split over the ranks, in CORRECTED
+    mode (every pair counted) so that the analytic g(r) = 1 can be checked: z = (count - expected) /
+    sqrt(expected x repeats) per bin with the exact shell volumes."""
+    import torch
+    from mdsuite_b200 import _cuda, synthetic
+    n_base, repeats = 8, 8
+    n_total = n_base * repeats
+    sysm = synthetic.ideal_gas(50_000, n_base, seed=5)
+    mine = np.array_split(np.arange(n_total), world)[rank]
+    base_dev = torch.from_numpy(sysm.positions).cuda(local_rank)
+    dev = base_dev[torch.from_numpy(mine % n_base).cuda(local_rank)].contiguous() if len(mine) \
+        else base_dev[:0]
+    n, L = sysm.n_atoms, float(sysm.box[0])
+    pairs_total = sysm.pairs_per_frame(parity=False) * n_total
+    rows = []
+    for cutoff in (10.0, 49.9):
+        for nbins in (100, 1000, 5000):
+            with _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, parity=False,
+                                 device=local_rank) as handle:
+                counts_dev = counts_tensor(handle, handle.n_pairs, nbins) if dist is not None else None
+
+                def step():
+                    if dist is not None and comm is None:
+                        handle.wait()
+                    handle.reset()
+                    if len(mine):
+                        handle.submit_device(dev)
+                    if dist is not None:
+                        if comm is not None:
+                            handle.allreduce(comm)
+                        else:
+                            handle.join()
+                            dist.all_reduce(counts_dev)
+                            handle.wait()
+                    handle.join()
+
+                step()
+                if dist is not None:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                for _ in range(2):
+                    step()
+                ev1.record()
+                torch.cuda.synchronize()
+                ms = ev0.elapsed_time(ev1) / 2
+                if dist is not None:
+                    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms = float(t.item())
+                got = handle.counts()
+                st = handle.stats()
+            if rank != 0:
+                continue
+            k = np.arange(nbins)
+            dr = cutoff / nbins
+            shell = 4 * np.pi / 3 * (((k + 1) * dr) ** 3 - (k * dr) ** 3)
+            expect = n_total * n * (n - 1) / 2 * shell / L ** 3
+            ok = ((k + 1) * dr <= L / 2) & (expect > 50)
+            z = (got[0][ok].astype(np.float64) - expect[ok]) / np.sqrt(expect[ok] * repeats)
+            rows.append({"cutoff": cutoff, "nbins": nbins, "path": st.path_name,
+                         "cell_stencil": list(st.cell_stencil), "ms_per_step": ms,
+                         "allpairs_equivalent_per_s": pairs_total / (ms * 1e-3),
+                         "ideal_gas_gate": {"bins_checked": int(ok.sum()),
+                                            "max_abs_z": float(np.abs(z).max()) if ok.any() else None,
+                                            "g_mean": float(np.mean(got[0][ok] / expect[ok])) if ok.any() else None}})
+    del dev, base_dev
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"workload": "cfg5 (BASELINE.json configs[4]): 50,000-atom uniform-random ideal gas, L=100, 64 "
+                        "configurations in total (8 distinct x 8), corrected mode, bins x cutoff sweep",
+            "n_gpus": world, "frames_total": n_total, "rows": rows}
 
 
 def run_ours(args):
@@ -670,6 +777,21 @@ def run_ours(args):
             if dist is not None:
                 raise  # a rank that drops out would leave the others in the collective
             target = {"error": str(exc)}
+
+    # ---- the other multi-GPU configurations BASELINE.json names: cfg4 at full size, the cfg5 sweep
+    other = None
+    if not args.no_other_configs:
+        other = {}
+        for key, fn in (("cfg4_full", lambda: target_config_probe(args, world, rank, local_rank, dist,
+                                                                  comm, fp32_peak, name="cfg4")),
+                        ("cfg5_sweep", lambda: cfg5_sweep_probe(args, world, rank, local_rank, dist,
+                                                                comm, fp32_peak))):
+            try:
+                other[key] = fn()
+            except Exception as exc:  # noqa: BLE001
+                if dist is not None:
+                    raise
+                other[key] = {"error": str(exc)}
 
     # ---- multi-rank parity: the sharded + allreduced histogram against ONE handle on rank 0 over
     # all the frames, and the first frames against the fused-C oracle ---------------------------
@@ -821,7 +943,8 @@ def run_ours(args):
                                   f"np.array_split, 1 NCCL allreduce/step "
                                   f"({'torch.distributed' if comm is None else 'mds_rdf_allreduce(ncclComm_t)'})"
                    if world > 1 else "1 GPU"},
-        "roofline": roofline, "target_config": target, "adf_path": adf, "user_api": user_api,
+        "roofline": roofline, "target_config": target, "other_configs": other, "adf_path": adf,
+        "user_api": user_api,
         "e2e_reference_binding": binding,
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * e2e_s / args.steps,
@@ -888,6 +1011,8 @@ def main():
                     help="allreduce with torch.distributed instead of mds_rdf_allreduce(ncclComm_t)")
     ap.add_argument("--no-target-config", action="store_true",
                     help="skip the full-size north-star block (100k atoms x 10k configurations)")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the cfg4 full-size block and the cfg5 sweep")
     ap.add_argument("--target-steps", type=int, default=3,
                     help="timed steps of the full-size north-star block (at most --steps)")
     ap.add_argument("--no-binding-probe", action="store_true",
