@@ -140,3 +140,39 @@ def test_atom_selection_and_species_subset(tmp_path, monkeypatch):
         ref = want[key.replace("_", "-")]["adf"]
         got = np.array(comp[key]["adf"], dtype=np.float32)
         assert np.array_equal(np.nan_to_num(got, nan=-1.0), np.nan_to_num(ref, nan=-1.0))
+
+
+def test_molecules_true_reads_molecule_datasets(tmp_path, monkeypatch):
+    """molecules=True (reference calculators/angular_distribution_function.py:154, :234-235):
+    species are the molecule names whose <molecule>/Positions datasets a MolecularMap run left in
+    the store; same engine, the molecule table supplies the index ranges."""
+    from mdsuite_b200.database.simulation_database import (PropertyInfo, SpeciesInfo,
+                                                           TrajectoryChunkData)
+    monkeypatch.setattr(AngularDistributionFunction, "handle_factory", OracleADFHandle)
+    case = GOLDEN[1]  # O 6, H 9, C 5
+    project, exp = make_experiment(tmp_path, case)
+    pos = positions_for(case)
+    # two kinds of "molecules": OH sites (midpoints of the first six O-H pairs) and the C atoms
+    oh = (0.5 * (pos[:, 0:6] + pos[:, 6:12])).astype(np.float32)
+    c = pos[:, 15:20]
+    table = {}
+    for name, arr in (("OH", oh), ("C1", c)):
+        info = SpeciesInfo(name, arr.shape[1], [PropertyInfo("Positions", 3)])
+        exp.database.add_dataset(f"{name}/Positions", arr.shape[1], 3)
+        chunk = TrajectoryChunkData([info], arr.shape[0])
+        chunk.add_data(arr, 0, name, "Positions")
+        exp.database.add_data(chunk)
+        table[name] = {"n_particles": arr.shape[1], "mass": None, "charge": None,
+                       "properties": ["Positions"]}
+    project.database.set_species("run", table, molecule=True)
+    comp = exp.run.AngularDistributionFunction(
+        number_of_configurations=2, cutoff=4.0, start=0, number_of_bins=24, norm_power=0,
+        molecules=True, batches=1, plot=False)
+    assert comp.keys() == ["OH_OH_OH", "OH_OH_C1", "OH_C1_C1", "C1_C1_C1"]
+    frames = np.linspace(0, case["frames"] - 1, 2, dtype=int)
+    sub = np.concatenate([oh, c], axis=1)
+    want = adf_oracle.adf(sub, [6, 5], ["OH", "C1"], case["box"], 4.0, 24, 0, [list(frames)])
+    for key in comp.keys():
+        ref = want[key.replace("_", "-")]["adf"]
+        got = np.array(comp[key]["adf"], dtype=np.float32)
+        assert np.array_equal(np.nan_to_num(got, nan=-1.0), np.nan_to_num(ref, nan=-1.0))
