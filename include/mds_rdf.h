@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MDS_RDF_ABI_VERSION 5
+#define MDS_RDF_ABI_VERSION 6
 
 #if defined(MDS_BUILD) && defined(__GNUC__)
 #define MDS_API __attribute__((visibility("default")))
@@ -173,6 +173,14 @@ MDS_API int mds_rdf_wait(mds_rdf_t* h, void* stream);
 /* Block the host until every host->device copy issued by mds_rdf_submit so far has completed,
  * i.e. until the submitted host buffers may be overwritten (the kernels may still be running). */
 MDS_API int mds_rdf_wait_host_copies(mds_rdf_t* h);
+
+/* Finer than the above, for a feeder with a ring of pinned buffers: mds_rdf_host_ticket returns
+ * the number of page-locked host submits made so far (the ticket of the latest one; 0: none),
+ * mds_rdf_wait_host_ticket blocks until the copies of submit number `ticket` have left the host
+ * buffer — later submits may still be in flight, so refilling buffer k overlaps the copy of
+ * buffer k + 1. */
+MDS_API int64_t mds_rdf_host_ticket(mds_rdf_t* h);
+MDS_API int mds_rdf_wait_host_ticket(mds_rdf_t* h, int64_t ticket);
 
 /* Item sharding — strong scaling WITHIN frames, for runs with fewer configurations than GPUs
  * (SURVEY.md §8e "fallback for F < G"): every rank submits the same frames, the handle of rank

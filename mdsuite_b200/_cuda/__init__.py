@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # (make -C csrc checked; see rdf_common.cuh MDS_CHECKED)
 LIB_PATH = os.environ.get("MDS_RDF_LIB") or os.path.join(_HERE, "libmds_rdf.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MDS_OK = 0
 PARITY_SKIP_FIRST = 0x1
 PATH_ALLPAIRS = 0x2
@@ -32,7 +32,7 @@ LAYOUT_ATOM_MAJOR = 1  # (n_atoms, n_frames, 3) — the reference's positions_te
 
 EXPORTED_SYMBOLS = (
     "mds_rdf_create", "mds_rdf_destroy", "mds_rdf_submit", "mds_rdf_submit_device",
-    "mds_rdf_counts", "mds_rdf_device_counts", "mds_rdf_allreduce", "mds_rdf_join", "mds_rdf_wait", "mds_rdf_wait_host_copies", "mds_rdf_synchronize",
+    "mds_rdf_counts", "mds_rdf_device_counts", "mds_rdf_allreduce", "mds_rdf_join", "mds_rdf_wait", "mds_rdf_wait_host_copies", "mds_rdf_host_ticket", "mds_rdf_wait_host_ticket", "mds_rdf_synchronize",
     "mds_rdf_reset", "mds_rdf_set_item_shard",
     "mds_rdf_stats_get", "mds_rdf_threshold_table", "mds_rdf_build_threshold_table",
     "mds_bench_shared_atomics",
@@ -140,6 +140,9 @@ def load() -> ctypes.CDLL:
     lib.mds_rdf_join.argtypes = [vp, vp]
     lib.mds_rdf_wait.argtypes = [vp, vp]
     lib.mds_rdf_wait_host_copies.argtypes = [vp]
+    lib.mds_rdf_host_ticket.argtypes = [vp]
+    lib.mds_rdf_host_ticket.restype = ctypes.c_int64
+    lib.mds_rdf_wait_host_ticket.argtypes = [vp, ctypes.c_int64]
     lib.mds_rdf_synchronize.argtypes = [vp]
     lib.mds_rdf_reset.argtypes = [vp]
     lib.mds_rdf_set_item_shard.argtypes = [vp, ctypes.c_int32, ctypes.c_int32]
@@ -304,6 +307,15 @@ class RDFHandle:
         """Block until the host buffers passed to :meth:`submit` so far may be overwritten."""
         _check(self._lib.mds_rdf_wait_host_copies(self._h), "mds_rdf_wait_host_copies")
         self._keepalive = []
+
+    def host_ticket(self) -> int:
+        """Ticket of the latest page-locked host submit (their count so far)."""
+        return int(self._lib.mds_rdf_host_ticket(self._h))
+
+    def wait_host_ticket(self, ticket: int):
+        """Block until the copies of host submit number ``ticket`` have left its buffer (later
+        submits may still be in flight)."""
+        _check(self._lib.mds_rdf_wait_host_ticket(self._h, int(ticket)), "mds_rdf_wait_host_ticket")
 
     def synchronize(self):
         _check(self._lib.mds_rdf_synchronize(self._h), "mds_rdf_synchronize")

@@ -145,6 +145,9 @@ struct mds_rdf {
   // major) into a ring of pinned buffers by the calling thread and sent on when a buffer is full
   float* stage[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_stage_done[3] = {nullptr, nullptr, nullptr};  // H2D out of the buffer finished
+  // tickets: one event per host submit, recorded on the copy stream after its last H2D
+  cudaEvent_t ev_ticket[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t tickets = 0;  // host submits whose copies have been enqueued so far
   int stage_slot = 0;
   int64_t stage_frames = 0;     // frames waiting in stage[stage_slot]
   int64_t stage_capacity = 0;   // frames per buffer
@@ -869,6 +872,8 @@ void mds_rdf_destroy(mds_rdf_t* h) {
     if (h->ev_raw_ready[b]) cudaEventDestroy(h->ev_raw_ready[b]);
     if (h->ev_raw_free[b]) cudaEventDestroy(h->ev_raw_free[b]);
   }
+  for (int k = 0; k < 8; ++k)
+    if (h->ev_ticket[k]) cudaEventDestroy(h->ev_ticket[k]);
   for (int k = 0; k < 3; ++k) {
     if (h->stage[k]) cudaFreeHost(h->stage[k]);
     if (h->ev_stage_done[k]) cudaEventDestroy(h->ev_stage_done[k]);
@@ -981,6 +986,12 @@ static int submit_pinned(mds_rdf_t* h, const float* xyz, int64_t n_frames, int l
   }
   CUDA_TRY(cudaEventRecord(h->ev_k1, h->s_compute));
   CUDA_TRY(cudaEventRecord(h->ev_t1, h->s_compute));
+  {
+    cudaEvent_t& ev = h->ev_ticket[h->tickets % 8];
+    if (!ev) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ev, h->s_copy));  // every H2D of this submit has been enqueued
+    h->tickets += 1;
+  }
   h->timing_valid = true;
   h->frames_done += n_frames;
   return MDS_OK;
@@ -1150,6 +1161,22 @@ int mds_rdf_wait_host_copies(mds_rdf_t* h) {
     if (rc != MDS_OK) return rc;
   }
   CUDA_TRY(cudaStreamSynchronize(h->s_copy));
+  return MDS_OK;
+}
+
+int64_t mds_rdf_host_ticket(mds_rdf_t* h) { return h ? h->tickets : -1; }
+
+int mds_rdf_wait_host_ticket(mds_rdf_t* h, int64_t ticket) {
+  if (!h) return fail(MDS_ERR_INVALID, "mds_rdf_wait_host_ticket: handle is NULL");
+  DeviceGuard guard(h->device);
+  if (ticket < 1 || ticket > h->tickets)
+    return fail(MDS_ERR_INVALID, "mds_rdf_wait_host_ticket: ticket %lld not in [1, %lld]",
+                (long long)ticket, (long long)h->tickets);
+  if (h->tickets - ticket >= 8) {  // older than the event ring: wait for the stream
+    CUDA_TRY(cudaStreamSynchronize(h->s_copy));
+    return MDS_OK;
+  }
+  CUDA_TRY(cudaEventSynchronize(h->ev_ticket[(ticket - 1) % 8]));
   return MDS_OK;
 }
 

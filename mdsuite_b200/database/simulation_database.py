@@ -66,7 +66,7 @@ class TrajectoryChunkData:
         sp[property_name][config_idx:config_idx + n] = array
 
 
-_COPY_THREADS = max(1, min(8, (os.cpu_count() or 1) // 2))
+_COPY_THREADS = max(1, min(16, os.cpu_count() or 1))
 _POOL = None
 
 
@@ -185,7 +185,7 @@ class Database:
                     out[k] = mm[frames[k]][select]
 
         n_bytes = len(frames) * n_sel * mm.shape[2] * 4
-        n_jobs = min(_COPY_THREADS, len(frames), max(1, n_bytes // (4 << 20)))
+        n_jobs = min(_COPY_THREADS, len(frames), max(1, n_bytes // (2 << 20)))
         if n_jobs <= 1:
             copy_block(0, len(frames))
         else:  # NumPy releases the GIL in these copies: the threads run on separate cores

@@ -143,11 +143,17 @@ class FrameBatcher:
             starts.append((lo, min(len(frames), lo + size)))
             lo += size
             k += 1
+        tickets = [None, None]  # the submit that last read each ring buffer
         for k, (lo, hi) in enumerate(starts):
             idx = frames[lo:hi]
             buf = self._ring[k & 1]
             if k >= 2:
-                self.handle.wait_host_copies()  # the buffer's previous H2D copy has finished
+                # the buffer's previous H2D copy has finished — the copy of the OTHER buffer,
+                # submitted a moment ago, keeps running while this one is refilled
+                if tickets[k & 1] is not None and hasattr(self.handle, "wait_host_ticket"):
+                    self.handle.wait_host_ticket(tickets[k & 1])
+                else:
+                    self.handle.wait_host_copies()
             view = buf.numpy()
             off = 0
             for path, n, sel in zip(self.paths, self.n_particles, self.atom_selections):
@@ -155,6 +161,8 @@ class FrameBatcher:
                                           atom_selection=sel)
                 off += n
             self.handle.submit(buf[:len(idx)], pinned=self.pinned)
+            if self.pinned and hasattr(self.handle, "host_ticket"):
+                tickets[k & 1] = self.handle.host_ticket()
             self.frames_submitted += len(idx)
             self.bytes_staged += len(idx) * off * 12
             yield self.frames_submitted
