@@ -308,3 +308,45 @@ def test_item_shards_add_up_to_the_full_histogram(path):
     with _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box, path=path) as h:
         with pytest.raises(_cuda.MdsCudaError, match="shard 3 of 3"):
             h.set_item_shard(3, 3)
+
+
+def test_host_submit_paths_agree_and_reuse_their_buffers():
+    """The three ways host frames reach the device give the oracle's histogram: page-locked memory
+    (copied straight out of the caller's buffer), pageable memory one configuration per call (the
+    reference's batching: coalesced in the library's pinned ring) and pageable (N, C, 3) blocks (sent
+    as they are).  A pageable buffer may be overwritten as soon as the call returns; reset discards
+    frames that are still waiting in the ring; tickets order the reuse of pinned buffers."""
+    import torch
+    sysm = synthetic.nacl_melt(3, 23, seed=77)  # 216 atoms, 23 frames
+    cutoff, nbins = 8.0, 160
+    want, _ = oracle_counts(sysm.positions, sysm.counts, sysm.box, cutoff, nbins)
+    with _cuda.RDFHandle(sysm.counts, nbins, cutoff, sysm.box) as h:
+        # pageable, one configuration per call, the SAME array reused for every call
+        scratch = np.empty((sysm.n_atoms, 1, 3), dtype=np.float32)
+        for f in range(sysm.n_frames):
+            scratch[:, 0, :] = sysm.positions[f]
+            h.submit(scratch, _cuda.LAYOUT_ATOM_MAJOR)
+            scratch[...] = np.nan  # the library has its own copy by now
+        assert_same(h.counts(), want)
+        # reset drops what is still waiting in the ring
+        h.reset()
+        h.submit(sysm.positions[:5])
+        h.reset()
+        h.submit(np.ascontiguousarray(sysm.positions.transpose(1, 0, 2)), _cuda.LAYOUT_ATOM_MAJOR)
+        assert_same(h.counts(), want)
+        # page-locked ring of two buffers, refilled under tickets
+        h.reset()
+        ring = [torch.empty((4, sysm.n_atoms, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        tickets = [None, None]
+        assert h.host_ticket() >= 0
+        for k, f0 in enumerate(range(0, sysm.n_frames, 4)):
+            n = min(4, sysm.n_frames - f0)
+            if tickets[k & 1] is not None:
+                h.wait_host_ticket(tickets[k & 1])
+            ring[k & 1][:n] = torch.from_numpy(sysm.positions[f0:f0 + n])
+            h.submit(ring[k & 1][:n], pinned=True)
+            tickets[k & 1] = h.host_ticket()
+        assert tickets[0] != tickets[1]
+        assert_same(h.counts(), want)
+        with pytest.raises(_cuda.MdsCudaError, match="ticket"):
+            h.wait_host_ticket(h.host_ticket() + 1)
