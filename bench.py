@@ -92,6 +92,16 @@ def make_workload(name: str, frames: int):
     return sysm, cutoff, nbins, desc
 
 
+def workload_config(desc, n_total, n_atoms, nbins, cutoff, n_pairs):
+    """The `config` object of a bench line: what the workload IS, identical for both arms and for
+    every N (how a run lays it out over GPUs is in `run_layout`)."""
+    return {"workload": desc, "frames_total": int(n_total), "atoms": int(n_atoms), "nbins": int(nbins),
+            "cutoff": float(cutoff), "species_pairs": int(n_pairs),
+            "l2": f"inputs larger than L2: {12 * n_atoms * n_total / 1e6:.0f} MB raw xyz + "
+                  f"{12 * n_atoms * n_total / 1e6:.0f} MB packed per step vs 126 MB L2 (no flush "
+                  f"between steps; a rank of an N-GPU run holds 1/N of it, see run_layout)"}
+
+
 # ----------------------------------------------------------------------------------------------
 # nvidia-smi clock sampler (B200_PROFILING.md "clocks DURING the timed region")
 # ----------------------------------------------------------------------------------------------
@@ -154,6 +164,45 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
                 "power_w_max": max(power) if power else None, "samples": len(sm),
                 "reasons": sorted(reasons)}
+
+
+L2_BYTES = 126e6  # B200
+
+
+class TimedSteps:
+    """K steps timed on the device.  If a step's inputs are larger than L2 the K steps are one
+    CUDA-event interval; otherwise L2 is flushed (a 256 MB write) before every step and the steps
+    are timed one by one, the flushes outside the intervals (timing rules of the bench contract)."""
+
+    def __init__(self, device, bytes_per_step: float):
+        import torch
+        self.torch = torch
+        self.flush = bytes_per_step < 1.5 * L2_BYTES
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=device) if self.flush else None
+        self.note = ("L2 flushed (256 MB write) before every timed step, steps timed one by one"
+                     if self.flush else "inputs of a step larger than L2, no flush")
+
+    def run(self, step, k: int) -> float:
+        """Milliseconds of k calls of step() on torch's current stream."""
+        torch = self.torch
+        if not self.flush:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(k):
+                step()
+            ev1.record()
+            torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1)
+        events = []
+        for _ in range(k):
+            self.buf.zero_()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            step()
+            ev1.record()
+            events.append((ev0, ev1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in events)
 
 
 def counts_tensor(handle, n_pairs: int, nbins: int):
@@ -230,11 +279,11 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": desc, "frames_total": args.frames, "atoms": sysm.n_atoms,
-                   "nbins": nbins, "cutoff": cutoff,
-                   "species_pairs": len(sysm.counts) * (len(sysm.counts) + 1) // 2,
-                   "sample": f"each step times {per_step} configuration(s) of the workload; the "
-                             f"rate is per pair evaluation, so it does not depend on the count"},
+        "config": workload_config(desc, args.frames, sysm.n_atoms, nbins, cutoff,
+                                  len(sysm.counts) * (len(sysm.counts) + 1) // 2),
+        "run_layout": {"sample": f"each step times {per_step} configuration(s) of the workload on "
+                                 f"the host cores; the rate is per pair evaluation, so it does not "
+                                 f"depend on the count"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -459,19 +508,21 @@ def target_config_probe(args, world, rank, local_rank, dist, comm, fp32_peak, na
         collective()
         return handle.counts()
 
+    timer = TimedSteps(torch.device("cuda", local_rank), 24.0 * sysm.n_atoms * len(mine))
+
     def timed(fn):
         fn()
         handle.stats()
         barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        box = {}
+
+        def one():
+            box["out"] = fn()
         t0 = time.perf_counter()
-        ev0.record()
-        for _ in range(steps):
-            out = fn()
-        ev1.record()
+        ms = timer.run(one, steps)
         barrier()
         wall = time.perf_counter() - t0
-        ms = ev0.elapsed_time(ev1)
+        out = box.get("out")
         if dist is not None:
             t = torch.tensor([ms, wall], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -572,6 +623,7 @@ def cfg5_sweep_probe(args, world, rank, local_rank, dist, comm, fp32_peak):
         else base_dev[:0]
     n, L = sysm.n_atoms, float(sysm.box[0])
     pairs_total = sysm.pairs_per_frame(parity=False) * n_total
+    timer = TimedSteps(torch.device("cuda", local_rank), 24.0 * n * len(mine))  # 38 MB at N = 1
     rows = []
     for cutoff in (10.0, 49.9):
         for nbins in (100, 1000, 5000):
@@ -598,13 +650,7 @@ def cfg5_sweep_probe(args, world, rank, local_rank, dist, comm, fp32_peak):
                 if dist is not None:
                     dist.barrier()
                 torch.cuda.synchronize()
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
-                for _ in range(2):
-                    step()
-                ev1.record()
-                torch.cuda.synchronize()
-                ms = ev0.elapsed_time(ev1) / 2
+                ms = timer.run(step, 2) / 2
                 if dist is not None:
                     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
                     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -631,7 +677,7 @@ def cfg5_sweep_probe(args, world, rank, local_rank, dist, comm, fp32_peak):
         return None
     return {"workload": "cfg5 (BASELINE.json configs[4]): 50,000-atom uniform-random ideal gas, L=100, 64 "
                         "configurations in total (8 distinct x 8), corrected mode, bins x cutoff sweep",
-            "n_gpus": world, "frames_total": n_total, "rows": rows}
+            "n_gpus": world, "frames_total": n_total, "l2": timer.note, "rows": rows}
 
 
 def run_ours(args):
@@ -729,15 +775,13 @@ def run_ours(args):
         while sampler.proc is not None and not sampler.rows and time.perf_counter() - t_wait < 5.0:
             time.sleep(0.05)  # nvidia-smi takes a moment to print its first sample
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # raw + packed frames of this rank per step against L2 (strong scaling: from N = 4 on a rank's
+    # share of cfg2 would fit)
+    timer = TimedSteps(torch.device("cuda", local_rank), 24.0 * n_atoms * n_frames)
     t_wall0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        step_resident()
-    ev1.record()
+    ms = timer.run(step_resident, args.steps)
     barrier()
     t_wall1 = time.perf_counter()
-    ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     st = handle.stats()
     result = handle.counts()
@@ -933,16 +977,13 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "frames_total": n_total, "frames_rank0": n_frames,
-                   "atoms": n_atoms, "nbins": nbins,
-                   "cutoff": cutoff, "species_pairs": n_pairs,
-                   "l2": f"inputs larger than L2 at N=1: {12 * n_atoms * n_total / 1e6:.0f} MB raw xyz + "
-                         f"{12 * n_atoms * n_total / 1e6:.0f} MB packed per step vs 126 MB L2 "
-                         f"(rank 0 here: {12 * n_atoms * n_frames / 1e6:.0f} MB raw)",
-                   "parallelism": f"the {n_total} configurations split over {world} GPU(s) with "
-                                  f"np.array_split, 1 NCCL allreduce/step "
-                                  f"({'torch.distributed' if comm is None else 'mds_rdf_allreduce(ncclComm_t)'})"
-                   if world > 1 else "1 GPU"},
+        "config": workload_config(desc, n_total, n_atoms, nbins, cutoff, n_pairs),
+        "run_layout": {"frames_rank0": n_frames, "raw_mb_rank0": 12 * n_atoms * n_frames / 1e6,
+                       "l2": timer.note,
+                       "parallelism": f"the {n_total} configurations split over {world} GPU(s) with "
+                                      f"np.array_split, 1 NCCL allreduce/step "
+                                      f"({'torch.distributed' if comm is None else 'mds_rdf_allreduce(ncclComm_t)'})"
+                       if world > 1 else "1 GPU"},
         "roofline": roofline, "target_config": target, "other_configs": other, "adf_path": adf,
         "user_api": user_api,
         "e2e_reference_binding": binding,
