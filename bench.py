@@ -97,9 +97,10 @@ def workload_config(desc, n_total, n_atoms, nbins, cutoff, n_pairs):
     every N (how a run lays it out over GPUs is in `run_layout`)."""
     return {"workload": desc, "frames_total": int(n_total), "atoms": int(n_atoms), "nbins": int(nbins),
             "cutoff": float(cutoff), "species_pairs": int(n_pairs),
-            "l2": f"inputs larger than L2: {12 * n_atoms * n_total / 1e6:.0f} MB raw xyz + "
-                  f"{12 * n_atoms * n_total / 1e6:.0f} MB packed per step vs 126 MB L2 (no flush "
-                  f"between steps; a rank of an N-GPU run holds 1/N of it, see run_layout)"}
+            "l2": f"a step reads {12 * n_atoms * n_total / 1e6:.0f} MB raw xyz + as much packed, "
+                  f"split over the ranks; a rank whose share (raw + packed) is above 1.5 x 126 MB L2 runs its steps "
+                  f"back to back, a rank below it flushes L2 (256 MB write, outside the timed "
+                  f"intervals) before every timed step - which one this run did is in run_layout.l2"}
 
 
 # ----------------------------------------------------------------------------------------------

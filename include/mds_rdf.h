@@ -108,7 +108,8 @@ typedef struct mds_rdf_stats {
   int32_t item_shards;         /* shard count set with mds_rdf_set_item_shard (1: none) */
   int32_t cell_stencil[3];     /* cell path: stencil half-widths — the cell kernel tests atoms whose
                                   cells are at most this many cells apart (1 or 2 per dimension) */
-  int32_t reserved0;
+  int32_t cell_build;          /* cell path, last batch: 1 = lists built by the one-kernel build (a CTA
+                                  per frame, counters in shared memory), 0 = pack / scan / scatter */
   double pairs_tested;         /* distances actually computed: = pairs_evaluated on the all-pairs
                                   path; on the cell path the kernel works on 64-atom chunks and tests
                                   a superset of the candidate pairs (cell kernel launches only) */

@@ -81,7 +81,7 @@ class _Stats(ctypes.Structure):
         ("cells", ctypes.c_int32 * 3),
         ("item_shards", ctypes.c_int32),
         ("cell_stencil", ctypes.c_int32 * 3),
-        ("reserved0", ctypes.c_int32),
+        ("cell_build", ctypes.c_int32),
         ("pairs_tested", ctypes.c_double),
     ]
 
@@ -109,6 +109,7 @@ class RDFStats:
     item_shards: int = 1
     cell_stencil: tuple = (0, 0, 0)
     pairs_tested: float = 0.0
+    cell_build: int = 0  # cell path: 1 = the last batch's lists came from the one-kernel build
 
     @property
     def path_name(self) -> str:
@@ -361,7 +362,8 @@ class RDFHandle:
                         st.pairs_binned, st.frames_general_minimage, st.kernel_launches,
                         st.kernel_ms, st.submit_ms, st.n_pairs, st.nbins, st.sm_count, st.variant,
                         st.pair_kernel_ms, st.pair_kernel_launches, st.dense, st.frames_far,
-                        tuple(st.cells), st.item_shards, tuple(st.cell_stencil), st.pairs_tested)
+                        tuple(st.cells), st.item_shards, tuple(st.cell_stencil), st.pairs_tested,
+                        st.cell_build)
 
     def threshold_table(self):
         """(edges[0..nbins] float32, s_cut): the squared-distance thresholds the kernels use."""

@@ -130,6 +130,9 @@ struct mds_rdf {
   int work_slot = 0;
   float* d_packed[2] = {nullptr, nullptr};   // quad-block positions, 12 B per slot
   uint32_t* d_rank[2] = {nullptr, nullptr};  // cell-list path: rank of each atom in its cell
+  bool build_fused = true;   // MDS_RDF_CELL_BUILD=split: always pack / scan / scatter
+  bool lazy_pack = true;     // MDS_RDF_CELL_BUILD=eager: the one-kernel build writes the quad blocks too
+  int built_fused = 0;       // the last batch went through the one-kernel build
   uint32_t* d_flags[2] = {nullptr, nullptr};
   float* d_raw[2] = {nullptr, nullptr};  // staging for host submits (lazy)
   // cell-list path only
@@ -382,6 +385,8 @@ mds::PackParams pack_params(mds_rdf* h, const float* d_xyz, int layout, int64_t 
   pp.cell_off = nullptr;
   pp.off_stride = 0;
   pp.rank = nullptr;
+  pp.gate = nullptr;
+  pp.need_bits = 0;
   pp.grid = h->grid;
   if (h->path == MDS_RDF_PATH_CELLLIST && h->shard_count > 1 && (uint32_t)h->grid.nz >= h->shard_count) {
     // only the handle's slab of z layers and the layers its stencil reaches are sorted
@@ -434,11 +439,26 @@ int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t fram
                         int64_t n_frames, int64_t n_frames_total, int buf) {
   CUDA_TRY(cudaMemsetAsync(h->d_flags[buf], 0, sizeof(uint32_t) * (size_t)n_frames, h->s_compute));
   const mds::PackParams pp = pack_params(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf);
+  const bool one_kernel = h->build_fused &&
+                          mds::cells_build_fused(layout, h->n_species * h->grid.nc);
+  const bool lazy_pack = one_kernel && h->lazy_pack;
   CUDA_TRY(mds::launch_cell_build(pp, h->n_species, h->d_sorted[buf], h->crowded_limit, h->d_scan_tmp,
-                                  h->sm_count, h->s_compute));
+                                  h->sm_count, h->build_fused, !lazy_pack, h->s_compute));
   CUDA_TRY(mds::launch_count_general(h->d_flags[buf], (int)n_frames, h->d_general,
                                      h->d_batch_far + buf, h->s_compute));
-  h->launches += 4;
+  h->built_fused = one_kernel ? 1 : 0;
+  h->launches += one_kernel ? 2 : 4;
+  if (lazy_pack && !h->items.empty()) {
+    // the frames the all-pairs kernel will take (flagged MDS_FRAME_FAR; normally none, and then
+    // this launch returns at once) get their quad-block copy now
+    mds::PackParams far = pp;
+    far.cell_off = nullptr;
+    far.rank = nullptr;
+    far.gate = h->d_batch_far + buf;
+    far.need_bits = mds::MDS_FRAME_FAR;
+    CUDA_TRY(mds::launch_pack(far, h->sm_count, h->s_compute));
+    h->launches += 1;
+  }
   if (h->n_real == 0) return MDS_OK;
   for (int p0 = 0; p0 < h->n_pairs; p0 += h->pair_group) {
     const int pc = std::min(h->pair_group, h->n_pairs - p0);
@@ -684,6 +704,10 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
         const int v = atoi(env);
         if (v >= 256 && v <= mds::cells_max_cap()) h->cap_atoms = v;
       }
+      if (const char* env = getenv("MDS_RDF_CELL_BUILD")) {
+        h->build_fused = strcmp(env, "split") != 0;
+        h->lazy_pack = strcmp(env, "eager") != 0;
+      }
       // one row cell (+ its kx own-pencil neighbours) against one neighbour pencil must fit
       h->crowded_limit = (uint32_t)(h->cap_atoms / (3 * K[0] + 2));
     }
@@ -731,6 +755,14 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
     // 128 MB of internal buffers per batch; 512 MB on the cell path, whose pair kernel spreads
     // (frame, pencil) items over persistent CTAs and loses ~3 % to ramp and tail on short batches
     bf = (int)std::min<int64_t>(4096, std::max<int64_t>(1, ((cells ? 512LL : 128LL) << 20) / per_frame));
+    if (cells && h->build_fused) {
+      // the one-kernel build takes a frame per CTA: a batch is a whole number of its waves (1 GB of
+      // buffers at most), so that no SM is left with one more frame than the others
+      const int wave = mds::cells_build_frames_per_wave(MDS_LAYOUT_FRAME_MAJOR_XYZ,
+                                                        h->n_species * h->grid.nc, h->sm_count);
+      const int64_t most = std::min<int64_t>(4096, (1024LL << 20) / per_frame);
+      if (wave > 0 && most >= wave) bf = (int)(most / wave * wave);
+    }
   }
   h->batch_frames = bf;
   build_items(h, mds::allpairs_variant_tile(h->variant), bf);
@@ -1294,6 +1326,7 @@ int mds_rdf_stats_get(mds_rdf_t* h, mds_rdf_stats* out) {
   out->cells[1] = h->grid.ny;
   out->cells[2] = h->grid.nz;
   for (int k = 0; k < 3; ++k) out->cell_stencil[k] = h->kcell[k];
+  out->cell_build = h->built_fused;
   out->item_shards = (int32_t)h->shard_count;
   return MDS_OK;
 }

@@ -183,6 +183,210 @@ __global__ void __launch_bounds__(256) rdf_cell_scatter_kernel(const PackParams 
   }
 }
 
+// ---- the whole build of a frame in one CTA ---------------------------------------------------
+//
+// The three kernels above move every atom through global memory three times (pack: raw ->
+// quad blocks + rank, one global atomic per atom; scatter: quad blocks + rank -> sorted) and are
+// bound by the global atomics, not by HBM.  When the key table of a frame fits in shared memory
+// and the input is frame-major (a frame's atoms are contiguous), one CTA does all of it for one
+// frame: count into a shared-memory table (ATOMS.POPC.INC), scan the table in place, write the
+// offsets, then read the frame a second time and place every atom with a returning shared atomic
+// on the running offsets — no rank array, no global atomics except the frame's flag word.
+// Order inside a cell is arbitrary, as it was (the histogram is a sum over pairs).
+// The quad-block copy of the frame is only needed by the all-pairs kernel, for frames flagged
+// MDS_FRAME_FAR: normally (PACKED = false) the kernel does not write it, pass 2 reads the raw frame
+// again, and the caller packs the flagged frames of a batch afterwards (launch_pack with a gate).
+#ifndef MDS_BUILD_THREADS
+#define MDS_BUILD_THREADS 1024
+#endif
+#ifndef MDS_BUILD_MINB
+#define MDS_BUILD_MINB 1
+#endif
+#ifndef MDS_BUILD_UNROLL
+#define MDS_BUILD_UNROLL 4
+#endif
+constexpr int BUILD_THREADS = MDS_BUILD_THREADS;  // a multiple of 128
+constexpr int BUILD_MAX_KEYS = 48 * 1024;  // 192 KB of counters
+
+constexpr int BUILD_UNROLL = MDS_BUILD_UNROLL;  // atoms per thread whose loads are in flight together
+
+// One CTA works on one frame, so the time of a batch is the time of a thread's loop: the loads of
+// BUILD_UNROLL atoms (slots q0 + u * BUILD_THREADS) are issued back to back, branch-free, and the
+// per-atom instruction count is kept down — the frame classification is taken from per-thread
+// minima / maxima instead of eight comparisons per atom, and pass 2 reads the key pass 1 computed
+// (three IEEE divisions per atom) instead of computing it again.
+template <bool PACKED>  // PACKED: also write the quad-block copy of the frame (see above)
+__global__ void __launch_bounds__(BUILD_THREADS, MDS_BUILD_MINB) rdf_cell_build_kernel(const PackParams p,
+                                                                          float4* __restrict__ sorted,
+                                                                          int n_keys,
+                                                                          uint32_t crowded_limit) {
+  extern __shared__ uint32_t s_key[];  // [n_keys] counts, then running offsets; [n_keys]: sink
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t chunk_total, s_bits, s_max;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float nan = __int_as_float(0x7fc00000);
+  const float inf = __int_as_float(0x7f800000);
+  const bool one_species = n_keys == p.grid.nc;
+  for (long long f = blockIdx.x; f < p.n_frames; f += gridDim.x) {
+    for (int i = threadIdx.x; i < n_keys; i += BUILD_THREADS) s_key[i] = 0u;
+    if (threadIdx.x == 0) { s_bits = 0u; s_max = 0u; }
+    __syncthreads();
+    const float* src_f = p.xyz + (p.frame0 + f) * p.n_atoms * 3;
+    float* out_f = p.out + f * p.frame_stride * 3;
+    int* key_f = reinterpret_cast<int*>(p.rank) + f * p.frame_stride;  // key of every slot, -1: none
+
+    // pass 1: quad-block copy, frame classification, keys and counts
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};  // fminf / fmaxf skip NaN
+    for (int q0 = threadIdx.x; q0 < p.n_packed; q0 += BUILD_UNROLL * BUILD_THREADS) {
+      int idx[BUILD_UNROLL];  // raw atom index, -1: padding slot, -2: beyond the end of the frame
+      float x[BUILD_UNROLL], y[BUILD_UNROLL], z[BUILD_UNROLL];
+#pragma unroll
+      for (int u = 0; u < BUILD_UNROLL; ++u) {
+        const int q = q0 + u * BUILD_THREADS;
+        idx[u] = (q < p.n_packed) ? __ldg(p.src_index + q) : -2;
+      }
+#pragma unroll
+      for (int u = 0; u < BUILD_UNROLL; ++u) {
+        const float* src = src_f + max(idx[u], 0) * 3;
+        x[u] = __ldg(src); y[u] = __ldg(src + 1); z[u] = __ldg(src + 2);
+      }
+      // (BUILD_THREADS is a multiple of 4: slot q0 + u * BUILD_THREADS sits 3 * u * BUILD_THREADS
+      // floats after slot q0 in the quad-block array)
+      float* dst0 = out_f + ((q0 & ~3) * 3 + (q0 & 3));
+      int* key0 = key_f + q0;
+#pragma unroll
+      for (int u = 0; u < BUILD_UNROLL; ++u) {
+        if (idx[u] == -2) continue;
+        float* dst = dst0 + u * (3 * BUILD_THREADS);
+        if (idx[u] < 0) {  // padding slot at the end of a species segment
+          if (PACKED) { dst[0] = nan; dst[4] = nan; dst[8] = nan; }
+          key0[u * BUILD_THREADS] = -1;
+          continue;
+        }
+        if (PACKED) { dst[0] = x[u]; dst[4] = y[u]; dst[8] = z[u]; }
+        lo[0] = fminf(lo[0], x[u]); hi[0] = fmaxf(hi[0], x[u]);
+        lo[1] = fminf(lo[1], y[u]); hi[1] = fmaxf(hi[1], y[u]);
+        lo[2] = fminf(lo[2], z[u]); hi[2] = fmaxf(hi[2], z[u]);
+        const int cell = cell_of(x[u], y[u], z[u], p.grid);
+        // (item shards: atoms outside this handle's slab of z layers are not part of its lists)
+        int key = -1;
+        if (cell_in_slab(cell, p.grid)) {
+          key = one_species ? cell : __ldg(p.species + q0 + u * BUILD_THREADS) * p.grid.nc + cell;
+          atomicAdd(&s_key[key], 1u);
+        }
+        key0[u * BUILD_THREADS] = key;
+      }
+    }
+    // the flags rdf_pack_kernel derives atom by atom (window_bits, MDS_FRAME_FAR), from the extrema:
+    // "some coordinate below a" is "the minimum is below a", and NaN coordinates set no bit there
+    uint32_t bits = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float box = p.box[d];  // (a thread without atoms keeps lo = +inf, hi = -inf: no bit)
+      if (lo[d] < -0.125f * box || hi[d] > 1.125f * box) bits |= MDS_FRAME_OUT_A;
+      if (lo[d] < -0.625f * box || hi[d] > 0.625f * box) bits |= MDS_FRAME_OUT_B;
+      if (lo[d] < -(8.0f * box) || hi[d] > 8.0f * box) bits |= MDS_FRAME_FAR;
+    }
+    bits = __reduce_or_sync(0xffffffffu, bits);
+    if (lane == 0 && bits) atomicOr(&s_bits, bits);
+    __syncthreads();
+
+    // exclusive scan of the table in place; the offsets also go to global memory for the pair kernel
+    uint32_t* off_f = p.cell_off + f * p.off_stride;
+    uint32_t carry = 0, mx = 0;
+    for (int base = 0; base < n_keys; base += 4 * BUILD_THREADS) {
+      const int i0 = base + threadIdx.x * 4;
+      uint32_t v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[k] = (i0 + k < n_keys) ? s_key[i0 + k] : 0u;
+        mx = max(mx, v[k]);
+      }
+      const uint32_t t = v[0] + v[1] + v[2] + v[3];
+      uint32_t inc = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      if (lane == 31) warp_sums[warp] = inc;
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t w = lane < BUILD_THREADS / 32 ? warp_sums[lane] : 0u;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+          if (lane >= o) winc += n;
+        }
+        warp_sums[lane] = winc - w;
+        if (lane == 31) chunk_total = winc;
+      }
+      __syncthreads();
+      uint32_t e = carry + warp_sums[warp] + inc - t;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (i0 + k < n_keys) {
+          s_key[i0 + k] = e;
+          off_f[i0 + k] = e;
+        }
+        e += v[k];
+      }
+      carry += chunk_total;
+      __syncthreads();
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0 && mx > crowded_limit) atomicMax(&s_max, mx);
+    __syncthreads();  // (also: this CTA's quad-block copy and keys are visible to all its threads)
+    if (threadIdx.x == 0) {
+      off_f[n_keys] = carry;
+      const uint32_t flags = s_bits | (s_max > crowded_limit ? MDS_FRAME_FAR : 0u);
+      if (flags) atomicOr(p.frame_flags + f, flags);
+    }
+
+    // pass 2: place the atoms — key and coordinates of a slot as pass 1 left them, the position
+    // from the running offset of the key
+    float4* sorted_f = sorted + f * p.frame_stride;
+    for (int q0 = threadIdx.x; q0 < p.n_packed; q0 += BUILD_UNROLL * BUILD_THREADS) {
+      int key[BUILD_UNROLL];
+      float x[BUILD_UNROLL], y[BUILD_UNROLL], z[BUILD_UNROLL];
+      if (PACKED) {
+        const float* src0 = out_f + ((q0 & ~3) * 3 + (q0 & 3));
+#pragma unroll
+        for (int u = 0; u < BUILD_UNROLL; ++u) {
+          const bool in = q0 + u * BUILD_THREADS < p.n_packed;
+          key[u] = in ? key_f[q0 + u * BUILD_THREADS] : -1;
+          const float* src = in ? src0 + u * (3 * BUILD_THREADS) : src0;
+          x[u] = src[0]; y[u] = src[4]; z[u] = src[8];
+        }
+      } else {
+        int idx[BUILD_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BUILD_UNROLL; ++u) {
+          const bool in = q0 + u * BUILD_THREADS < p.n_packed;
+          key[u] = in ? key_f[q0 + u * BUILD_THREADS] : -1;
+          idx[u] = in ? __ldg(p.src_index + q0 + u * BUILD_THREADS) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < BUILD_UNROLL; ++u) {
+          const float* src = src_f + max(idx[u], 0) * 3;
+          x[u] = __ldg(src); y[u] = __ldg(src + 1); z[u] = __ldg(src + 2);
+        }
+      }
+      // the returning atomics of the unrolled slots are issued together, then the stores
+      uint32_t pos[BUILD_UNROLL];
+#pragma unroll
+      for (int u = 0; u < BUILD_UNROLL; ++u)
+        pos[u] = atomicAdd(&s_key[key[u] >= 0 ? key[u] : n_keys], key[u] >= 0 ? 1u : 0u);
+#pragma unroll
+      for (int u = 0; u < BUILD_UNROLL; ++u)
+        if (key[u] >= 0)
+          sorted_f[pos[u]] = make_float4(x[u], y[u], z[u], __int_as_float(q0 + u * BUILD_THREADS));
+    }
+    __syncthreads();  // the table is zeroed again for the next frame
+  }
+}
+
 // ---- the pair kernel -------------------------------------------------------------------------
 //
 // Geometry.  Cells are at least 1.001 cutoff / K wide (K = kx, ky, kz per dimension), so the
@@ -732,18 +936,50 @@ size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem, int cap_atom
   return b;
 }
 
+bool cells_build_fused(int layout, int n_keys) {
+  return layout == MDS_LAYOUT_FRAME_MAJOR_XYZ && n_keys <= BUILD_MAX_KEYS;
+}
+
+// frames the one-kernel build works on at a time: its resident CTAs on the device (0: not eligible)
+int cells_build_frames_per_wave(int layout, int n_keys, int sm_count) {
+  if (!cells_build_fused(layout, n_keys)) return 0;
+  const size_t smem = ((size_t)n_keys + 1) * sizeof(uint32_t);
+  auto kern = rdf_cell_build_kernel<false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return 0;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BUILD_THREADS, smem) != cudaSuccess)
+    return 0;
+  return per_sm * sm_count;
+}
+
 cudaError_t launch_cell_build(const PackParams& pp, int n_species, float4* sorted,
                               uint32_t crowded_limit, uint32_t* scan_tmp, int sm_count,
-                              cudaStream_t stream) {
+                              bool allow_fused, bool write_packed, cudaStream_t stream) {
   const long long total = (long long)pp.n_frames * pp.n_packed;
   if (total <= 0) return cudaSuccess;
+  const int n_keys = n_species * pp.grid.nc;
+  if (allow_fused && cells_build_fused(pp.layout, n_keys)) {
+    // one CTA per frame, persistent: counts and running offsets live in shared memory
+    const size_t smem = ((size_t)n_keys + 1) * sizeof(uint32_t);
+    auto kern = write_packed ? rdf_cell_build_kernel<true> : rdf_cell_build_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BUILD_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    long long grid = (long long)per_sm * sm_count;
+    if (grid > pp.n_frames) grid = pp.n_frames;
+    kern<<<(unsigned)grid, BUILD_THREADS, smem, stream>>>(pp, sorted, n_keys, crowded_limit);
+    return cudaGetLastError();
+  }
   cudaError_t e = cudaMemsetAsync(pp.cell_off, 0,
                                   sizeof(uint32_t) * (size_t)pp.off_stride * (size_t)pp.n_frames,
                                   stream);
   if (e != cudaSuccess) return e;
   e = launch_pack(pp, sm_count, stream);  // quad-block positions + per-cell counts and ranks + frame flags
   if (e != cudaSuccess) return e;
-  const int n_keys = n_species * pp.grid.nc;
   const int n_blocks = (n_keys + 4095) / 4096;
   if (n_blocks <= 2 || !scan_tmp) {
     rdf_cell_scan_kernel<<<(unsigned)pp.n_frames, 1024, 0, stream>>>(

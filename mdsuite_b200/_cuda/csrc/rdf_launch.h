@@ -51,6 +51,10 @@ struct PackParams {
   CellGrid grid;
   uint32_t* frame_flags;   // [n_frames], zeroed by the kernel's caller
   float box[3];
+  // pack only what a fallback needs: nothing if *gate == 0, else the frames whose flags have one
+  // of need_bits (nullptr / 0: every frame)
+  const unsigned long long* gate;
+  uint32_t need_bits;
 };
 cudaError_t launch_pack(const PackParams& p, int sm_count, cudaStream_t stream);
 // out[0] += frames on the general minimum-image path, out[1] += frames flagged MDS_FRAME_FAR,
@@ -100,9 +104,15 @@ int cells_max_entries();  // (x cell, neighbour pencil) entries of a staged segm
 // scan_tmp: cells_scan_tmp_words(frames per batch, keys) zeroed uint32 words (nullptr: one CTA
 // scans a frame's keys on its own)
 size_t cells_scan_tmp_words(int n_frames, int n_keys);
+// allow_fused: frame-major input whose key table fits in shared memory (cells_build_fused) is
+// built by ONE kernel, a CTA per frame; otherwise (and when false) pack / scan / scatter.
+// write_packed = false (one-kernel build only): pp.out is left alone — the caller packs the frames
+// that need the all-pairs kernel afterwards (launch_pack with gate / need_bits)
+bool cells_build_fused(int layout, int n_keys);
+int cells_build_frames_per_wave(int layout, int n_keys, int sm_count);
 cudaError_t launch_cell_build(const PackParams& pp, int n_species, float4* sorted,
                               uint32_t crowded_limit, uint32_t* scan_tmp, int sm_count,
-                              cudaStream_t stream);
+                              bool allow_fused, bool write_packed, cudaStream_t stream);
 cudaError_t launch_cells(const CellsParams& p, int sm_count, cudaStream_t stream, int* grid_out);
 
 // ---- microbench.cu ----

@@ -26,11 +26,13 @@ __global__ void __launch_bounds__(256, 8) rdf_pack_kernel(const PackParams p) {
   const long long inner_n = atom_major ? p.n_frames : (long long)p.n_packed;
   const long long outer_n = atom_major ? (long long)p.n_packed : p.n_frames;
   const int lane = threadIdx.x & 31;
+  if (p.gate && *p.gate == 0ull) return;  // no frame of this batch needs the copy
   for (long long outer = blockIdx.y; outer < outer_n; outer += gridDim.y) {
     for (long long inner = (long long)blockIdx.x * blockDim.x + threadIdx.x; inner < inner_n;
          inner += (long long)gridDim.x * blockDim.x) {
       const long long f = atom_major ? inner : outer;
       const long long q = atom_major ? outer : inner;
+      if (p.need_bits && !(p.frame_flags[f] & p.need_bits)) continue;
       float* dst = p.out + (f * p.frame_stride + (q & ~3LL)) * 3 + (q & 3);
       const long long a = p.src_index[q];
       if (a < 0) {  // padding slot at the end of a species segment: never inside the cutoff

@@ -8,6 +8,8 @@ so one frame of cfg3 goes against the oracle and the large cases are checked thr
 size-independent property: the cell-list kernel and the (independently written, oracle-checked)
 all-pairs kernel must produce identical histograms.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -17,13 +19,21 @@ from oracle import c_oracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["1", "2", "2,1,2", "4,1,1"], ids=["K1", "K2", "K212", "K411"])
+@pytest.fixture(params=["1", "2", "2,1,2", "4,1,1", "1|split", "2,1,2|split", "4,1,1|eager"],
+                ids=["K1", "K2", "K212", "K411", "K1-split-build", "K212-split-build",
+                     "K411-eager-pack"])
 def cell_k(request, monkeypatch):
     """Stencil half-widths of the cell kernel (cells per cutoff length), forced through the
     library's tuning variable so that every case runs on the classical grid, on the half-width
-    grid and on a mixed one."""
-    monkeypatch.setenv("MDS_RDF_CELL_K", request.param)
-    k = [int(v) for v in request.param.split(",")]
+    grid and on a mixed one; "split-build": the lists come from pack / scan / scatter instead of
+    the one-kernel build (which frame-major input with a small key table gets by default);
+    "eager-pack": the one-kernel build also writes the all-pairs kernel's copy of every frame
+    (default: only flagged frames are packed, afterwards)."""
+    spec, _, build = request.param.partition("|")
+    monkeypatch.setenv("MDS_RDF_CELL_K", spec)
+    if build:
+        monkeypatch.setenv("MDS_RDF_CELL_BUILD", build)
+    k = [int(v) for v in spec.split(",")]
     return tuple(k * 3 if len(k) == 1 else k)
 
 
@@ -47,6 +57,15 @@ def run(pos, counts, box, cutoff, nbins, path, parity=True, layout=_cuda.LAYOUT_
             h.submit(arr, layout)
         out = h.counts()
         st = h.stats()
+    if st.path == _cuda.PATH_CELLLIST and st.frames:
+        # which build ran: one kernel for frame-major input whose (species, cell) table fits in
+        # shared memory (rdf_cells.cu BUILD_MAX_KEYS), else pack / scan / scatter
+        fits = len(counts) * int(np.prod(st.cells)) <= 48 * 1024
+        if os.environ.get("MDS_RDF_CELL_BUILD") == "split" or not fits:
+            assert st.cell_build == 0
+        elif layout == _cuda.LAYOUT_FRAME_MAJOR:
+            assert st.cell_build == 1
+        # (atom-major input takes the one-kernel build only where a block of it is one frame)
     return out, st
 
 
