@@ -976,17 +976,38 @@ static int submit_pinned(mds_rdf_t* h, const float* xyz, int64_t n_frames, int l
     }
     h->raw_bytes = need;
   }
+  const bool idle = cudaStreamQuery(h->s_compute) == cudaSuccess;
+  (void)cudaGetLastError();  // (cudaErrorNotReady is an answer, not a failure)
   CUDA_TRY(cudaEventRecord(h->ev_t0, h->s_compute));
   bool first_kernel = true;
-  // Ramp: the first host->device copy of a submit cannot overlap any compute, so the first two
-  // batches are small (1/16 and 1/4 of a full one) and the pipeline fills in a fraction of a
-  // full batch's copy time.
-  int64_t ramp = 0;
-  for (int64_t f0 = 0; f0 < n_frames;) {
-    int64_t cap = h->batch_frames;
-    if (n_frames > h->batch_frames && ramp < 2) cap = std::max<int64_t>(1, cap / (ramp == 0 ? 16 : 4));
-    ++ramp;
-    const int64_t nf = std::min<int64_t>(cap, n_frames - f0);
+  // Batch plan.  If the compute stream is idle the first host->device copy cannot overlap any
+  // compute, so the batches start small (1/16 of a full one) and grow no faster than the kernels
+  // of one batch can hide the copy of the next (cell path: x 1.5 — its compute time per frame is
+  // close to the copy time; all-pairs path: x 4).  If earlier work is still running (the caller
+  // streams a trajectory block by block) the copy of the first batch is hidden behind it and a
+  // ramp would only make the full-size copy that follows wait on a small batch's kernels.  The
+  // rest of the call is split into equal batches, for the same reason: a short last batch would
+  // expose most of the next call's first copy.
+  std::vector<int64_t> plan;
+  {
+    int64_t rem = n_frames;
+    if (idle && n_frames >= 8) {
+      const bool cells = h->path == MDS_RDF_PATH_CELLLIST;
+      for (int64_t cur = std::max<int64_t>(1, h->batch_frames / 16); rem > 0 && cur < h->batch_frames;
+           cur = cells ? cur + (cur + 1) / 2 : cur * 4) {
+        const int64_t nf = std::min(cur, rem);
+        plan.push_back(nf);
+        rem -= nf;
+      }
+    }
+    if (rem > 0) {
+      const int64_t nb = (rem + h->batch_frames - 1) / h->batch_frames;
+      const int64_t per = (rem + nb - 1) / nb;
+      for (; rem > 0; rem -= std::min(per, rem)) plan.push_back(std::min(per, rem));
+    }
+  }
+  int64_t f0 = 0;
+  for (const int64_t nf : plan) {
     const int b = h->buf;
     // the staging buffer must have been consumed by the pack kernel of two batches ago
     CUDA_TRY(cudaStreamWaitEvent(h->s_copy, h->ev_raw_free[b], 0));
