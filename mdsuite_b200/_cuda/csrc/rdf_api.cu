@@ -130,8 +130,15 @@ struct mds_rdf {
   int work_slot = 0;
   float* d_packed[2] = {nullptr, nullptr};   // quad-block positions, 12 B per slot
   uint32_t* d_rank[2] = {nullptr, nullptr};  // cell-list path: rank of each atom in its cell
-  bool build_fused = true;   // MDS_RDF_CELL_BUILD=split: always pack / scan / scatter
-  bool lazy_pack = true;     // MDS_RDF_CELL_BUILD=eager: the one-kernel build writes the quad blocks too
+  // Cell lists of a batch: the one-kernel build (a CTA per frame) for batches of at least one wave
+  // of its CTAs — below that its CTAs leave most SMs idle and pack / scan / scatter, which spread
+  // the atoms of all frames over the device, are faster.  MDS_RDF_CELL_BUILD (tuning / tests):
+  // "split" never, "fused" whenever the input is eligible, "eager" = "fused" + the quad-block copy
+  // of every frame written by the build instead of only for the frames the all-pairs kernel takes.
+  bool build_fused = true;
+  bool build_always = false;
+  bool lazy_pack = true;
+  int build_wave = 0;        // frames per wave of the one-kernel build (0: not eligible)
   int built_fused = 0;       // the last batch went through the one-kernel build
   uint32_t* d_flags[2] = {nullptr, nullptr};
   float* d_raw[2] = {nullptr, nullptr};  // staging for host submits (lazy)
@@ -440,10 +447,11 @@ int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t fram
   CUDA_TRY(cudaMemsetAsync(h->d_flags[buf], 0, sizeof(uint32_t) * (size_t)n_frames, h->s_compute));
   const mds::PackParams pp = pack_params(h, d_xyz, layout, frame0, n_frames, n_frames_total, buf);
   const bool one_kernel = h->build_fused &&
-                          mds::cells_build_fused(layout, h->n_species * h->grid.nc);
+                          mds::cells_build_fused(layout, h->n_species * h->grid.nc) &&
+                          (h->build_always || (h->build_wave > 0 && n_frames >= h->build_wave));
   const bool lazy_pack = one_kernel && h->lazy_pack;
   CUDA_TRY(mds::launch_cell_build(pp, h->n_species, h->d_sorted[buf], h->crowded_limit, h->d_scan_tmp,
-                                  h->sm_count, h->build_fused, !lazy_pack, h->s_compute));
+                                  h->sm_count, one_kernel, !lazy_pack, h->s_compute));
   CUDA_TRY(mds::launch_count_general(h->d_flags[buf], (int)n_frames, h->d_general,
                                      h->d_batch_far + buf, h->s_compute));
   h->built_fused = one_kernel ? 1 : 0;
@@ -706,6 +714,7 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
       }
       if (const char* env = getenv("MDS_RDF_CELL_BUILD")) {
         h->build_fused = strcmp(env, "split") != 0;
+        h->build_always = strcmp(env, "fused") == 0 || strcmp(env, "eager") == 0;
         h->lazy_pack = strcmp(env, "eager") != 0;
       }
       // one row cell (+ its kx own-pencil neighbours) against one neighbour pencil must fit
@@ -749,20 +758,19 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
     if (const char* env = getenv("MDS_RDF_DENSE")) h->dense = atoi(env) != 0;
   }
   h->variant = pick_variant(h);
+  if (cells && h->build_fused)
+    h->build_wave = mds::cells_build_frames_per_wave(MDS_LAYOUT_FRAME_MAJOR_XYZ,
+                                                     h->n_species * h->grid.nc, h->sm_count);
   int bf = cfg->max_frames_in_flight;
   if (bf <= 0) {
     const int64_t per_frame = h->frame_stride * (cells ? 12 + 4 + 16 : 12) + h->off_stride * 4;
     // 128 MB of internal buffers per batch; 512 MB on the cell path, whose pair kernel spreads
     // (frame, pencil) items over persistent CTAs and loses ~3 % to ramp and tail on short batches
     bf = (int)std::min<int64_t>(4096, std::max<int64_t>(1, ((cells ? 512LL : 128LL) << 20) / per_frame));
-    if (cells && h->build_fused) {
-      // the one-kernel build takes a frame per CTA: a batch is a whole number of its waves (1 GB of
-      // buffers at most), so that no SM is left with one more frame than the others
-      const int wave = mds::cells_build_frames_per_wave(MDS_LAYOUT_FRAME_MAJOR_XYZ,
-                                                        h->n_species * h->grid.nc, h->sm_count);
-      const int64_t most = std::min<int64_t>(4096, (1024LL << 20) / per_frame);
-      if (wave > 0 && most >= wave) bf = (int)(most / wave * wave);
-    }
+    // the one-kernel build takes a frame per CTA: a batch is a whole number of its waves (1 GB of
+    // buffers at most), so that no SM is left with one more frame than the others
+    const int64_t most = std::min<int64_t>(4096, (1024LL << 20) / per_frame);
+    if (h->build_wave > 0 && most >= h->build_wave) bf = (int)(most / h->build_wave * h->build_wave);
   }
   h->batch_frames = bf;
   build_items(h, mds::allpairs_variant_tile(h->variant), bf);

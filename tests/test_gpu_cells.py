@@ -19,16 +19,18 @@ from oracle import c_oracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["1", "2", "2,1,2", "4,1,1", "1|split", "2,1,2|split", "4,1,1|eager"],
+@pytest.fixture(params=["1|fused", "2|fused", "2,1,2|fused", "4,1,1|fused", "1|split", "2,1,2|split",
+                        "4,1,1|eager", "2"],
                 ids=["K1", "K2", "K212", "K411", "K1-split-build", "K212-split-build",
-                     "K411-eager-pack"])
+                     "K411-eager-pack", "K2-auto-build"])
 def cell_k(request, monkeypatch):
     """Stencil half-widths of the cell kernel (cells per cutoff length), forced through the
     library's tuning variable so that every case runs on the classical grid, on the half-width
-    grid and on a mixed one; "split-build": the lists come from pack / scan / scatter instead of
-    the one-kernel build (which frame-major input with a small key table gets by default);
-    "eager-pack": the one-kernel build also writes the all-pairs kernel's copy of every frame
-    (default: only flagged frames are packed, afterwards)."""
+    grid and on a mixed one.  The cell lists of these small cases are built by the one-kernel build
+    (forced: by default only batches of at least one wave of its CTAs take it); "split-build":
+    by pack / scan / scatter; "eager-pack": the one-kernel build also writes the all-pairs kernel's
+    copy of every frame (default: only flagged frames are packed, afterwards); "auto-build": the
+    library's own choice."""
     spec, _, build = request.param.partition("|")
     monkeypatch.setenv("MDS_RDF_CELL_K", spec)
     if build:
@@ -61,11 +63,13 @@ def run(pos, counts, box, cutoff, nbins, path, parity=True, layout=_cuda.LAYOUT_
         # which build ran: one kernel for frame-major input whose (species, cell) table fits in
         # shared memory (rdf_cells.cu BUILD_MAX_KEYS), else pack / scan / scatter
         fits = len(counts) * int(np.prod(st.cells)) <= 48 * 1024
-        if os.environ.get("MDS_RDF_CELL_BUILD") == "split" or not fits:
+        mode = os.environ.get("MDS_RDF_CELL_BUILD")
+        if mode == "split" or not fits:
             assert st.cell_build == 0
-        elif layout == _cuda.LAYOUT_FRAME_MAJOR:
+        elif mode in ("fused", "eager") and layout == _cuda.LAYOUT_FRAME_MAJOR:
             assert st.cell_build == 1
-        # (atom-major input takes the one-kernel build only where a block of it is one frame)
+        # (atom-major input takes the one-kernel build only where a block of it is one frame;
+        # without the variable the library decides by the size of the batch)
     return out, st
 
 
@@ -290,6 +294,24 @@ def test_cfg3_lj_100k_one_frame_vs_oracle_and_allpairs():
     want, _ = oracle(sysm.positions[:1], sysm.counts, sysm.box, 3.0, 300)
     one, _ = run(sysm.positions[:1], sysm.counts, sysm.box, 3.0, 300, "celllist")
     assert_same(one, want)
+
+
+@pytest.mark.parametrize("mode", ["fused", "eager"])
+def test_cfg3_lj_100k_one_kernel_build_equals_split_build(monkeypatch, mode):
+    """The two ways of building the cell lists at cfg3's size (12 288 keys, 8 atoms per cell): same
+    histograms, same candidate-pair count; one far-out atom sends its frame to the all-pairs kernel
+    through the copy that is packed afterwards (default) or by the build itself ("eager")."""
+    sysm = synthetic.lj_fluid(46, 3, seed=3)
+    pos = sysm.positions.copy()
+    pos[1, 17, 0] += 9.0 * sysm.box[0]  # frame 1: beyond 8 box lengths -> MDS_FRAME_FAR
+    monkeypatch.setenv("MDS_RDF_CELL_BUILD", "split")
+    want, st_split = run(pos, sysm.counts, sysm.box, 3.0, 300, "celllist")
+    monkeypatch.setenv("MDS_RDF_CELL_BUILD", mode)
+    got, st = run(pos, sysm.counts, sysm.box, 3.0, 300, "celllist")
+    assert st.cell_build == 1 and st_split.cell_build == 0
+    assert st.frames_far == 1 and st_split.frames_far == 1
+    assert st.pairs_evaluated == st_split.pairs_evaluated
+    assert_same(got, want)
 
 
 def test_cfg4_water_1m_atoms_cells_equals_allpairs():
