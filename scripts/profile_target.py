@@ -1,4 +1,5 @@
-"""Short single-GPU workloads for ncu captures: python scripts/profile_target.py allpairs|cells|cells4"""
+"""Short single-GPU workloads for ncu captures:
+python scripts/profile_target.py allpairs|cells|cellbuild|cells4"""
 import os
 import sys
 
@@ -15,6 +16,9 @@ if which == "allpairs":
 elif which == "cells":
     s = synthetic.lj_fluid(47, 4, seed=3, n_atoms=100_000)
     cutoff, nbins, frames, path = 3.0, 300, 64, "celllist"
+elif which == "cellbuild":  # two waves of the one-kernel build (-k regex:cell_build)
+    s = synthetic.lj_fluid(47, 4, seed=3, n_atoms=100_000)
+    cutoff, nbins, frames, path = 3.0, 300, 296, "celllist"
 else:
     s = synthetic.spc_water(69, 1, seed=4)
     cutoff, nbins, frames, path = 8.0, 800, 2, "celllist"
