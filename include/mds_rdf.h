@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MDS_RDF_ABI_VERSION 6
+#define MDS_RDF_ABI_VERSION 7
 
 #if defined(MDS_BUILD) && defined(__GNUC__)
 #define MDS_API __attribute__((visibility("default")))
@@ -182,6 +182,18 @@ MDS_API int mds_rdf_wait_host_copies(mds_rdf_t* h);
  * buffer k + 1. */
 MDS_API int64_t mds_rdf_host_ticket(mds_rdf_t* h);
 MDS_API int mds_rdf_wait_host_ticket(mds_rdf_t* h, int64_t ticket);
+
+/* How mds_rdf_submit cuts a call of n_frames host frames into batches (each batch: one
+ * host->device copy on the copy stream, overlapped with the kernels of the batch before it; the
+ * reference's counterpart is the np.array_split of calculators/radial_distribution_function.py:594
+ * into memory-sized batches).  batch_frames: the handle's full batch; compute_idle != 0: nothing is
+ * running on the handle when the call arrives, so the first copy cannot be hidden and the batches
+ * start at batch_frames / 16 and grow by x 1.5 (cell_path != 0) or x 4 until a full batch is
+ * reached; the rest of the call is split into equal batches of at most batch_frames.  Pure host
+ * arithmetic (no CUDA call, works without a GPU).  Writes up to `capacity` batch sizes to `out`
+ * and returns how many batches the plan has (negative: invalid argument). */
+MDS_API int64_t mds_rdf_plan_host_batches(int64_t n_frames, int32_t batch_frames, int compute_idle,
+                                          int cell_path, int64_t* out, int64_t capacity);
 
 /* Item sharding — strong scaling WITHIN frames, for runs with fewer configurations than GPUs
  * (SURVEY.md §8e "fallback for F < G"): every rank submits the same frames, the handle of rank

@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # (make -C csrc checked; see rdf_common.cuh MDS_CHECKED)
 LIB_PATH = os.environ.get("MDS_RDF_LIB") or os.path.join(_HERE, "libmds_rdf.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MDS_OK = 0
 PARITY_SKIP_FIRST = 0x1
 PATH_ALLPAIRS = 0x2
@@ -32,7 +32,7 @@ LAYOUT_ATOM_MAJOR = 1  # (n_atoms, n_frames, 3) — the reference's positions_te
 
 EXPORTED_SYMBOLS = (
     "mds_rdf_create", "mds_rdf_destroy", "mds_rdf_submit", "mds_rdf_submit_device",
-    "mds_rdf_counts", "mds_rdf_device_counts", "mds_rdf_allreduce", "mds_rdf_join", "mds_rdf_wait", "mds_rdf_wait_host_copies", "mds_rdf_host_ticket", "mds_rdf_wait_host_ticket", "mds_rdf_synchronize",
+    "mds_rdf_counts", "mds_rdf_device_counts", "mds_rdf_allreduce", "mds_rdf_join", "mds_rdf_wait", "mds_rdf_wait_host_copies", "mds_rdf_host_ticket", "mds_rdf_wait_host_ticket", "mds_rdf_plan_host_batches", "mds_rdf_synchronize",
     "mds_rdf_reset", "mds_rdf_set_item_shard",
     "mds_rdf_stats_get", "mds_rdf_threshold_table", "mds_rdf_build_threshold_table",
     "mds_bench_shared_atomics",
@@ -143,6 +143,9 @@ def load() -> ctypes.CDLL:
     lib.mds_rdf_wait_host_copies.argtypes = [vp]
     lib.mds_rdf_host_ticket.argtypes = [vp]
     lib.mds_rdf_host_ticket.restype = ctypes.c_int64
+    lib.mds_rdf_plan_host_batches.argtypes = [ctypes.c_int64, ctypes.c_int32, ctypes.c_int, ctypes.c_int,
+                                              ctypes.POINTER(ctypes.c_int64), ctypes.c_int64]
+    lib.mds_rdf_plan_host_batches.restype = ctypes.c_int64
     lib.mds_rdf_wait_host_ticket.argtypes = [vp, ctypes.c_int64]
     lib.mds_rdf_synchronize.argtypes = [vp]
     lib.mds_rdf_reset.argtypes = [vp]
@@ -419,6 +422,18 @@ def drop_parked_handles():
     for _key, h in list(_PARKED.values()):
         h.close()
     _PARKED.clear()
+
+
+def plan_host_batches(n_frames: int, batch_frames: int, compute_idle: bool, cell_path: bool):
+    """Batch sizes ``mds_rdf_submit`` cuts a call of ``n_frames`` host frames into (pure host
+    arithmetic of the library; no GPU needed)."""
+    lib = load()
+    n = lib.mds_rdf_plan_host_batches(n_frames, batch_frames, int(compute_idle), int(cell_path), None, 0)
+    if n < 0:
+        raise ValueError("mds_rdf_plan_host_batches: invalid argument")
+    out = (ctypes.c_int64 * max(1, n))()
+    lib.mds_rdf_plan_host_batches(n_frames, batch_frames, int(compute_idle), int(cell_path), out, n)
+    return [int(out[k]) for k in range(n)]
 
 
 def build_threshold_table(cutoff: float, nbins: int):

@@ -968,6 +968,43 @@ int mds_rdf_submit_device(mds_rdf_t* h, const float* d_xyz, int64_t n_frames, in
   return MDS_OK;
 }
 
+// Batch plan of a host submit.  If the compute stream is idle the first host->device copy cannot
+// overlap any compute, so the batches start small (1/16 of a full one) and grow no faster than
+// the kernels of one batch can hide the copy of the next (cell path: x 1.5 — its compute time per
+// frame is close to the copy time; all-pairs path: x 4).  If earlier work is still running (the
+// caller streams a trajectory block by block) the copy of the first batch is hidden behind it and
+// a ramp would only make the full-size copy that follows wait on a small batch's kernels.  The
+// rest of the call is split into equal batches, for the same reason: a short last batch would
+// expose most of the next call's first copy.
+static std::vector<int64_t> plan_host_batches(int64_t n_frames, int64_t batch_frames, bool idle,
+                                              bool cells) {
+  std::vector<int64_t> plan;
+  int64_t rem = n_frames;
+  if (idle && n_frames >= 8) {
+    for (int64_t cur = std::max<int64_t>(1, batch_frames / 16); rem > 0 && cur < batch_frames;
+         cur = cells ? cur + (cur + 1) / 2 : cur * 4) {
+      const int64_t nf = std::min(cur, rem);
+      plan.push_back(nf);
+      rem -= nf;
+    }
+  }
+  if (rem > 0) {
+    const int64_t nb = (rem + batch_frames - 1) / batch_frames;
+    const int64_t per = (rem + nb - 1) / nb;
+    for (; rem > 0; rem -= std::min(per, rem)) plan.push_back(std::min(per, rem));
+  }
+  return plan;
+}
+
+int64_t mds_rdf_plan_host_batches(int64_t n_frames, int32_t batch_frames, int compute_idle,
+                                  int cell_path, int64_t* out, int64_t capacity) {
+  if (n_frames < 0 || batch_frames < 1 || capacity < 0 || (capacity > 0 && !out)) return -1;
+  const std::vector<int64_t> plan =
+      plan_host_batches(n_frames, batch_frames, compute_idle != 0, cell_path != 0);
+  for (int64_t k = 0; k < (int64_t)plan.size() && k < capacity; ++k) out[k] = plan[k];
+  return (int64_t)plan.size();
+}
+
 // Host frames in page-locked memory: H2D on the side stream in batches, double buffered against
 // the kernels.
 static int submit_pinned(mds_rdf_t* h, const float* xyz, int64_t n_frames, int layout) {
@@ -988,32 +1025,9 @@ static int submit_pinned(mds_rdf_t* h, const float* xyz, int64_t n_frames, int l
   (void)cudaGetLastError();  // (cudaErrorNotReady is an answer, not a failure)
   CUDA_TRY(cudaEventRecord(h->ev_t0, h->s_compute));
   bool first_kernel = true;
-  // Batch plan.  If the compute stream is idle the first host->device copy cannot overlap any
-  // compute, so the batches start small (1/16 of a full one) and grow no faster than the kernels
-  // of one batch can hide the copy of the next (cell path: x 1.5 — its compute time per frame is
-  // close to the copy time; all-pairs path: x 4).  If earlier work is still running (the caller
-  // streams a trajectory block by block) the copy of the first batch is hidden behind it and a
-  // ramp would only make the full-size copy that follows wait on a small batch's kernels.  The
-  // rest of the call is split into equal batches, for the same reason: a short last batch would
-  // expose most of the next call's first copy.
-  std::vector<int64_t> plan;
-  {
-    int64_t rem = n_frames;
-    if (idle && n_frames >= 8) {
-      const bool cells = h->path == MDS_RDF_PATH_CELLLIST;
-      for (int64_t cur = std::max<int64_t>(1, h->batch_frames / 16); rem > 0 && cur < h->batch_frames;
-           cur = cells ? cur + (cur + 1) / 2 : cur * 4) {
-        const int64_t nf = std::min(cur, rem);
-        plan.push_back(nf);
-        rem -= nf;
-      }
-    }
-    if (rem > 0) {
-      const int64_t nb = (rem + h->batch_frames - 1) / h->batch_frames;
-      const int64_t per = (rem + nb - 1) / nb;
-      for (; rem > 0; rem -= std::min(per, rem)) plan.push_back(std::min(per, rem));
-    }
-  }
+  // batch plan (plan_host_batches above): ramp only if nothing is running, equal batches after it
+  const std::vector<int64_t> plan =
+      plan_host_batches(n_frames, h->batch_frames, idle, h->path == MDS_RDF_PATH_CELLLIST);
   int64_t f0 = 0;
   for (const int64_t nf : plan) {
     const int b = h->buf;

@@ -85,3 +85,34 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "from oracle" not in text and "import oracle" not in text, f
                 assert "librdf_oracle" not in text, f
+
+
+@pytest.mark.parametrize("cell_path", [False, True])
+def test_host_submit_batch_plan(cell_path):
+    """mds_rdf_plan_host_batches (include/mds_rdf.h): how a host submit is cut into copy/compute
+    batches.  Every frame exactly once, no batch above the handle's size; a ramp only when the
+    handle is idle, growing no faster than x 1.5 (cell path) / x 4; equal batches otherwise, so that
+    no short batch's kernels have to hide a full-size copy."""
+    for bf in (1, 3, 16, 164, 296):
+        for n in (0, 1, 7, 8, 100, bf, bf + 1, 1200, 10_000):
+            busy = _cuda.plan_host_batches(n, bf, False, cell_path)
+            assert sum(busy) == n and all(1 <= b <= bf for b in busy)
+            assert len(busy) == -(-n // bf)                      # as few batches as possible ...
+            assert all(b == busy[0] for b in busy[:-1])            # ... all equal but the last,
+            assert not busy or busy[0] - len(busy) < busy[-1] <= busy[0]  # short by rounding only
+            idle = _cuda.plan_host_batches(n, bf, True, cell_path)
+            assert sum(idle) == n and all(1 <= b <= bf for b in idle)
+            if n < 8 or bf < 2:
+                assert idle == busy
+                continue
+            assert idle[0] == min(n, max(1, bf // 16))           # the exposed first copy is small
+            growth = 1.5 if cell_path else 4.0
+            full = [k for k, b in enumerate(idle) if b * growth >= bf] or [len(idle)]
+            for a, b in zip(idle[:full[0]], idle[1:full[0] + 1]):
+                assert b <= np.ceil(a * growth) + 1 or b <= -(-n // max(1, len(idle)))
+    # the schedule quoted in DESIGN.md §7 for cfg3 (296-frame batches, 1,250 frames of a rank)
+    assert _cuda.plan_host_batches(1250, 296, True, True) == [18, 27, 41, 62, 93, 140, 210, 220, 220, 219]
+    assert _cuda.plan_host_batches(1200, 296, False, True) == [240] * 5
+    assert _cuda.plan_host_batches(1000, 48, True, False)[:3] == [3, 12, 47]
+    with pytest.raises(ValueError):
+        _cuda.plan_host_batches(10, 0, True, True)
