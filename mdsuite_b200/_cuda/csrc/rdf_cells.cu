@@ -12,12 +12,16 @@
 // derives the margin).  Frames with coordinates further out are flagged by the pack kernel and
 // handed to the all-pairs kernel instead.
 //
-// Per batch of frames:
+// Per batch of frames, either
+//   rdf_cell_build_kernel  a CTA per frame does the whole build (counts in shared memory, scan,
+//                          placement); see "the whole build of a frame in one CTA" below
+// or (atom-major input, key tables beyond shared memory, batches shorter than a wave of CTAs)
 //   rdf_pack_kernel        (rdf_pack.cu) raw xyz -> quad-block positions; per-(frame, species,
 //                          cell) counts and ranks with one global atomic per atom; frame flags
 //   rdf_cell_scan_kernel   exclusive scan of the counts of a frame -> cell offsets (one CTA/frame);
 //                          flags frames with an absurdly crowded cell for the all-pairs kernel
 //   rdf_cell_scatter_kernel counting-sort scatter -> atoms ordered by (species, cell), x fastest
+// and then
 //   rdf_cells_kernel       persistent CTAs; one work item = (frame, species pair, pencil of cells
 //                          along x).  See "the pair kernel" below.
 #include "rdf_common.cuh"

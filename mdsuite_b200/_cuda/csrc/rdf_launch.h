@@ -99,8 +99,9 @@ size_t cells_smem_bytes(int nbins, int pair_cnt, bool hist_in_smem, int cap_atom
 int cells_max_seg();   // longest segment (x cells) the kernel's tables can hold
 int cells_max_cap();   // largest cap_atoms the kernel's tables can hold
 int cells_max_entries();  // (x cell, neighbour pencil) entries of a staged segment, at most
-// pp must have cell_off / rank / grid set: pack + count, scan, scatter into `sorted`; frames with
-// a cell of more than crowded_limit atoms are flagged MDS_FRAME_FAR
+// pp must have cell_off / rank / grid set: cell offsets into pp.cell_off, atoms ordered by
+// (species, cell) into `sorted`; frames with a cell of more than crowded_limit atoms are flagged
+// MDS_FRAME_FAR
 // scan_tmp: cells_scan_tmp_words(frames per batch, keys) zeroed uint32 words (nullptr: one CTA
 // scans a frame's keys on its own)
 size_t cells_scan_tmp_words(int n_frames, int n_keys);
