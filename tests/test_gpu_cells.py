@@ -296,6 +296,25 @@ def test_cfg3_lj_100k_one_frame_vs_oracle_and_allpairs():
     assert_same(one, want)
 
 
+def test_long_batches_take_the_one_kernel_build_with_several_frames_per_cta():
+    """The library's own choice: a batch of at least one wave of build CTAs (one per SM) goes through
+    the one-kernel build, each CTA taking one frame after another (its shared-memory table is
+    cleared in between); shorter batches through pack / scan / scatter.  Same counts either way."""
+    sysm = synthetic.lj_fluid(12, 7, seed=36)  # 1728 atoms
+    want, _ = oracle(sysm.positions, sysm.counts, sysm.box, 2.5, 125)
+    reps = 60                                   # 420 frames: one batch, ~3 frames per CTA
+    pos = np.tile(sysm.positions, (reps, 1, 1))
+    pos[211, 5, 1] -= 8.5 * sysm.box[1]         # one far-out frame in the middle (frame 211 = base 1)
+    far, _ = oracle(pos[211:212], sysm.counts, sysm.box, 2.5, 125)
+    near, _ = oracle(sysm.positions[1:2], sysm.counts, sysm.box, 2.5, 125)
+    got, st = run(pos, sysm.counts, sysm.box, 2.5, 125, "celllist", device_input=True)
+    assert st.cell_build == 1 and st.frames_far == 1
+    assert_same(got, want * reps - near + far)
+    short, st = run(pos[:70], sysm.counts, sysm.box, 2.5, 125, "celllist", device_input=True)
+    assert st.cell_build == 0
+    assert_same(short, want * 10)
+
+
 @pytest.mark.parametrize("mode", ["fused", "eager"])
 def test_cfg3_lj_100k_one_kernel_build_equals_split_build(monkeypatch, mode):
     """The two ways of building the cell lists at cfg3's size (12 288 keys, 8 atoms per cell): same

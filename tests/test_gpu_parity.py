@@ -278,10 +278,14 @@ def test_committed_golden_vectors(case):
     assert_same(got, np.array(case["counts_corrected"], dtype=np.uint64))
 
 
-@pytest.mark.parametrize("path", ["allpairs", "celllist"])
-def test_item_shards_add_up_to_the_full_histogram(path):
+@pytest.mark.parametrize("path", ["allpairs", "celllist", "celllist-one-kernel-build"])
+def test_item_shards_add_up_to_the_full_histogram(path, monkeypatch):
     """mds_rdf_set_item_shard: strong scaling inside frames (fewer frames than GPUs).  The shards
-    of one frame, summed, equal the unsharded histogram and the oracle's; so do their pair counts."""
+    of one frame, summed, equal the unsharded histogram and the oracle's; so do their pair counts.
+    (Third case: the slab of z layers of a shard as the one-kernel build of the cell lists cuts it.)"""
+    if path.endswith("one-kernel-build"):
+        monkeypatch.setenv("MDS_RDF_CELL_BUILD", "fused")
+        path = "celllist"
     sysm = synthetic.lj_fluid(14, 2, seed=41) if path == "celllist" else synthetic.nacl_melt(6, 2, seed=41)
     cutoff, nbins = (2.9, 145) if path == "celllist" else (9.0, 300)
     want, ev = oracle_counts(sysm.positions, sysm.counts, sysm.box, cutoff, nbins)
