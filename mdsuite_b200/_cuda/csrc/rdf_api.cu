@@ -115,6 +115,8 @@ struct mds_rdf {
   int kcell[3] = {0, 0, 0};       // stencil half-widths of the cell path (cells per cutoff)
   int cap_atoms = 0;              // positions a CTA of the cell kernel stages in shared memory
   int cell_segments = 1;          // work items per pencil (x segments), see CellsParams.n_seg
+  std::vector<int> pair_pieces;   // the same per species pair (launches with one pair use their own)
+  int cell_pair_group = 1;        // species pairs per launch of the cell pair kernel
   uint32_t crowded_limit = 0;     // atoms per cell above which a frame goes to the all-pairs kernel
   int64_t off_stride = 0;         // uint32 entries per frame of the cell-offset table
   uint32_t flush_threshold = 1u << 30;
@@ -468,8 +470,8 @@ int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t fram
     h->launches += 1;
   }
   if (h->n_real == 0) return MDS_OK;
-  for (int p0 = 0; p0 < h->n_pairs; p0 += h->pair_group) {
-    const int pc = std::min(h->pair_group, h->n_pairs - p0);
+  for (int p0 = 0; p0 < h->n_pairs; p0 += h->cell_pair_group) {
+    const int pc = std::min(h->cell_pair_group, h->n_pairs - p0);
     mds::CellsParams cp;
     cp.spos = h->d_sorted[buf];
     cp.frame_stride = h->frame_stride;
@@ -496,7 +498,7 @@ int process_batch_cells(mds_rdf* h, const float* d_xyz, int layout, int64_t fram
     // if there are enough layers; else every count-th item
     cp.pen_lo = 0;
     cp.n_pen = h->grid.ny * h->grid.nz;
-    cp.n_seg = h->cell_segments;
+    cp.n_seg = (pc == 1) ? h->pair_pieces[p0] : h->cell_segments;
     cp.shard_index = h->shard_index;
     cp.shard_count = h->shard_count;
     if (h->shard_count > 1 && (uint32_t)h->grid.nz >= h->shard_count) {
@@ -738,9 +740,13 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
   h->hist_in_smem = true;
   h->pair_group = h->n_pairs;
   while (h->pair_group > 1 && smem_need(h->pair_group) > target) --h->pair_group;
+  bool group_forced = false;
   if (const char* env = getenv("MDS_RDF_PAIR_GROUP")) {  // tuning aid
     const int v = atoi(env);
-    if (v >= 1 && v <= h->n_pairs && smem_need(v) <= smem_cap) h->pair_group = v;
+    if (v >= 1 && v <= h->n_pairs && smem_need(v) <= smem_cap) {
+      h->pair_group = v;
+      group_forced = true;
+    }
   }
   if (smem_need(h->pair_group) > target) {
     // a single pair does not fit the 2-CTA budget: allow the full opt-in size, then give up on smem
@@ -749,6 +755,12 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
       h->pair_group = h->n_pairs;
     }
   }
+  // The cell pair kernel takes ONE species pair per launch when there are few of them: its table
+  // and histogram then share one interleaved array (rdf_cells.cu), a CTA needs less shared memory
+  // (cfg4, 800 bins x 3 pairs: 4 resident CTAs per SM instead of 3) and a launch has the work items
+  // of its own segment length only — 10 % on cfg4.  With many pairs the launches would get too
+  // short; those keep the grouping of the all-pairs kernel.
+  h->cell_pair_group = (h->hist_in_smem && h->n_pairs <= 6 && !group_forced) ? 1 : h->pair_group;
 
   {
     // expected fraction of pairs inside the cutoff sphere (ideal gas): 4/3 pi rc^3 / V
@@ -841,6 +853,7 @@ int mds_rdf_create(mds_rdf_t** out, const mds_rdf_config* cfg) {
         const int pieces = (h->grid.nx + seg - 1) / seg;  // even pieces
         seg = (h->grid.nx + pieces - 1) / pieces;
         ab.push_back(make_int4(row, col, seg, 0));
+        h->pair_pieces.push_back(pieces);
         h->cell_segments = std::max(h->cell_segments, pieces);
       }
     CREATE_TRY(cudaMalloc(&h->d_pair_ab, ab.size() * sizeof(int4)));

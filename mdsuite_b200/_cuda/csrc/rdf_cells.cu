@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(BUILD_THREADS, MDS_BUILD_MINB) rdf_cell_build_
 // capacity before staging it, so no density distribution can overflow the buffers.
 
 #ifndef CELL_UNROLL
-#define CELL_UNROLL 4  // row pairs per pass of the inner loop (measured: 4 beats 2 by 3-4 %)
+#define CELL_UNROLL 8  // row pairs per pass of the inner loop (measured on cfg3: 4 beats 2 by 3-4 %, 8 beats 4 by 1.4 %, 6 = 4)
 #endif
 #ifndef CELL_MINB
 #define CELL_MINB 4    // resident CTAs per SM the register budget is set for
@@ -457,7 +457,10 @@ struct BinConsts {
 // address give the register pairs of the packed FADD2 / FMUL2 sequence, two rows per pass.
 // MASK: the column only counts against rows [lo, lo + len) of the 2 n2 (same-species chunks of the
 // own pencil: rows before the column itself; chunks whose rows could alias a periodic image).
-template <bool FAST, bool MASK, bool HIST_SMEM>
+// INTER: the CTA's threshold table and histogram are one interleaved array (rdf_common.cuh,
+// bin_count_dense_interleaved; launches with one species pair), k.c_edge / k.four then hold the
+// slot constants.
+template <bool FAST, bool MASK, bool HIST_SMEM, bool INTER>
 __device__ __forceinline__ void rows_vs_column(const float* __restrict__ rx,
                                                const float* __restrict__ ry,
                                                const float* __restrict__ rz, int n2, float4 c, int lo,
@@ -489,7 +492,10 @@ __device__ __forceinline__ void rows_vs_column(const float* __restrict__ rx,
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      if (HIST_SMEM) {
+      if (HIST_SMEM && INTER) {
+        bin_count_dense_interleaved(s[q], k.s_cut, k.inv_step, k.c_edge, k.four);
+        MDS_CHK(issued += 1;)
+      } else if (HIST_SMEM) {
         bin_count_dense<false, false>(s[q], k.s_cut, k.inv_step, 0.f, k.c_edge, k.c_hist, k.four, 0,
                                       0, hi);
         MDS_CHK(issued += 1;)
@@ -540,7 +546,8 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 // Move what has accumulated in the CTA's shared histogram to the global counts while other warps
 // keep counting: atomicExch takes each bin's value and zeroes it in one step, so nothing is lost.
-__device__ __forceinline__ void flush_hist_warp(uint32_t* s_hist, const CellsParams& p, int lane,
+// hs: words between consecutive bins (2 for the interleaved table, where pair_cnt is 1)
+__device__ __forceinline__ void flush_hist_warp(uint32_t* s_hist, int hs, const CellsParams& p, int lane,
                                                 unsigned long long* s_chk = nullptr) {
   (void)s_chk;
   const int stride = p.nbins + 1;
@@ -548,14 +555,14 @@ __device__ __forceinline__ void flush_hist_warp(uint32_t* s_hist, const CellsPar
     unsigned long long* g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
     uint32_t* h = s_hist + pr * stride;
     for (int k = lane; k < p.nbins; k += 32) {
-      const uint32_t v = atomicExch(h + k, 0u);
+      const uint32_t v = atomicExch(h + k * hs, 0u);
       if (v) {
         atomicAdd(g + k, (unsigned long long)v);
         MDS_CHK(atomicAdd(&s_chk[1], (unsigned long long)v);)
       }
     }
     if (lane == 0) {  // the sink may wrap; nobody reads it
-      const uint32_t v = atomicExch(h + p.nbins, 0u);
+      const uint32_t v = atomicExch(h + p.nbins * hs, 0u);
       (void)v;
       MDS_CHK(atomicAdd(&s_chk[1], (unsigned long long)v);)
     }
@@ -575,7 +582,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-template <bool HIST_SMEM>
+template <bool HIST_SMEM, bool INTER>
 __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) rdf_cells_kernel(const CellsParams p) {
   // fixed-size tables first (constant offsets), then the staged atoms, then table + histograms
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -591,7 +598,10 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) rdf_cells_kernel(cons
   float4* S = reinterpret_cast<float4*>(RZ + ROWS_CAP);  // [cap] the rows' pencil, then the slabs
   float* s_edges = reinterpret_cast<float*>(S + p.cap_atoms);
   const int n_edges = p.nbins + 2;
-  uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_edges + ((n_edges + 3) & ~3));
+  // INTER (pair_cnt == 1): the same bytes hold nbins + 1 slots {edges[k + 1], hist[k]}
+  uint32_t* s_hist = INTER ? reinterpret_cast<uint32_t*>(s_edges) + 1
+                           : reinterpret_cast<uint32_t*>(s_edges + ((n_edges + 3) & ~3));
+  constexpr int hs = INTER ? 2 : 1;  // words between consecutive bins
   const int hist_stride = p.nbins + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned long long issued = 0;  // only counted in checked builds
@@ -623,17 +633,22 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) rdf_cells_kernel(cons
     s_misc[M_SEG] = (uint32_t)seg;
   };
 
-  if (HIST_SMEM) {
+  if (HIST_SMEM && INTER) {
+    for (int k = tid; k < hist_stride; k += CELL_THREADS) {
+      s_edges[2 * k] = p.edges[k + 1];
+      s_hist[2 * k] = 0u;
+    }
+  } else if (HIST_SMEM) {
     for (int k = tid; k < n_edges; k += CELL_THREADS) s_edges[k] = p.edges[k];
     for (int k = tid; k < p.pair_cnt * hist_stride; k += CELL_THREADS) s_hist[k] = 0u;
   }
   if (tid == 0) {
     s_misc[M_EVALS] = 0u;
     // address constants of the binning sequence, made opaque to ptxas (see rdf_allpairs.cu)
-    s_misc[M_CEDGE] = smem_u32(s_edges + 1) - kMagic4;
+    s_misc[M_CEDGE] = INTER ? smem_u32(s_edges) - kMagic8 : smem_u32(s_edges + 1) - kMagic4;
     s_misc[M_HIST0] = smem_u32(s_hist) - kMagic4;
-    s_misc[M_FOUR] = 4u;
-    s_misc[M_FOUR + 1] = 4u;
+    s_misc[M_FOUR] = INTER ? 8u : 4u;
+    s_misc[M_FOUR + 1] = INTER ? 8u : 4u;
     fetch_item();
   }
   __syncthreads();
@@ -855,7 +870,7 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) rdf_cells_kernel(cons
         float4 c = nan4;  // slots past the end hold NaN atoms (never inside the cutoff)
         if (q < lim) c = lds128(s_addr + ((uint32_t)((own ? 0 : n_r) + q) << 4));
         if (!masked && fast) {
-          rows_vs_column<true, false, HIST_SMEM>(RX + rb, RY + rb, RZ + rb, n2, c, 0, 0u, bc, issued);
+          rows_vs_column<true, false, HIST_SMEM, INTER>(RX + rb, RY + rb, RZ + rb, n2, c, 0, 0u, bc, issued);
         } else {
           // rows [lo, lo + len) of this chunk's row range are the ones column q may pair with
           int lo = 0;
@@ -871,9 +886,9 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) rdf_cells_kernel(cons
               len = (uint32_t)max(0, ro[min(Sx, cell + 1)] - rb - lo);
             }
           }
-          if (fast) rows_vs_column<true, true, HIST_SMEM>(RX + rb, RY + rb, RZ + rb, n2, c, lo, len, bc,
+          if (fast) rows_vs_column<true, true, HIST_SMEM, INTER>(RX + rb, RY + rb, RZ + rb, n2, c, lo, len, bc,
                                                          issued);
-          else rows_vs_column<false, true, HIST_SMEM>(RX + rb, RY + rb, RZ + rb, n2, c, lo, len, bc,
+          else rows_vs_column<false, true, HIST_SMEM, INTER>(RX + rb, RY + rb, RZ + rb, n2, c, lo, len, bc,
                                                       issued);
         }
         tested += (uint32_t)n2 * 64u;
@@ -886,7 +901,7 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) rdf_cells_kernel(cons
             // the warp whose contribution crosses the threshold empties the histogram
             if (old < p.flush_threshold && old + unpublished >= p.flush_threshold) {
               if (lane == 0) atomicSub(s_misc + M_EVALS, p.flush_threshold);
-              flush_hist_warp(s_hist, p, lane MDS_CHK(, s_chk));
+              flush_hist_warp(s_hist, hs, p, lane MDS_CHK(, s_chk));
             }
             unpublished = 0;
           }
@@ -905,13 +920,13 @@ __global__ void __launch_bounds__(CELL_THREADS, CELL_MINB) rdf_cells_kernel(cons
   if (HIST_SMEM) {
     __syncthreads();
     MDS_CHK(checked_conservation(s_chk, issued, s_hist, p.pair_cnt * hist_stride, tid, CELL_THREADS,
-                                 "rdf_cells_kernel");)
+                                 "rdf_cells_kernel", hs);)
     const int stride = p.nbins + 1;
     for (int pr = 0; pr < p.pair_cnt; ++pr) {
       unsigned long long* g = p.counts + (long long)(p.pair_lo + pr) * p.nbins;
       const uint32_t* h = s_hist + pr * stride;
       for (int k = tid; k < p.nbins; k += CELL_THREADS) {
-        const uint32_t v = h[k];
+        const uint32_t v = h[k * hs];
         if (v) atomicAdd(g + k, (unsigned long long)v);
       }
     }
@@ -1007,7 +1022,10 @@ cudaError_t launch_cell_build(const PackParams& pp, int n_species, float4* sorte
 
 cudaError_t launch_cells(const CellsParams& p, int sm_count, cudaStream_t stream, int* grid_out) {
   const size_t smem = cells_smem_bytes(p.nbins, p.pair_cnt, p.hist_in_smem != 0, p.cap_atoms);
-  auto kern = p.hist_in_smem ? rdf_cells_kernel<true> : rdf_cells_kernel<false>;
+  // one species pair per launch: threshold table and histogram interleaved (one address per pair)
+  auto kern = !p.hist_in_smem ? rdf_cells_kernel<false, false>
+              : (p.pair_cnt == 1 && !getenv("MDS_RDF_CELL_TWO_TABLES")) ? rdf_cells_kernel<true, true>
+                                                                        : rdf_cells_kernel<true, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;

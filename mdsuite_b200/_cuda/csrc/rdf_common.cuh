@@ -27,10 +27,11 @@ namespace mds {
 __device__ __forceinline__ void checked_conservation(unsigned long long* s_chk,
                                                      unsigned long long issued,
                                                      const uint32_t* s_hist, int n_slots, int tid,
-                                                     int n_threads, const char* kernel) {
+                                                     int n_threads, const char* kernel,
+                                                     int slot_stride = 1) {
   if (issued) atomicAdd(&s_chk[0], issued);
   unsigned long long part = 0;
-  for (int k = tid; k < n_slots; k += n_threads) part += s_hist[k];
+  for (int k = tid; k < n_slots; k += n_threads) part += s_hist[k * slot_stride];
   if (part) atomicAdd(&s_chk[1], part);
   __syncthreads();
   if (tid == 0 && s_chk[0] != s_chk[1]) {
@@ -249,6 +250,7 @@ __device__ __forceinline__ float sqrt_approx(float s) {
 // below it; a single compare against edges[k~ + 1] settles it.
 constexpr float kBinGuessBias = 1.0f - 9.5367431640625e-07f;  // 1 - 2^-20
 constexpr uint32_t kMagic4 = 0x4B000000u * 4u;                 // 4 * bits(2^23), mod 2^32
+constexpr uint32_t kMagic8 = 0x4B000000u * 8u;                 // 8 * bits(2^23), mod 2^32
 
 // Generic-pointer version for s < s_cut (global-memory histogram fallback).
 __device__ __forceinline__ int bin_of_s(float s, float inv_step_biased,
@@ -345,6 +347,32 @@ __device__ __forceinline__ void bin_count_dense(float s, float s_cut, float inv_
         "f"(inv_lo), "r"(c_edge), "r"(c_hist), "r"(four)
         : "memory");
   }
+}
+
+// Interleaved table (cell kernel, one species pair per launch): slot k of an 8-byte array holds
+// edges[k + 1] and, four bytes on, hist[k], so ONE address serves the threshold load and the atomic
+// (the increment of the bin becomes "+ 8" and the histogram word is reached through the immediate
+// offset of the atomic): one IMAD per pair less than with two arrays.  c_slot = smem address of
+// slot 0 minus kMagic8, eight = the constant 8 in a register ptxas cannot see through.
+__device__ __forceinline__ void bin_count_dense_interleaved(float s, float s_cut, float inv_lo,
+                                                            uint32_t c_slot, uint32_t eight) {
+  const float t = fminf(s, s_cut);  // min.f32 returns the non-NaN operand
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      ".reg .f32 d, f, hi;\n"
+      ".reg .u32 a, e;\n"
+      "sqrt.approx.ftz.f32 d, %0;\n"
+      "fma.rz.f32 f, d, %1, 0f4B000000;\n"
+      "mov.b32 a, f;\n"
+      "mad.lo.u32 e, a, %3, %2;\n"
+      "ld.shared.f32 hi, [e];\n"
+      "setp.ge.f32 q, %0, hi;\n"
+      "@q add.u32 e, e, 8;\n"
+      "red.shared.add.u32 [e+4], 1;\n"
+      "}\n" ::"f"(t),
+      "f"(inv_lo), "r"(c_slot), "r"(eight)
+      : "memory");
 }
 
 // Sparse path: the unconditional sequence for a pair already known to be inside the cutoff (under

@@ -142,6 +142,23 @@ def test_lj_4096_vs_oracle(parity, cell_k):
     assert st.frames_general_minimage == 0 and st.frames_far == 0
 
 
+def test_single_pair_launches_with_separate_tables_vs_oracle(monkeypatch):
+    """A launch with one species pair keeps threshold table and histogram interleaved in one
+    shared-memory array (one address per pair in the binning sequence); MDS_RDF_CELL_TWO_TABLES
+    switches such launches back to the two arrays multi-pair launches use.  Same counts."""
+    sysm = synthetic.lj_fluid(16, 3, seed=32)
+    want, _ = oracle(sysm.positions, sysm.counts, sysm.box, 2.5, 250)
+    inter, _ = run(sysm.positions, sysm.counts, sysm.box, 2.5, 250, "celllist")
+    monkeypatch.setenv("MDS_RDF_CELL_TWO_TABLES", "1")
+    monkeypatch.setenv("MDS_RDF_FLUSH_THRESHOLD", "8192")
+    two, _ = run(sysm.positions, sysm.counts, sysm.box, 2.5, 250, "celllist")
+    monkeypatch.delenv("MDS_RDF_CELL_TWO_TABLES")
+    flushed, _ = run(sysm.positions, sysm.counts, sysm.box, 2.5, 250, "celllist")  # interleaved + flushes
+    assert_same(inter, want)
+    assert_same(two, want)
+    assert_same(flushed, want)
+
+
 def test_water_three_pairs_vs_oracle(cell_k):
     sysm = synthetic.spc_water(12, 2, seed=4)  # 5184 atoms, L = 37.26, cutoff 8 -> 4 / 9 cells
     got, st = run(sysm.positions, sysm.counts, sysm.box, 8.0, 800, "celllist")
