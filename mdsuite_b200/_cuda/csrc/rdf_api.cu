@@ -1039,8 +1039,11 @@ static int submit_pinned(mds_rdf_t* h, const float* xyz, int64_t n_frames, int l
   CUDA_TRY(cudaEventRecord(h->ev_t0, h->s_compute));
   bool first_kernel = true;
   // batch plan (plan_host_batches above): ramp only if nothing is running, equal batches after it
+  // (an atom-major block that fits one batch stays whole: it travels as ONE plain copy, while
+  // pieces of it would need strided copies with rows of a few hundred bytes)
+  const bool ramp = idle && (layout == MDS_LAYOUT_FRAME_MAJOR_XYZ || n_frames > h->batch_frames);
   const std::vector<int64_t> plan =
-      plan_host_batches(n_frames, h->batch_frames, idle, h->path == MDS_RDF_PATH_CELLLIST);
+      plan_host_batches(n_frames, h->batch_frames, ramp, h->path == MDS_RDF_PATH_CELLLIST);
   int64_t f0 = 0;
   for (const int64_t nf : plan) {
     const int b = h->buf;
